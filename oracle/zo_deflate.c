@@ -864,8 +864,9 @@ static void insert_match(dstate *s, match_t m) /* :210-262 */
         m.strstart++;
         m.match_length--;
         if (m.match_length > 0 && m.strstart >= m.orgstart) {
-            if ((unsigned)m.strstart + m.match_length > m.orgstart) insert_string(s, m.strstart, m.match_length);
-            else insert_string(s, m.strstart, (size_t)(m.orgstart - m.strstart + 1));
+            /* u16 arithmetic as in the reference (wraps in release builds when match_length was 0) */
+            if ((uint16_t)(m.strstart + m.match_length) > m.orgstart) insert_string(s, m.strstart, m.match_length);
+            else insert_string(s, m.strstart, (size_t)(uint16_t)(m.orgstart - m.strstart + 1));
         }
         return;
     }
@@ -873,8 +874,9 @@ static void insert_match(dstate *s, match_t m) /* :210-262 */
         m.match_length--;
         m.strstart++;
         if (m.strstart >= m.orgstart) {
-            if ((unsigned)m.strstart + m.match_length > m.orgstart) insert_string(s, m.strstart, m.match_length);
-            else insert_string(s, m.strstart, (size_t)(m.orgstart - m.strstart + 1));
+            /* u16 arithmetic as in the reference (wraps in release builds when match_length was 0) */
+            if ((uint16_t)(m.strstart + m.match_length) > m.orgstart) insert_string(s, m.strstart, m.match_length);
+            else insert_string(s, m.strstart, (size_t)(uint16_t)(m.orgstart - m.strstart + 1));
         } else if ((unsigned)m.orgstart < (unsigned)m.strstart + m.match_length) {
             insert_string(s, m.orgstart, (size_t)(m.strstart + m.match_length - m.orgstart));
         }

@@ -1,0 +1,148 @@
+// hostmodel.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles zlib_rs_b200/csrc/zb_core.h (the device functions of the CUDA engine) for the host and
+// drives them in the same phase order as the kernels, so the parallel algorithm can be checked against
+// the oracle on a machine without a GPU.  Never linked into the shipped library.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../zlib_rs_b200/csrc/zb_core.h"
+extern "C" {
+#include "../../oracle/zoracle.h"
+}
+using namespace zb;
+
+struct HostAcc {
+    const uint8_t *data; uint32_t N; const uint16_t *L; const uint32_t *holes; const uint32_t *M;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 65536) return 0; y -= 32768; }
+        return data[y];
+    }
+    uint32_t link(uint32_t y) const { return y + 4 <= N ? L[y] : 0; }
+    bool inserted(uint32_t y) const { return !((holes[y >> 5] >> (y & 31)) & 1u); }
+    Match mlook(uint32_t x) const { uint32_t v = M[x]; return Match{v >> 16, x - (v & 0xffff)}; }
+};
+
+static void build_links(const uint8_t *d, uint32_t N, std::vector<uint16_t> &L)
+{
+    L.assign(N + 8, 0);
+    std::vector<int64_t> head(65536, -1);
+    for (uint32_t x = 0; x + 4 <= N; x++) {
+        uint32_t v = d[x] | (d[x + 1] << 8) | (d[x + 2] << 16) | ((uint32_t)d[x + 3] << 24);
+        uint32_t h = hash_u32(v);
+        if (head[h] >= 0 && x - head[h] <= kMaxDist) L[x] = (uint16_t)(x - head[h]);
+        head[h] = x;
+    }
+}
+
+struct SymOut { uint32_t pos; uint16_t dist; uint16_t lc; };
+
+extern "C" int hm_parse_serial(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), ins((N >> 5) + 2, 0);
+    HostAcc a{data, N, L.data(), holes.data(), nullptr};
+    LevelParams lp = level_params(level);
+    uint32_t n = 0;
+    serial_medium(a, N, 0, ins.data(), (uint32_t)ins.size(), lp, [&](Sym s, uint32_t) {
+        if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc};
+        n++;
+    });
+    *nsyms = n;
+    return 0;
+}
+
+// Phase-by-phase model of the GPU pipeline.
+extern "C" int hm_parse_parallel(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms,
+                                 uint32_t *iters_out)
+{
+    LevelParams lp = level_params(level);
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), newholes((N >> 5) + 2, 0);
+    std::vector<uint32_t> M(N + 1024, 0), nxt(N + 1, 0);
+    HostAcc a{data, N, L.data(), holes.data(), M.data()};
+    uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    uint32_t iters = 0;
+    std::vector<uint32_t> path;
+    uint32_t tail_entry = 0;
+    bool first = true;
+    for (;;) {
+        iters++;
+        // K2: M for every position (hole-aware)
+        for (uint32_t x = 0; x < N; x++) {
+            if (!first) { /* model recomputes everything; the GPU restricts this to affected tiles */ }
+            Match m = (x + kMSafe <= N) ? lm_walk(a, x, 0xffffffffu, lp) : Match{0, 0};
+            M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+        }
+        first = false;
+        // P1: nxt for every canonical position below the tail
+        for (uint32_t p = 0; p < tail_start; p++) {
+            uint32_t ns;
+            uint32_t np = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns);
+            nxt[p] = np;
+        }
+        // P2: path from 0
+        path.clear();
+        uint32_t p = 0;
+        tail_entry = 0;
+        while (p < tail_start) {
+            if (nxt[p] >= tail_start) break; // p is the tail entry (re-simulated serially)
+            path.push_back(p);
+            p = nxt[p];
+        }
+        tail_entry = p;
+        // holes from the path's long matches
+        std::fill(newholes.begin(), newholes.end(), 0);
+        for (uint32_t q : path) {
+            uint32_t ns;
+            macro_step(a, q, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy)
+                    for (uint32_t y = s.pos + 1; y + 1 < s.pos + s.lc + 3; y++) newholes[y >> 5] |= 1u << (y & 31);
+            }, &ns);
+        }
+        if (newholes == holes) break;
+        holes = newholes;
+        a.holes = holes.data();
+        if (iters > 64) return -1;
+    }
+    // P3: symbols
+    uint32_t n = 0;
+    for (uint32_t q : path) {
+        uint32_t ns;
+        macro_step(a, q, lp, tail_start, [&](Sym s) { if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc}; n++; }, &ns);
+    }
+    // tail
+    std::vector<uint32_t> ins(64 + (N - tail_entry) / 32 + 2, 0);
+    serial_medium(a, N, tail_entry, ins.data(), (uint32_t)ins.size(), lp, [&](Sym s, uint32_t) {
+        if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc};
+        n++;
+    });
+    *nsyms = n;
+    *iters_out = iters;
+    return 0;
+}
+
+// Oracle trace (reference parser's tallied symbols)
+struct TraceCtx { SymOut *out; uint32_t cap, n; };
+static void trace_cb(void *ctx, uint64_t pos, unsigned dist, unsigned lc_or_len)
+{
+    TraceCtx *t = (TraceCtx *)ctx;
+    if (t->n < t->cap) t->out[t->n] = SymOut{(uint32_t)pos, (uint16_t)dist, (uint16_t)(dist ? lc_or_len - 3 : lc_or_len)};
+    t->n++;
+}
+extern "C" int hm_oracle_trace(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    zo_stream s;
+    memset(&s, 0, sizeof s);
+    if (zo_deflate_init(&s, level, 15, 8, 0) != 0) return -1;
+    TraceCtx t{out, cap, 0};
+    zo_deflate_set_trace(&s, trace_cb, &t);
+    std::vector<uint8_t> dst(zo_compress_bound(N) + 64);
+    s.next_in = data; s.avail_in = N; s.next_out = dst.data(); s.avail_out = (uint32_t)dst.size();
+    int rc = zo_deflate(&s, ZO_FINISH);
+    zo_deflate_end(&s);
+    *nsyms = t.n;
+    return rc == ZO_STREAM_END ? 0 : -2;
+}
