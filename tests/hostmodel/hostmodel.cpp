@@ -146,3 +146,133 @@ extern "C" int hm_oracle_trace(const uint8_t *data, uint32_t N, int level, SymOu
     *nsyms = t.n;
     return rc == ZO_STREAM_END ? 0 : -2;
 }
+
+// ------------------------------------------------------------------------------------------
+// Encode model: blocks -> trees -> bit stream, phase by phase as the kernels do it.
+// ------------------------------------------------------------------------------------------
+#include "../../zlib_rs_b200/csrc/zb_huff.h"
+
+static void put_bits(std::vector<uint8_t> &out, uint64_t bitpos, uint64_t val, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t p = bitpos + i;
+        if ((p >> 3) >= out.size()) out.resize((p >> 3) + 1, 0);
+        out[p >> 3] |= (uint8_t)(((val >> i) & 1) << (p & 7));
+    }
+}
+
+extern "C" int hm_deflate(const uint8_t *data, uint32_t N, int level, uint8_t *dst, uint32_t cap, uint32_t *out_len,
+                          uint32_t *iters_out, int *data_type_out)
+{
+    LevelParams lp = level_params(level);
+    // ---- parse (same as hm_parse_parallel, but keeping per-symbol window bases for the tail) ----
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), newholes((N >> 5) + 2, 0);
+    std::vector<uint32_t> M(N + 1024, 0), nxt(N + 1, 0);
+    HostAcc a{data, N, L.data(), holes.data(), M.data()};
+    uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    uint32_t iters = 0, tail_entry = 0;
+    std::vector<uint32_t> path;
+    for (;;) {
+        iters++;
+        for (uint32_t x = 0; x < N; x++) {
+            Match m = (x + kMSafe <= N) ? lm_walk(a, x, 0xffffffffu, lp) : Match{0, 0};
+            M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+        }
+        for (uint32_t p = 0; p < tail_start; p++) { uint32_t ns; nxt[p] = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns); }
+        path.clear();
+        uint32_t p = 0;
+        while (p < tail_start && nxt[p] < tail_start) { path.push_back(p); p = nxt[p]; }
+        tail_entry = p;
+        std::fill(newholes.begin(), newholes.end(), 0);
+        for (uint32_t q : path) {
+            uint32_t ns;
+            macro_step(a, q, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy)
+                    for (uint32_t y = s.pos + 1; y + 1 < s.pos + s.lc + 3; y++) newholes[y >> 5] |= 1u << (y & 31);
+            }, &ns);
+        }
+        if (newholes == holes) break;
+        holes = newholes;
+        a.holes = holes.data();
+        if (iters > 64) return -1;
+    }
+    std::vector<Sym> syms;
+    std::vector<uint32_t> symB;
+    for (uint32_t q : path) {
+        uint32_t ns;
+        macro_step(a, q, lp, tail_start, [&](Sym s) { syms.push_back(s); symB.push_back(wbase(s.pos)); }, &ns);
+    }
+    std::vector<uint32_t> ins(64 + (N - tail_entry) / 32 + 2, 0);
+    uint32_t finalB = serial_medium(a, N, tail_entry, ins.data(), (uint32_t)ins.size(), lp,
+                                    [&](Sym s, uint32_t B) { syms.push_back(s); symB.push_back(B); });
+    // ---- blocks ----
+    HuffTables T;
+    init_tables(T);
+    uint32_t nsyms = (uint32_t)syms.size();
+    uint32_t nblocks = nsyms / kBlockSyms + 1;
+    std::vector<BlockDesc> blocks(nblocks);
+    TreeScratch scratch;
+    uint32_t in_pos = 0;
+    int data_type = 2;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        BlockDesc &bd = blocks[b];
+        bd.sym_begin = b * kBlockSyms;
+        bd.sym_count = (b + 1 < nblocks) ? kBlockSyms : nsyms - bd.sym_begin;
+        bd.last = b + 1 == nblocks;
+        bd.in_start = in_pos;
+        uint32_t end = bd.last ? N : (syms[bd.sym_begin + bd.sym_count - 1].pos +
+                                      (syms[bd.sym_begin + bd.sym_count - 1].dist ? syms[bd.sym_begin + bd.sym_count - 1].lc + 3u : 1u));
+        bd.in_len = end - in_pos;
+        in_pos = end;
+        uint32_t Bflush = bd.last ? finalB : symB[bd.sym_begin + bd.sym_count - 1];
+        uint32_t lfreq[kLCodes] = {0}, dfreq[kDCodes] = {0};
+        for (uint32_t i = 0; i < bd.sym_count; i++) {
+            const Sym &s = syms[bd.sym_begin + i];
+            if (s.dist == 0) lfreq[s.lc]++;
+            else { lfreq[257 + T.length_code[s.lc]]++; dfreq[d_code(T, s.dist - 1u)]++; }
+        }
+        build_block(T, scratch, bd, lfreq, dfreq, bd.in_start >= Bflush, false);
+        if (data_type == 2 && bd.sym_count) data_type = (int)bd.data_type;
+    }
+    // ---- scan + pack ----
+    std::vector<uint8_t> out(2, 0);
+    uint32_t lf = level < 2 ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+    uint32_t h = ((8 + (7 << 4)) << 8) | (lf << 6);
+    h += 31 - (h % 31);
+    out[0] = (uint8_t)(h >> 8); out[1] = (uint8_t)h;
+    uint64_t bit = 16;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        BlockDesc &bd = blocks[b];
+        bd.bit_base = bit;
+        if (bd.type == 0) {
+            put_bits(out, bit, bd.hdr[0], 3);
+            uint64_t p = (bit + 3 + 7) & ~7ull;
+            uint16_t sl = (uint16_t)bd.in_len;
+            put_bits(out, p, sl, 16); put_bits(out, p + 16, (uint16_t)~sl, 16);
+            for (uint32_t i = 0; i < sl; i++) put_bits(out, p + 32 + 8ull * i, data[bd.in_start + i], 8);
+        } else {
+            for (uint32_t i = 0; i < bd.hdr_bits; i++) put_bits(out, bit + i, (bd.hdr[i >> 3] >> (i & 7)) & 1, 1);
+            uint64_t q = bit + bd.hdr_bits;
+            for (uint32_t i = 0; i < bd.sym_count; i++) {
+                const Sym &s = syms[bd.sym_begin + i];
+                uint64_t v; uint32_t n = sym_bits(T, bd, s.dist, s.lc, v);
+                put_bits(out, q, v, n); q += n;
+            }
+            put_bits(out, q, bd.lcode[kEndBlock], bd.llen[kEndBlock]); q += bd.llen[kEndBlock];
+            if (q != bit + bd.hdr_bits + bd.body_bits) return -7;
+        }
+        bit = block_end_bit(bd, bit);
+    }
+    uint64_t bytes = (bit + 7) >> 3;
+    out.resize(bytes, 0);
+    uint32_t ad = zo_adler32(1, data, N);
+    out.push_back((uint8_t)(ad >> 24)); out.push_back((uint8_t)(ad >> 16)); out.push_back((uint8_t)(ad >> 8)); out.push_back((uint8_t)ad);
+    if (out.size() > cap) return -5;
+    memcpy(dst, out.data(), out.size());
+    *out_len = (uint32_t)out.size();
+    *iters_out = iters;
+    *data_type_out = data_type;
+    return 0;
+}
