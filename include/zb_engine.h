@@ -1,0 +1,99 @@
+/*
+ * zb_engine.h -- low-level C ABI of the B200 DEFLATE engine (libz_b200.so).
+ *
+ * Plain pointers and sizes only.  This is the layer the zlib-compatible entry points in zlib_b200.h are
+ * built on, and what a Rust `zlib-rs` FFI shim would bind for the hot path:
+ *
+ *   zb_deflate      <- zlib_rs::deflate::compress / deflate(Z_FINISH)   zlib-rs/src/deflate.rs:2858-2957, 2489
+ *   zb_inflate      <- zlib_rs::inflate::uncompress / inflate           zlib-rs/src/inflate.rs:195-277, 2376
+ *   zb_adler32      <- zlib_rs::adler32::adler32                        zlib-rs/src/adler32.rs:19
+ *   zb_crc32        <- zlib_rs::crc32::crc32                            zlib-rs/src/crc32.rs:19
+ *
+ * All compute runs on the GPU.  There is no CPU fallback: without a usable CUDA device every call
+ * returns ZB_E_NODEVICE.
+ */
+#ifndef ZB_ENGINE_H
+#define ZB_ENGINE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_API __attribute__((visibility("default")))
+
+#define ZB_OK 0
+#define ZB_E_NODEVICE (-100) /* no CUDA device / driver */
+#define ZB_E_CUDA (-101)     /* a CUDA call failed (zb_last_error() has the text) */
+#define ZB_E_BUF (-5)        /* output buffer too small (Z_BUF_ERROR) */
+#define ZB_E_MEM (-4)        /* device/host allocation failed (Z_MEM_ERROR) */
+#define ZB_E_PARAM (-2)      /* invalid argument (Z_STREAM_ERROR) */
+#define ZB_E_DATA (-3)       /* corrupt input (Z_DATA_ERROR) */
+#define ZB_E_INTERNAL (-102) /* engine invariant violated */
+
+typedef struct zb_engine zb_engine;
+
+typedef struct zb_deflate_result {
+    uint64_t out_bytes;    /* length of the produced stream */
+    uint32_t check;        /* adler32 (zlib) / crc32 (gzip) / 0 (raw) of the input */
+    int32_t data_type;     /* Z_BINARY 0 / Z_TEXT 1 / Z_UNKNOWN 2, as deflate() leaves it in z_stream */
+    uint32_t iterations;   /* hole fixed-point iterations of the parser */
+    uint32_t n_symbols;    /* literal/match symbols */
+    uint32_t n_blocks;     /* deflate blocks */
+    uint32_t gpu_launches; /* kernels launched for this call */
+    int32_t exact_parity;  /* 1: bytes equal zlib-rs' compress2 at this level/strategy; 0: valid stream only */
+    float gpu_ms;          /* device time of the call (CUDA events), copies included when buffers are on the host */
+} zb_deflate_result;
+
+/* One engine = one CUDA device + stream + grow-only device buffers.  Not thread safe; create one per thread. */
+ZB_API zb_engine *zb_engine_create(int device, int *err);
+ZB_API void zb_engine_destroy(zb_engine *e);
+ZB_API const char *zb_last_error(void);
+ZB_API int zb_device_count(void);
+
+/* window_bits follows deflateInit2: 9..15 zlib, -9..-15 raw, 25..31 gzip.  Only a 32 KiB window is implemented;
+ * other sizes are accepted and compressed with the 32 KiB engine (valid stream, CINFO=7). */
+ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
+               int level, int strategy, int window_bits, zb_deflate_result *res);
+/* flags for zb_deflate_ex */
+#define ZB_FLAG_NOT_LAST 1u /* raw segment that is not the end of the stream: BFINAL stays 0 and the Z_SYNC_FLUSH marker
+                               (empty stored block 00 00 ff ff, zlib-rs/src/deflate.rs:2733-2738) is appended, so segments
+                               concatenate into one stream (pigz-style sharding) */
+ZB_API int zb_deflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
+                  int level, int strategy, int window_bits, uint32_t flags, zb_deflate_result *res);
+ZB_API size_t zb_deflate_bound(size_t src_len);
+
+typedef struct zb_inflate_result {
+    uint64_t out_bytes;
+    uint64_t in_bytes;   /* compressed bytes consumed */
+    uint32_t check;      /* adler32 / crc32 of the output */
+    int32_t status;      /* ZB_OK, ZB_E_DATA, ZB_E_BUF */
+    uint32_t gpu_launches;
+    float gpu_ms;
+    char msg[64];        /* zlib-style error message on ZB_E_DATA */
+} zb_inflate_result;
+
+ZB_API int zb_inflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
+               int window_bits, zb_inflate_result *res);
+
+ZB_API int zb_adler32(zb_engine *e, uint32_t start, const void *buf, size_t len, int on_device, uint32_t *out, float *gpu_ms);
+ZB_API int zb_crc32(zb_engine *e, uint32_t start, const void *buf, size_t len, int on_device, uint32_t *out, float *gpu_ms);
+
+/* Per-phase device timing of the last zb_deflate call (CUDA events around each kernel group; adds a sync per
+ * phase, so only for measurement).  Phases: 0 links, 1 match, 2 nxt, 3 path, 4 emit+holes, 5 tail, 6 blocks,
+ * 7 encode, 8 checksum, 9 h2d, 10 d2h. */
+ZB_API void zb_engine_set_profile(zb_engine *e, int on);
+ZB_API int zb_engine_get_profile(zb_engine *e, float *ms, uint32_t *launches, int n);
+
+/* device memory helpers so that host languages without a CUDA binding can keep data resident */
+ZB_API void *zb_device_alloc(zb_engine *e, size_t bytes);
+ZB_API void zb_device_free(zb_engine *e, void *p);
+ZB_API int zb_copy_to_device(zb_engine *e, void *dst, const void *src, size_t bytes);
+ZB_API int zb_copy_to_host(zb_engine *e, void *dst, const void *src, size_t bytes);
+ZB_API int zb_device_fill_random(zb_engine *e, void *dst, size_t bytes, uint64_t seed); /* splitmix64 of the 8-byte index */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,95 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the headers declare,
+keeps the z_stream layout, and the entry points that need no device behave like the reference.
+(No compute calls: there is no GPU here and the library has no CPU fallback.)"""
+import ctypes
+import os
+import re
+
+import pytest
+
+import oracle_lib as O
+import zlib_rs_b200 as Z
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, macro):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(macro + r"[^;(]*?\b(\w+)\s*\(", src)) - {"__attribute__"})
+
+
+def test_library_exports_every_declared_symbol():
+    L = Z.lib()
+    names = _declared("zlib_b200.h", "ZB_EXPORT") + _declared("zb_engine.h", "ZB_API")
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    # north_star's mandatory surface
+    for n in ("deflateInit2_", "deflate", "deflateEnd", "inflateInit2_", "inflate", "inflateEnd", "compress2", "uncompress",
+              "crc32", "adler32"):
+        assert n in names
+
+
+def test_z_stream_layout():
+    # zlib-rs/src/c_api.rs:56-71: 112 bytes on LP64
+    assert ctypes.sizeof(Z.ZStream) == 112
+    assert Z.ZStream.total_in.offset == 16 and Z.ZStream.next_out.offset == 24 and Z.ZStream.state.offset == 56
+    assert Z.ZStream.data_type.offset == 88 and Z.ZStream.adler.offset == 96
+
+
+def test_version_rule():
+    # libz-rs-sys/src/lib.rs:2133-2145
+    L = Z.lib()
+    s = Z.ZStream()
+    assert L.zlibVersion().startswith(b"1.3.0-zlib-rs-0.6.7")
+    assert L.deflateInit2_(ctypes.byref(s), 6, 8, 15, 8, 0, b"2.0", 112) == Z.Z_VERSION_ERROR
+    assert L.deflateInit2_(ctypes.byref(s), 6, 8, 15, 8, 0, None, 112) == Z.Z_VERSION_ERROR
+    assert L.deflateInit2_(ctypes.byref(s), 6, 8, 15, 8, 0, Z.ZLIB_VERSION, 111) == Z.Z_VERSION_ERROR
+    assert L.inflateInit2_(ctypes.byref(s), 15, b"0.9", 112) == Z.Z_VERSION_ERROR
+    assert L.deflateInit2_(None, 6, 8, 15, 8, 0, Z.ZLIB_VERSION, 112) == Z.Z_STREAM_ERROR
+
+
+def test_parameter_errors_before_device_use():
+    # zlib-rs/src/deflate.rs:282-312, inflate.rs:2298-2327
+    L = Z.lib()
+    s = Z.ZStream()
+    for lvl, wb, mem, strat in ((10, 15, 8, 0), (6, 16, 8, 0), (6, 7, 8, 0), (6, 15, 0, 0), (6, 15, 10, 0), (6, 15, 8, 5), (6, -8, 8, 0),
+                                (6, -16, 8, 0)):
+        assert L.deflateInit2_(ctypes.byref(s), lvl, 8, wb, mem, strat, Z.ZLIB_VERSION, 112) == Z.Z_STREAM_ERROR, (lvl, wb, mem, strat)
+    assert L.deflateInit2_(ctypes.byref(s), 6, 7, 15, 8, 0, Z.ZLIB_VERSION, 112) == Z.Z_STREAM_ERROR  # method
+    assert L.inflateInit2_(ctypes.byref(s), 7, Z.ZLIB_VERSION, 112) == Z.Z_STREAM_ERROR
+    assert L.inflateInit2_(ctypes.byref(s), -16, Z.ZLIB_VERSION, 112) == Z.Z_STREAM_ERROR
+    s2 = Z.ZStream()
+    assert L.deflate(ctypes.byref(s2), 0) == Z.Z_STREAM_ERROR      # NULL state
+    assert L.deflateEnd(ctypes.byref(s2)) == Z.Z_STREAM_ERROR
+    assert L.inflate(ctypes.byref(s2), 0) == Z.Z_STREAM_ERROR
+    assert L.inflateEnd(ctypes.byref(s2)) == Z.Z_STREAM_ERROR
+    assert L.deflate(None, 0) == Z.Z_STREAM_ERROR
+
+
+def test_no_device_is_loud_not_a_fallback():
+    L = Z.lib()
+    if L.zb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = Z.ZStream()
+    assert L.deflateInit2_(ctypes.byref(s), 6, 8, 15, 8, 0, Z.ZLIB_VERSION, 112) == Z.Z_MEM_ERROR
+    assert s.msg == b"no CUDA device"
+    assert L.inflateInit2_(ctypes.byref(s), 15, Z.ZLIB_VERSION, 112) == Z.Z_MEM_ERROR
+    n = ctypes.c_ulong(100)
+    assert L.compress2(ctypes.create_string_buffer(100), ctypes.byref(n), b"abc", 3, 6) == Z.Z_MEM_ERROR
+    with pytest.raises(RuntimeError):
+        Z.Engine(0)
+
+
+def test_null_buffer_checksums_and_combine_algebra():
+    # libz-rs-sys/src/lib.rs:150-155, 307-312; combine: crc32/combine.rs, adler32.rs:58-87
+    L = Z.lib()
+    assert L.crc32_z(123, None, 10) == 0 and L.adler32_z(77, None, 10) == 1
+    Lo = O.lib()
+    for a, b, n in ((1, 1, 0), (0x12345678, 0x9abcdef0, 1), (0xdeadbeef, 0x0badf00d, 5552), (5, 7, 1 << 33)):
+        assert L.crc32_combine64(a, b, n) == Lo.zo_crc32_combine(a, b, n)
+        assert L.crc32_combine_op(a, b, L.crc32_combine_gen64(n)) == Lo.zo_crc32_combine(a, b, n)
+        assert L.adler32_combine64(a % 65521 | ((a >> 16) % 65521) << 16, b % 65521 | ((b >> 16) % 65521) << 16, n) == \
+            Lo.zo_adler32_combine(a % 65521 | ((a >> 16) % 65521) << 16, b % 65521 | ((b >> 16) % 65521) << 16, n)
+    assert L.zError(-3) == b"data error" and L.zError(-5) == b"buffer error"
+    assert L.compressBound(0) >= 13 and L.compressBound(1 << 20) >= (1 << 20) + 13

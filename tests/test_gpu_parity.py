@@ -1,0 +1,250 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of libz_b200.so and is
+compared with the CPU oracle on the same inputs -- bit-exact for the level 3..6 one-shot path."""
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import zlib_rs_b200 as Z
+from corpus import silesia_gz, silesia_member, silesia_tar, synthetic_mix
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Z.Engine(0)
+    yield e
+    e.close()
+
+
+def test_checksums_vs_oracle_and_stock(eng):
+    for n in (0, 1, 15, 16, 17, 1023, 4096, 65535, 65536, 1 << 20, 3 * (1 << 20) + 7):
+        d = synthetic_mix(n, seed=n + 3)
+        assert Z.adler32(d) == O.adler32(d) == zlib.adler32(d)
+        assert Z.crc32(d) == O.crc32(d) == zlib.crc32(d)
+        assert Z.adler32(d, 0x1234ABCD % 65521) == O.adler32(d, 0x1234ABCD % 65521)
+        assert Z.crc32(d, 0xDEADBEEF) == O.crc32(d, 0xDEADBEEF)
+    assert Z.crc32(bytes([1, 2, 3])) == 1438416925  # libz-rs-sys/src/lib.rs:146
+
+
+def test_checksum_of_checksums_large(eng):
+    """Size-independent property at a large size: chunk checksums combine to the whole (device resident)."""
+    n = 256 << 20
+    p = eng.alloc(n)
+    try:
+        eng.fill_random(p, n, 42)
+        whole_a, _ = eng.adler32(p, n, on_device=True)
+        whole_c, _ = eng.crc32(p, n, on_device=True)
+        L = Z.lib()
+        acc_a, acc_c, off = 1, 0, 0
+        for part in (1 << 20, 77 << 20, 100 << 20, n - (178 << 20)):
+            a, _ = eng.adler32(p + off, part, on_device=True)
+            c, _ = eng.crc32(p + off, part, on_device=True)
+            acc_a = L.adler32_combine64(acc_a, a, part)
+            acc_c = L.crc32_combine64(acc_c, c, part)
+            off += part
+        assert off == n and acc_a == whole_a and acc_c == whole_c
+        host = eng.to_host(p, 8 << 20)
+        assert zlib.crc32(host) == eng.crc32(p, 8 << 20, on_device=True)[0]
+        assert zlib.adler32(host) == eng.adler32(p, 8 << 20, on_device=True)[0]
+    finally:
+        eng.free(p)
+
+
+L6_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["level"] in (-1, 6) and v["window_bits"] == 15
+           and v["mem_level"] == 8 and v["strategy"] == 0 and v["flush"] == 4]
+
+
+@pytest.mark.parametrize("v", L6_KATS, ids=[v["name"] for v in L6_KATS])
+def test_reference_golden_vectors_level6(v):
+    """The reference's own byte-exact level-6 vectors (deflate_medium_fizzle_bug, deflate_medium_bypass)."""
+    assert Z.compress2(bytes.fromhex(v["input_hex"]), 6) == bytes.fromhex(v["expected_hex"])
+
+
+SMALL = [0, 1, 2, 3, 4, 5, 100, 261, 262, 263, 300, 1000, 2047, 2048, 2049, 5000, 16383, 16384, 20000, 65535, 65536, 65537, 70000,
+         131072, 200000, 400000]
+
+
+@pytest.mark.parametrize("n", SMALL)
+def test_compress2_bit_exact_small(n):
+    d = synthetic_mix(n, seed=n)
+    out = Z.compress2(d, 6)
+    assert out == O.compress(d, 6)[1]
+    assert zlib.decompress(out) == d
+
+
+def test_compress2_bit_exact_special_inputs():
+    rng = np.random.default_rng(5)
+    cases = [bytes(300000), b"a" * 100000, b"abc" * 50000, rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+             rng.integers(0, 256, 16383, dtype=np.uint8).tobytes(), rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+             (b"x" * 65274 + synthetic_mix(1000, 1)) * 3, bytes(65274) + b"\x01" + bytes(70000)]
+    for d in cases:
+        out = Z.compress2(d, 6)
+        assert out == O.compress(d, 6)[1]
+
+
+@pytest.mark.parametrize("level", [3, 4, 5, 6])
+def test_medium_levels_bit_exact(level):
+    for k in (1, 5, 9):
+        d = silesia_member(k)[:300000]
+        assert Z.compress2(d, level) == O.compress(d, level)[1]
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_silesia_members_bit_exact_and_roundtrip(k):
+    """north_star: bit-identical round trip on all Silesia members (and bytes equal to the oracle's)."""
+    d = silesia_member(k)
+    out = Z.compress2(d, 6)
+    assert out == O.compress(d, 6)[1]
+    assert zlib.decompress(out) == d
+    assert Z.uncompress(out, len(d)) == d
+
+
+def test_silesia_tar_level6_golden(eng):
+    """BASELINE config 2: silesia-small.tar, level 6, one deflate(Z_FINISH)."""
+    d = silesia_tar()
+    out, res = eng.deflate(d, level=6)
+    assert res.exact_parity == 1
+    assert len(out) == 6457822
+    assert hashlib.sha256(out).hexdigest() == "939f96c8934588fefa2f5dabc37f5dace0ee945c0abbc0e54267337e88eafadc"
+    assert res.check == zlib.adler32(d)
+    assert zlib.decompress(out) == d
+
+
+def test_other_levels_and_strategies_valid_streams(eng):
+    d = silesia_member(3)[:200000]
+    for level in (0, 1, 2, 7, 8, 9):
+        out, res = eng.deflate(d, level=level)
+        assert zlib.decompress(out) == d
+        if level == 0:
+            assert out == O.compress(d, 0)[1]
+    for strategy in (1, 2, 3, 4):
+        out, res = eng.deflate(d, level=6, strategy=strategy)
+        assert zlib.decompress(out) == d
+        if strategy in (1, 2, 4):  # FILTERED / HUFFMAN_ONLY / FIXED follow the reference exactly
+            assert out == O.compress(d, 6, 15, 8, strategy)[1], strategy
+    for wb in (-15, 31):
+        out, res = eng.deflate(d, level=6, window_bits=wb)
+        assert out == O.compress(d, 6, wb)[1]
+
+
+def test_streaming_deflate_zpipe_shape():
+    """zpipe.c: 16 KiB in / 16 KiB out through deflate(Z_NO_FLUSH ... Z_FINISH)."""
+    d = silesia_member(4)[:500000]
+    z = Z.Deflate(6)
+    out = bytearray()
+    for i in range(0, len(d), 16384):
+        last = i + 16384 >= len(d)
+        out += z.deflate(d[i:i + 16384], Z.Z_FINISH if last else Z.Z_NO_FLUSH, out_chunk=16384)
+    assert z.last_rc == Z.Z_STREAM_END
+    assert bytes(out) == O.compress(d, 6)[1]      # the engine sees the whole input at Z_FINISH: one-shot bytes
+    assert z.total_in == len(d) and z.total_out == len(out) and z.adler == zlib.adler32(d)
+    assert z.end() == Z.Z_OK
+
+
+def test_flush_modes_produce_stitchable_stream():
+    d = synthetic_mix(300000, 9)
+    z = Z.Deflate(6)
+    out = z.deflate(d[:100000], Z.Z_SYNC_FLUSH) + z.deflate(d[100000:200000], Z.Z_FULL_FLUSH) + z.deflate(d[200000:], Z.Z_FINISH)
+    assert zlib.decompress(out) == d
+    assert z.adler == zlib.adler32(d)
+
+
+def test_segments_stitch_like_split_deflate(eng):
+    """zlib-rs/src/deflate.rs:4149-4221 (split_deflate): raw segments ended with the sync marker concatenate."""
+    d = silesia_member(6)[:400000]
+    a, _ = eng.deflate(d[:150000], level=6, window_bits=-15, flags=Z.ZB_FLAG_NOT_LAST)
+    b, _ = eng.deflate(d[150000:300000], level=6, window_bits=-15, flags=Z.ZB_FLAG_NOT_LAST)
+    c, _ = eng.deflate(d[300000:], level=6, window_bits=-15)
+    assert a.endswith(b"\x00\x00\xff\xff")
+    assert zlib.decompress(a + b + c, -15) == d
+
+
+def test_error_codes(eng):
+    import ctypes
+    L = Z.lib()
+    n = ctypes.c_ulong(10)
+    d = synthetic_mix(5000, 1)
+    assert L.compress2(ctypes.create_string_buffer(10), ctypes.byref(n), d, len(d), 6) == Z.Z_BUF_ERROR
+    assert L.compress2(None, ctypes.byref(n), d, len(d), 6) == Z.Z_STREAM_ERROR
+    z = Z.Deflate(6)
+    z.deflate(b"abc", Z.Z_NO_FLUSH)
+    assert z.end() == Z.Z_DATA_ERROR  # deflateEnd on a busy stream (libz-rs-sys/src/lib.rs:1583-1591)
+
+
+# ---------------------------------------------------------------- inflate
+def test_uncompress_kats_and_silesia(eng):
+    v = next(x for x in KAT["vectors"] if x["name"] == "uncompress_ferris")
+    assert Z.uncompress(bytes.fromhex(v["input_hex"]), 100) == b"Ferris"
+    rc, out, res = eng.inflate(silesia_gz(), len(silesia_tar()))
+    assert rc == 0 and out == silesia_tar() and res.check == zlib.adler32(silesia_tar())
+    assert res.in_bytes == len(silesia_gz())
+
+
+def test_inflate_all_block_types_and_wrappers(eng):
+    d = silesia_member(0)[:300000]
+    for level in (0, 1, 6, 9):
+        for wb in (15, -15, 31):
+            comp = zlib.compressobj(level, 8, wb)
+            c = comp.compress(d) + comp.flush()
+            rc, out, res = eng.inflate(c, len(d), window_bits=wb)
+            assert rc == 0 and out == d, (level, wb, res.msg)
+            rc, out, res = eng.inflate(c, len(d), window_bits=47 if wb > 0 else wb)
+            assert rc == 0 and out == d
+    c = zlib.compressobj(6, 8, 15, 8, zlib.Z_FIXED)
+    fixed = c.compress(d) + c.flush()
+    assert eng.inflate(fixed, len(d))[1] == d
+    for f in sorted(os.listdir(os.path.join(HERE, "golden", "data"))):
+        if f.startswith("The_"):
+            raw = open(os.path.join(HERE, "golden", "data", f), "rb").read()
+            exp = zlib.decompress(raw, 31)
+            rc, out, res = eng.inflate(raw, len(exp), window_bits=31)
+            assert rc == 0 and out == exp, f
+
+
+TRY = [v for v in KAT["vectors"] if v["kind"] == "try_inflate"]
+
+
+@pytest.mark.parametrize("v", TRY, ids=[v["name"] for v in TRY])
+def test_inflate_error_vectors(eng, v):
+    data = bytes.fromhex(v["input_hex"])
+    wbits = 47 if v["expected"] in ("Z_DATA_ERROR", "Z_MEM_ERROR", "Z_BUF_ERROR") else -15
+    rc, out, res = eng.inflate(data, max(8 * len(data), 64), window_bits=wbits)
+    orc, oout, omsg, _ = O.inflate_stream(data, wbits, out_chunk=max(8 * len(data), 64))
+    if v["expected"] != "Z_OK":
+        assert rc == Z.Z_DATA_ERROR
+        if orc == -3:
+            assert res.msg.decode() == omsg
+    else:
+        assert out == oout
+
+
+def test_uncompress_error_mapping():
+    d = synthetic_mix(5000, 5)
+    comp = zlib.compress(d, 6)
+    assert Z.uncompress(comp, 5000) == d
+    for bad, cap, code in ((comp[:-5], 6000, Z.Z_DATA_ERROR), (comp, 100, Z.Z_BUF_ERROR), (comp[:-1] + bytes([comp[-1] ^ 1]), 5000, Z.Z_DATA_ERROR)):
+        with pytest.raises(Z.ZlibError) as ei:
+            Z.uncompress(bad, cap)
+        assert ei.value.code == code
+
+
+def test_streaming_inflate():
+    d = silesia_member(7)[:400000]
+    comp = zlib.compress(d, 6)
+    z = Z.Inflate(15)
+    out = bytearray()
+    for i in range(0, len(comp), 16384):
+        out += z.inflate(comp[i:i + 16384], out_chunk=16384)
+    while not z.eof:
+        got = z.inflate(b"", out_chunk=16384)
+        assert got or z.eof
+        out += got
+    assert bytes(out) == d and z.adler == zlib.adler32(d)

@@ -1,0 +1,82 @@
+"""CPU tests of the GPU engine's algorithm: tests/hostmodel compiles the device functions of
+zlib_rs_b200/csrc (zb_core.h, zb_huff.h) for the host and runs them in the kernels' phase order.
+Checked against the oracle: the parse (symbol by symbol) and the final bytes."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from corpus import silesia_member, synthetic_mix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_H = None
+
+
+def H():
+    global _H
+    if _H is None:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "hostmodel")], stdout=subprocess.DEVNULL)
+        _H = ctypes.CDLL(os.path.join(ROOT, "tests", "hostmodel", "_build", "libhostmodel.so"))
+    return _H
+
+
+def _syms(fn, data, level, extra=False):
+    n = len(data)
+    out = np.zeros((n + 16) * 2, dtype=np.uint32)
+    ns, it = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    args = [data, n, level, out.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(ns)]
+    if extra:
+        args.append(ctypes.byref(it))
+    assert getattr(H(), fn)(*args) == 0
+    return out[: ns.value * 2].copy()
+
+
+def _deflate(data, level):
+    cap = len(data) + len(data) // 8 + 1024
+    buf = ctypes.create_string_buffer(cap)
+    n, it, dt = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_int(0)
+    rc = H().hm_deflate(data, len(data), level, buf, cap, ctypes.byref(n), ctypes.byref(it), ctypes.byref(dt))
+    assert rc == 0, rc
+    return buf.raw[: n.value]
+
+
+CASES = [("empty", b""), ("one", b"a"), ("three", b"abc"), ("mix262", synthetic_mix(262, 1)), ("mix5000", synthetic_mix(5000, 2)),
+         ("mix65536", synthetic_mix(65536, 3)), ("mix131072", synthetic_mix(131072, 131072)), ("zeros", bytes(200000)),
+         ("rand", np.random.default_rng(7).integers(0, 256, 70000, dtype=np.uint8).tobytes()),
+         ("lit16383", np.random.default_rng(2).integers(0, 256, 16383, dtype=np.uint8).tobytes()),
+         ("nci", silesia_member(1)[:150000]), ("xml", silesia_member(9)[:150000]), ("mozilla", silesia_member(2)[:150000])]
+
+
+@pytest.mark.parametrize("name,data", CASES, ids=[c[0] for c in CASES])
+def test_parse_matches_reference_parser(name, data):
+    """serial_medium (absolute-coordinate restatement) and the parallel pipeline both reproduce every
+    symbol the reference's deflate_medium tallies."""
+    for level in (6,):
+        o = _syms("hm_oracle_trace", data, level)
+        s = _syms("hm_parse_serial", data, level)
+        p = _syms("hm_parse_parallel", data, level, True)
+        assert len(o) == len(s) and (o == s).all()
+        assert len(o) == len(p) and (o == p).all()
+
+
+@pytest.mark.parametrize("name,data", CASES, ids=[c[0] for c in CASES])
+def test_bytes_match_reference(name, data):
+    assert _deflate(data, 6) == O.compress(data, 6)[1]
+
+
+@pytest.mark.parametrize("level", [3, 4, 5])
+def test_other_medium_levels(level):
+    for k in (5, 9):
+        data = silesia_member(k)[:120000]
+        assert _deflate(data, level) == O.compress(data, level)[1]
+
+
+def test_window_base_schedule():
+    """wbase(): slides at the first loop-top beyond base+65274 (zlib-rs/src/deflate.rs:1787)."""
+    data = synthetic_mix(300000, 11)
+    o = _syms("hm_oracle_trace", data, 6)
+    p = _syms("hm_parse_parallel", data, 6, True)
+    assert (o == p).all()

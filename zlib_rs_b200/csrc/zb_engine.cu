@@ -1,0 +1,498 @@
+// zb_engine.cu -- host orchestration of the B200 DEFLATE engine and the low-level C ABI (zb_engine.h).
+// Host code only allocates, copies and launches; every byte of compute happens in kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "../../include/zb_engine.h"
+#include "zb_kernels.cuh"
+#include "zb_engine_internal.h"
+
+namespace zb {
+
+thread_local char g_err[256] = "";
+
+static void set_err(const char *what, cudaError_t e)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) { set_err(#call, e_); return ZB_E_CUDA; } \
+    } while (0)
+
+// kernels (zb_kernels.cu)
+__global__ void k_links(JobBufs);
+__global__ void k_match(JobBufs);
+__global__ void k_nxt(JobBufs);
+__global__ void k_path_tiles(JobBufs);
+__global__ void k_path_chain(JobBufs, uint32_t);
+__global__ void k_path_mark(JobBufs);
+__global__ void k_emit(JobBufs);
+__global__ void k_holes_cmp(JobBufs, uint32_t, uint32_t);
+__global__ void k_tail(JobBufs);
+__global__ void k_block_hist(JobBufs, uint32_t *);
+__global__ void k_build_blocks(JobBufs, const uint32_t *);
+__global__ void k_scan_blocks(JobBufs);
+__global__ void k_encode(JobBufs);
+__global__ void k_finish(JobBufs, const uint32_t *);
+__global__ void k_literal_syms(JobBufs);
+__global__ void k_stored(JobBufs);
+
+constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
+constexpr uint32_t kMatchSmemBytes = (2 * kWSize + 512) + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
+constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
+
+int Engine::init(int dev)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(g_err, sizeof g_err, "no CUDA device (%s)", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+        return ZB_E_NODEVICE;
+    }
+    if (dev < 0 || dev >= n) { snprintf(g_err, sizeof g_err, "device %d out of range", dev); return ZB_E_PARAM; }
+    device = dev;
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(upload_tables());
+    CK(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmemBytes));
+    CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
+    CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
+    CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
+    CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
+    CK(cudaMalloc(&d_info, sizeof(JobInfo)));
+    CK(cudaMalloc(&d_check, 16));
+    { int rc_ = inflate_init(); if (rc_ != ZB_OK) return rc_; }
+    return ZB_OK;
+}
+
+Engine::~Engine()
+{
+    if (device < 0) return;
+    cudaSetDevice(device);
+    for (auto &b : bufs) if (b.p) cudaFree(b.p);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (h_info) cudaFreeHost(h_info);
+    if (d_info) cudaFree(d_info);
+    if (d_check) cudaFree(d_check);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+}
+
+void Engine::pbegin()
+{
+    if (!profile) return;
+    if (!pev0) { cudaEventCreate(&pev0); cudaEventCreate(&pev1); }
+    cudaEventRecord(pev0, st);
+}
+
+void Engine::pend(int phase, uint32_t nlaunch)
+{
+    if (!profile) return;
+    cudaEventRecord(pev1, st);
+    cudaEventSynchronize(pev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pev0, pev1);
+    phase_ms[phase] += ms;
+    phase_launches[phase] += nlaunch;
+}
+
+int Engine::reserve(int slot, size_t bytes, void **out)
+{
+    Buf &b = bufs[slot];
+    if (b.cap < bytes) {
+        if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        size_t want = bytes + (bytes >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { set_err("cudaMalloc", e); return ZB_E_MEM; }
+        b.cap = want;
+    }
+    *out = b.p;
+    return ZB_OK;
+}
+
+int Engine::stage(size_t bytes)
+{
+    if (h_stage_cap < bytes) {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        h_stage_cap = 0;
+        cudaError_t e = cudaMallocHost(&h_stage, bytes + (bytes >> 3) + 4096);
+        if (e != cudaSuccess) { set_err("cudaMallocHost", e); return ZB_E_MEM; }
+        h_stage_cap = bytes + (bytes >> 3) + 4096;
+    }
+    return ZB_OK;
+}
+
+enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_COUNT };
+static_assert(S_COUNT <= Engine::kSlots, "slots");
+
+size_t deflate_bound(size_t n)
+{
+    // stored blocks are the worst case for every path of the engine (deflate.rs:3193-3307 gives the
+    // reference's tighter figure for its own block splitting; ours never exceeds stored + framing)
+    return n + (n / 16383 + 2) * 8 + (n >> 10) + 64;
+}
+
+int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int level, int strategy,
+                    int window_bits, uint32_t flags, zb_deflate_result *res)
+{
+    if (!res || (!src && n) || !dst) return ZB_E_PARAM;
+    memset(res, 0, sizeof *res);
+    if (n > 0xF0000000ull) { snprintf(g_err, sizeof g_err, "input too large for one job (%zu)", n); return ZB_E_PARAM; }
+    if (level == -1) level = 6;
+    if (level < 0 || level > 9 || strategy < 0 || strategy > 4) return ZB_E_PARAM;
+    uint32_t wrap;
+    if (window_bits < 0) { if (window_bits < -15 || window_bits > -8) return ZB_E_PARAM; wrap = 0; }
+    else if (window_bits > 15) { if (window_bits < 24 || window_bits > 31) return ZB_E_PARAM; wrap = 2; }
+    else { if (window_bits < 8) return ZB_E_PARAM; wrap = 1; }
+    const int wb = window_bits < 0 ? -window_bits : window_bits > 15 ? window_bits - 16 : window_bits;
+    CK(cudaSetDevice(device));
+    const uint32_t N = (uint32_t)n;
+    launches = 0;
+
+    JobBufs jb;
+    memset(&jb, 0, sizeof jb);
+    int rc;
+    void *p;
+    const size_t npad = (size_t)N + kPad;
+    const uint32_t nwords = (N >> 5) + 2;
+    const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
+    const uint32_t max_blocks = N / kBlockSyms + 2;
+    const size_t out_cap = (deflate_bound(n) + 15) & ~(size_t)15;
+#define RES(slot, bytes, field, type)                                   \
+    if ((rc = reserve(slot, bytes, &p)) != ZB_OK) return rc;            \
+    jb.field = static_cast<type>(p);
+    uint8_t *d_in;
+    if (src_dev) d_in = const_cast<uint8_t *>(static_cast<const uint8_t *>(src));
+    else { if ((rc = reserve(S_IN, npad + 16, &p)) != ZB_OK) return rc; d_in = static_cast<uint8_t *>(p); }
+    jb.in = d_in;
+    jb.N = N;
+    jb.tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    RES(S_L, npad * 2, L, uint16_t *)
+    RES(S_HOLES, (size_t)nwords * 4, holes, uint32_t *)
+    RES(S_HOLESN, (size_t)nwords * 4, holes_new, uint32_t *)
+    RES(S_M, npad * 4, M, uint32_t *)
+    RES(S_NXT, ((size_t)N + 16) * 4, nxt, uint32_t *)
+    RES(S_PEXIT, ((size_t)N + 16) * 4, pexit, uint32_t *)
+    RES(S_PCNT, ((size_t)N + 16) * 4, pcnt, uint32_t *)
+    RES(S_SYMIDX, ((size_t)N + 16) * 4, symidx, uint32_t *)
+    RES(S_TENTRY, (size_t)npt * 4, tile_entry, uint32_t *)
+    RES(S_TSYMB, (size_t)npt * 4, tile_symbase, uint32_t *)
+    RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
+    RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
+    RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
+    RES(S_BLOCKS, (size_t)max_blocks * sizeof(BlockDesc), blocks, BlockDesc *)
+    RES(S_SCRATCH, (size_t)max_blocks * sizeof(TreeScratch), scratch, TreeScratch *)
+    uint32_t *d_freq;
+    if ((rc = reserve(S_FREQ, (size_t)max_blocks * 320 * 4, &p)) != ZB_OK) return rc;
+    d_freq = static_cast<uint32_t *>(p);
+    uint8_t *d_out;
+    if (dst_dev && dst_cap >= out_cap) d_out = static_cast<uint8_t *>(dst);
+    else { if ((rc = reserve(S_OUT, out_cap + 16, &p)) != ZB_OK) return rc; d_out = static_cast<uint8_t *>(p); }
+    jb.out = d_out;
+    jb.out_cap = out_cap;
+    void *d_ck;
+    const size_t ck_bytes = ((size_t)N / 16384 + 16) * 8;
+    if ((rc = reserve(S_CK, ck_bytes, &d_ck)) != ZB_OK) return rc;
+#undef RES
+    jb.info = d_info;
+    jb.level = (uint32_t)level;
+    jb.strategy_fixed = strategy == 4;
+    jb.wrap = wrap;
+    jb.hdr_len = wrap == 1 ? 2 : wrap == 2 ? 10 : 0;
+    jb.huffman_only = strategy == 2 && level != 0;
+    jb.not_last = (flags & ZB_FLAG_NOT_LAST) ? 1 : 0;
+    if (jb.not_last && (level == 0 || wrap != 0)) { snprintf(g_err, sizeof g_err, "NOT_LAST needs raw deflate and level > 0"); return ZB_E_PARAM; }
+    jb.xfl = level == 9 ? 2 : (strategy >= 2 || level < 2) ? 4 : 0;
+    // levels 3..6 follow the reference parser exactly; the other levels run the closest exact kernel set
+    int eng_level = level;
+    bool exact = wb == 15;
+    if (level != 0 && !jb.huffman_only) {
+        if (level < 3) { eng_level = 3; exact = false; }
+        if (level > 6) { eng_level = 6; exact = false; }
+        if (strategy == 3) exact = false; // Z_RLE parser not implemented: medium parser instead
+    }
+    jb.lp = level_params(eng_level);
+    if (level != 0 && !jb.huffman_only) jb.level = (uint32_t)level; // header flag bits follow the requested level
+
+    CK(cudaEventRecord(ev0, st));
+    if (profile) { for (int i = 0; i < kPhases; i++) { phase_ms[i] = 0; phase_launches[i] = 0; } }
+    if (!src_dev) {
+        pbegin();
+        if (n) CK(cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(d_in + n, 0, kPad, st));
+        pend(9, 0);
+    }
+    CK(cudaMemsetAsync(d_info, 0, sizeof(JobInfo), st));
+    CK(cudaMemsetAsync(d_out, 0, out_cap, st));
+    // checksum of the input (deflate.rs:1705-1713 computes it while filling the window)
+    pbegin();
+    if (wrap == 1) { CK(launch_adler32(d_in, n, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    else if (wrap == 2) { CK(launch_crc32(d_in, n, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    else CK(cudaMemsetAsync(d_check, 0, 4, st));
+    pend(8, 2);
+
+    uint32_t iters = 0;
+    if (level == 0) {
+        const uint32_t nb = N == 0 ? 1 : (N + 65534) / 65535;
+        k_stored<<<nb, 256, 0, st>>>(jb);
+        launches++;
+        k_finish<<<1, 32, 0, st>>>(jb, d_check);
+        launches++;
+    } else {
+        if (jb.huffman_only) {
+            k_literal_syms<<<N / 256 + 1, 256, 0, st>>>(jb);
+            launches++;
+        } else {
+            CK(cudaMemsetAsync(jb.holes, 0, (size_t)nwords * 4, st));
+            CK(cudaMemsetAsync(jb.holes_new, 0, (size_t)nwords * 4, st));
+            CK(cudaMemsetAsync(jb.tile_dirty, 1, nmt, st));
+            CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
+            CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
+            pbegin();
+            k_links<<<nmt, 32, kLinksSmemBytes, st>>>(jb);
+            launches++;
+            pend(0, 1);
+            if (jb.tail_start > 0) {
+                for (;;) {
+                    iters++;
+                    pbegin();
+                    k_match<<<nmt, 1024, kMatchSmemBytes, st>>>(jb);
+                    pend(1, 1);
+                    pbegin();
+                    k_nxt<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                    pend(2, 1);
+                    pbegin();
+                    k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    k_path_chain<<<1, 32, 0, st>>>(jb, npt);
+                    k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    pend(3, 3);
+                    pbegin();
+                    k_emit<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                    CK(cudaMemsetAsync(jb.tile_dirty, 0, nmt, st));
+                    CK(cudaMemsetAsync(&d_info->holes_changed, 0, 4, st));
+                    k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
+                    pend(4, 2);
+                    launches += 7;
+                    CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    if (h_info->error) { snprintf(g_err, sizeof g_err, "engine error flags 0x%x (parse)", h_info->error); return ZB_E_INTERNAL; }
+                    if (!h_info->holes_changed) break;
+                    if (iters > 4096) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; }
+                }
+            }
+            pbegin();
+            k_tail<<<1, 32, 0, st>>>(jb);
+            launches++;
+            pend(5, 1);
+        }
+        CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_info->error) { snprintf(g_err, sizeof g_err, "engine error flags 0x%x (tail)", h_info->error); return ZB_E_INTERNAL; }
+        const uint32_t nblocks = h_info->n_blocks;
+        if (nblocks == 0 || nblocks > max_blocks) { snprintf(g_err, sizeof g_err, "bad block count %u", nblocks); return ZB_E_INTERNAL; }
+        pbegin();
+        k_block_hist<<<nblocks, 256, 0, st>>>(jb, d_freq);
+        k_build_blocks<<<(nblocks + 31) / 32, 32, 0, st>>>(jb, d_freq);
+        k_scan_blocks<<<1, 32, 0, st>>>(jb);
+        pend(6, 3);
+        pbegin();
+        k_encode<<<nblocks, 1024, 0, st>>>(jb);
+        k_finish<<<1, 32, 0, st>>>(jb, d_check);
+        pend(7, 2);
+        launches += 5;
+    }
+    CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h_info->error) {
+        if (h_info->error & 8u) return ZB_E_BUF;
+        snprintf(g_err, sizeof g_err, "engine error flags 0x%x (encode)", h_info->error);
+        return ZB_E_INTERNAL;
+    }
+    const uint64_t out_bytes = h_info->out_bytes;
+    if (out_bytes > dst_cap) {
+        res->out_bytes = out_bytes;
+        return ZB_E_BUF;
+    }
+    if (d_out != dst) {
+        pbegin();
+        CK(cudaMemcpyAsync(dst, d_out, out_bytes, dst_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        pend(10, 0);
+    }
+    CK(cudaEventRecord(ev1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    res->out_bytes = out_bytes;
+    res->check = h_info->adler;
+    res->data_type = (int32_t)h_info->data_type;
+    res->iterations = iters;
+    res->n_symbols = h_info->n_syms;
+    res->n_blocks = h_info->n_blocks;
+    res->gpu_launches = launches;
+    res->exact_parity = exact ? 1 : 0;
+    res->gpu_ms = ms;
+    return ZB_OK;
+}
+
+int Engine::checksum(bool crc, uint32_t start, const void *buf, size_t len, bool on_dev, uint32_t *out, float *ms_out)
+{
+    if (!out) return ZB_E_PARAM;
+    CK(cudaSetDevice(device));
+    int rc;
+    void *p;
+    const uint8_t *d = static_cast<const uint8_t *>(buf);
+    CK(cudaEventRecord(ev0, st));
+    if (!on_dev && len) {
+        if ((rc = reserve(S_IN, len + 16, &p)) != ZB_OK) return rc;
+        CK(cudaMemcpyAsync(p, buf, len, cudaMemcpyHostToDevice, st));
+        d = static_cast<const uint8_t *>(p);
+    }
+    void *d_ck;
+    const size_t ck_bytes = (len / 16384 + 16) * 8;
+    if ((rc = reserve(S_CK, ck_bytes, &d_ck)) != ZB_OK) return rc;
+    if (crc) CK(launch_crc32(d, len, start, d_ck, ck_bytes, d_check, st));
+    else CK(launch_adler32(d, len, start, d_ck, ck_bytes, d_check, st));
+    launches = 2;
+    CK(cudaMemcpyAsync(h_info, d_check, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ev1, st));
+    CK(cudaStreamSynchronize(st));
+    *out = *reinterpret_cast<uint32_t *>(h_info);
+    if (ms_out) CK(cudaEventElapsedTime(ms_out, ev0, ev1));
+    return ZB_OK;
+}
+
+__global__ void k_fill_random(uint64_t *dst, uint64_t nwords, uint64_t seed)
+{
+    // splitmix64 of the 8-byte index
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t z = (i + seed) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        dst[i] = z ^ (z >> 31);
+    }
+}
+
+} // namespace zb
+
+using zb::Engine;
+
+extern "C" {
+
+struct zb_engine { Engine e; };
+
+const char *zb_last_error(void) { return zb::g_err; }
+
+int zb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+zb_engine *zb_engine_create(int device, int *err)
+{
+    zb_engine *z = new (std::nothrow) zb_engine;
+    int rc = z ? z->e.init(device) : ZB_E_MEM;
+    if (err) *err = rc;
+    if (rc != ZB_OK) { delete z; return nullptr; }
+    return z;
+}
+
+void zb_engine_destroy(zb_engine *z) { delete z; }
+
+int zb_deflate(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev, int level, int strategy,
+               int window_bits, zb_deflate_result *res)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.deflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, level, strategy, window_bits, 0, res);
+}
+
+int zb_deflate_ex(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev, int level, int strategy,
+                  int window_bits, uint32_t flags, zb_deflate_result *res)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.deflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, level, strategy, window_bits, flags, res);
+}
+
+size_t zb_deflate_bound(size_t n) { return zb::deflate_bound(n); }
+
+int zb_inflate(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev, int window_bits,
+               zb_inflate_result *res)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.inflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, window_bits, res);
+}
+
+int zb_adler32(zb_engine *z, uint32_t start, const void *buf, size_t len, int on_dev, uint32_t *out, float *ms)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.checksum(false, start, buf, len, on_dev != 0, out, ms);
+}
+
+int zb_crc32(zb_engine *z, uint32_t start, const void *buf, size_t len, int on_dev, uint32_t *out, float *ms)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.checksum(true, start, buf, len, on_dev != 0, out, ms);
+}
+
+void zb_engine_set_profile(zb_engine *z, int on) { if (z) z->e.profile = on != 0; }
+
+int zb_engine_get_profile(zb_engine *z, float *ms, uint32_t *launches, int n)
+{
+    if (!z) return 0;
+    int k = n < Engine::kPhases ? n : Engine::kPhases;
+    for (int i = 0; i < k; i++) { if (ms) ms[i] = z->e.phase_ms[i]; if (launches) launches[i] = z->e.phase_launches[i]; }
+    return k;
+}
+
+void *zb_device_alloc(zb_engine *z, size_t bytes)
+{
+    if (!z) return nullptr;
+    cudaSetDevice(z->e.device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes + zb::kPad + 16) != cudaSuccess) return nullptr;
+    cudaMemset(static_cast<uint8_t *>(p) + bytes, 0, zb::kPad);
+    return p;
+}
+
+void zb_device_free(zb_engine *z, void *p)
+{
+    if (!z || !p) return;
+    cudaSetDevice(z->e.device);
+    cudaFree(p);
+}
+
+int zb_copy_to_device(zb_engine *z, void *dst, const void *src, size_t bytes)
+{
+    if (!z) return ZB_E_NODEVICE;
+    cudaSetDevice(z->e.device);
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? ZB_OK : ZB_E_CUDA;
+}
+
+int zb_copy_to_host(zb_engine *z, void *dst, const void *src, size_t bytes)
+{
+    if (!z) return ZB_E_NODEVICE;
+    cudaSetDevice(z->e.device);
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? ZB_OK : ZB_E_CUDA;
+}
+
+int zb_device_fill_random(zb_engine *z, void *dst, size_t bytes, uint64_t seed)
+{
+    if (!z) return ZB_E_NODEVICE;
+    cudaSetDevice(z->e.device);
+    zb::k_fill_random<<<148 * 8, 256, 0, z->e.st>>>(static_cast<uint64_t *>(dst), bytes / 8, seed);
+    return cudaStreamSynchronize(z->e.st) == cudaSuccess ? ZB_OK : ZB_E_CUDA;
+}
+
+} // extern "C"

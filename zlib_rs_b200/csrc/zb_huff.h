@@ -265,6 +265,8 @@ struct BlockDesc {
     uint32_t last;
     uint32_t hdr_bits;             // 3-bit block header + (dynamic) tree description
     uint32_t data_type;            // detect_data_type of this block's literals
+    uint32_t have_window;          // block_start >= 0 in window coordinates at flush time
+    uint32_t pad0;
     uint64_t body_bits;            // symbol bits + end-of-block code
     uint64_t bit_base;             // position of the block header in the output bit stream (set by the scan)
     uint16_t lcode[kLCodes];

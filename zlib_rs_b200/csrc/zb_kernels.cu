@@ -1,0 +1,668 @@
+// zb_kernels.cu -- CUDA kernels of the B200 deflate engine (compiled for sm_100a only).
+//
+// Pipeline for one level-3..6 job (DESIGN.md has the full picture):
+//   k_links      L[x]   : previous position with the same 4-byte hash (the reference's head/prev chains)
+//   k_match      M[x]   : longest_match for EVERY position, 64 KiB window + chains staged in shared memory
+//   k_nxt        nxt[p] : canonical macro step of the reference parser from every position
+//   k_path_*            : which positions the serial parser really visits (tile-local pointer jumping,
+//                         a short serial chain over tiles, then marking)
+//   k_emit              : symbols of the path nodes + the hole set they imply
+//   k_holes_cmp         : fixed-point test of the hole set (holes change M, M changes the path)
+//   k_tail              : exact serial simulation of the last ~1 KiB
+//   k_block_hist / k_build_blocks / k_scan_blocks / k_encode / k_finish : Huffman blocks and bit packing
+#include "zb_kernels.cuh"
+
+namespace zb {
+
+__constant__ HuffTables c_tab;
+
+cudaError_t upload_tables()
+{
+    HuffTables t;
+    init_tables(t);
+    return cudaMemcpyToSymbol(c_tab, &t, sizeof t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// accessors
+// ------------------------------------------------------------------------------------------------
+struct GAcc { // global memory, absolute coordinates
+    const uint8_t *data;
+    uint32_t N;
+    const uint16_t *L;
+    const uint32_t *holes;
+    const uint32_t *M;
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const
+    {
+        // bytes beyond the input are what the reference's window buffer still holds there
+        while (y >= N) {
+            if (y < 2 * kWSize) return 0;
+            y -= kWSize;
+        }
+        return data[y];
+    }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { return y + 4 <= N ? L[y] : 0; }
+    __device__ __forceinline__ bool inserted(uint32_t y) const { return !((holes[y >> 5] >> (y & 31)) & 1u); }
+    __device__ __forceinline__ Match mlook(uint32_t x) const
+    {
+        uint32_t v = M[x];
+        return Match{v >> 16, x - (v & 0xffffu)};
+    }
+};
+
+struct SAcc { // shared-memory window of k_match
+    const uint8_t *sdata;
+    const uint16_t *sL;
+    const uint32_t *sholes;
+    uint32_t ws; // absolute position of sdata[0]
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const { return sdata[y - ws]; }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { return sL[y - ws]; }
+    __device__ __forceinline__ bool inserted(uint32_t y) const
+    {
+        uint32_t i = y - ws;
+        return !((sholes[i >> 5] >> (i & 31)) & 1u);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_links: one warp per 32 KiB tile inserts positions in order into a shared-memory head table
+// (hash_calc.rs:40-59), 32 positions per step; __match_any_sync resolves equal hashes inside a step.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kLinksSmem = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
+
+__global__ void __launch_bounds__(32) k_links(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *head = reinterpret_cast<uint16_t *>(smem);
+    uint8_t *sd = smem + 65536 * 2;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t N = jb.N;
+    const uint32_t ts = blockIdx.x * kLinkTile;
+    const uint32_t te = min(ts + kLinkTile, N);
+    const uint32_t ws = ts > kLinkWarm ? ts - kLinkWarm : 0;
+    for (uint32_t i = lane; i < 32768; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
+    // stage [ws, te + 3) ; the input buffer is zero padded
+    const uint32_t nbytes = te + 3 - ws;
+    for (uint32_t i = lane * 4; i < nbytes; i += 128) {
+        uint32_t a = ws + i;
+        sd[i] = jb.in[a]; sd[i + 1] = jb.in[a + 1]; sd[i + 2] = jb.in[a + 2]; sd[i + 3] = jb.in[a + 3];
+    }
+    __syncwarp();
+    for (uint32_t base = ws; base < te; base += 32) {
+        const uint32_t x = base + lane;
+        const bool valid = x < te && x + 4 <= N;
+        uint32_t key = 0x10000u + lane;
+        if (valid) {
+            const uint8_t *q = sd + (x - ws);
+            key = hash_u32(q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24));
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t pred_rel = 0;
+        if (valid) {
+            const uint32_t lower = peers & ((1u << lane) - 1u);
+            if (lower) pred_rel = (base + (31 - __clz(lower))) - ws + 1;
+            else pred_rel = head[key];
+        }
+        __syncwarp();
+        if (valid) {
+            const uint32_t rel = x - ws + 1;
+            if (x >= ts) {
+                uint32_t d = pred_rel ? rel - pred_rel : 0;
+                jb.L[x] = (uint16_t)((d && d <= kMaxDist) ? d : 0);
+            }
+            if ((peers >> lane) == 1u) head[key] = (uint16_t)rel;
+        } else if (x < te && x >= ts) {
+            jb.L[x] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_match: M[x] for every x of a 32 KiB tile.  The tile plus the 32 KiB before it (data, chain links,
+// hole bits) are staged in shared memory; 1024 threads walk their chains independently.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMatchData = 2 * kWSize + 512;
+constexpr uint32_t kMatchSmem = kMatchData + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
+
+__global__ void __launch_bounds__(1024) k_match(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tile = blockIdx.x;
+    if (!jb.tile_dirty[tile]) return;
+    uint8_t *sdata = smem;
+    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kMatchData);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kMatchData + 2 * kWSize * 2);
+    const uint32_t N = jb.N;
+    const uint32_t ts = tile * kMatchTile;
+    const uint32_t te = min(ts + kMatchTile, N);
+    const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
+    const uint32_t tid = threadIdx.x;
+    // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
+    {
+        const uint32_t n16 = (te + 512 - ws + 15) / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
+        uint4 *dst = reinterpret_cast<uint4 *>(sdata);
+        for (uint32_t i = tid; i < n16 && i < kMatchData / 16; i += 1024) dst[i] = src[i];
+        const uint32_t nl = (te - ws + 7) / 8; // 8 links per uint4
+        const uint4 *ls = reinterpret_cast<const uint4 *>(jb.L + ws);
+        uint4 *ld = reinterpret_cast<uint4 *>(sL);
+        for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
+        const uint32_t nw = (te - ws + 31) / 32;
+        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
+    }
+    __syncthreads();
+    SAcc a{sdata, sL, sh, ws};
+    const LevelParams lp = jb.lp;
+    for (uint32_t x = ts + tid; x < te; x += 1024) {
+        uint32_t v = 0;
+        if (x + kMSafe <= N) {
+            Match m = lm_walk(a, x, 0xffffffffu, lp);
+            if (m.len) v = (m.len << 16) | (x - m.start);
+        }
+        jb.M[x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_nxt: canonical macro step from every position below the tail zone.
+// nxt[p] = delta (16 bits) | symbols emitted (8 bits) << 16 | kNxtTail
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= jb.tail_start) return;
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    uint32_t ns = 0;
+    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [](const Sym &) {}, &ns);
+    const uint32_t delta = np - p;
+    if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
+    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (np >= jb.tail_start ? kNxtTail : 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// path: tile-local resolution of "where does the parser leave this sub-tile/tile when it enters at p"
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kStuck = 0x80000000u;
+
+// Level 0 for one sub-tile [s0, s1) (tile-relative), executed by one warp.  nx: packed nxt values.
+// ex[p]: first path position >= s1 (tile-relative) or kStuck | tail-entry position; cn[p]: symbols on the way.
+__device__ __forceinline__ void path_subtile(const uint32_t *nx, uint32_t *ex, uint32_t *cn, uint32_t s0, uint32_t s1, uint32_t lane)
+{
+    for (int32_t b = (int32_t)s1 - 32; b >= (int32_t)s0; b -= 32) {
+        const uint32_t p = (uint32_t)b + lane;
+        const uint32_t v = nx[p];
+        uint32_t t, c;
+        if (v & kNxtTail) { t = kStuck | p; c = 0; }
+        else { t = p + (v & 0xffffu); c = (v >> 16) & 0xffu; }
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const bool inb = !(t & kStuck) && t < (uint32_t)b + 32u;
+            const uint32_t src = inb ? t - (uint32_t)b : lane;
+            const uint32_t t2 = __shfl_sync(0xffffffffu, t, src);
+            const uint32_t c2 = __shfl_sync(0xffffffffu, c, src);
+            if (inb) { t = t2; c += c2; }
+        }
+        if (!(t & kStuck) && t < s1) { c += cn[t]; t = ex[t]; }
+        ex[p] = t;
+        cn[p] = c;
+        __syncwarp();
+    }
+}
+
+constexpr uint32_t kPathSmem = kPathTile * 4 * 3;
+
+// Stage nxt of the tile; positions at or beyond tail_start behave as tail entries.
+__device__ __forceinline__ void path_load(const JobBufs &jb, uint32_t tbeg, uint32_t *nx)
+{
+    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
+        const uint32_t p = tbeg + i;
+        nx[i] = p < jb.tail_start ? jb.nxt[p] : (kNxtTail | 1u);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *nx = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *ex = nx + kPathTile;
+    uint32_t *cn = ex + kPathTile;
+    const uint32_t tbeg = blockIdx.x * kPathTile;
+    path_load(jb, tbeg, nx);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t nsub = kPathTile / kPathSub;
+    for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
+    __syncthreads();
+    // compose sub-tiles from the back: afterwards ex[p] >= kPathTile or stuck
+    for (int32_t j = (int32_t)nsub - 2; j >= 0; j--) {
+        for (uint32_t i = threadIdx.x; i < kPathSub; i += blockDim.x) {
+            const uint32_t p = (uint32_t)j * kPathSub + i;
+            uint32_t t = ex[p];
+            if (!(t & kStuck) && t < kPathTile) { cn[p] += cn[t]; ex[p] = ex[t]; }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
+        const uint32_t p = tbeg + i;
+        if (p < jb.tail_start) {
+            const uint32_t t = ex[i];
+            jb.pexit[p] = (t & kStuck) ? (kStuck | (tbeg + (t & ~kStuck))) : tbeg + t;
+            jb.pcnt[p] = cn[i];
+        }
+    }
+}
+
+// One thread follows the tile exits from position 0.
+__global__ void k_path_chain(JobBufs jb, uint32_t ntiles)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t e = 0, base = 0;
+    bool done = jb.tail_start == 0;
+    uint32_t tail_entry = 0;
+    for (uint32_t t = 0; t < ntiles; t++) {
+        const uint32_t tend = (t + 1) * kPathTile;
+        jb.tile_symbase[t] = base;
+        if (done || e >= tend || e >= jb.tail_start) { jb.tile_entry[t] = 0xffffffffu; continue; }
+        jb.tile_entry[t] = e;
+        const uint32_t x = jb.pexit[e];
+        base += jb.pcnt[e];
+        if (x & kStuck) { tail_entry = x & ~kStuck; done = true; }
+        else e = x;
+    }
+    if (!done) { tail_entry = e; if (e < jb.tail_start) atomicOr(&jb.info->error, 2u); }
+    jb.info->tail_entry = tail_entry;
+    jb.info->n_mid_syms = base;
+}
+
+// Mark the path nodes of a tile: symidx[p] = 1 + index of the node's first symbol.
+__global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *nx = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *ex = nx + kPathTile;
+    uint32_t *cn = ex + kPathTile;
+    __shared__ uint32_t sub_entry[kPathTile / kPathSub], sub_base[kPathTile / kPathSub];
+    const uint32_t tbeg = blockIdx.x * kPathTile;
+    const uint32_t entry = jb.tile_entry[blockIdx.x];
+    constexpr uint32_t nsub = kPathTile / kPathSub;
+    if (entry == 0xffffffffu) { // no path node starts in this tile
+        for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
+            if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = 0;
+        return;
+    }
+    path_load(jb, tbeg, nx);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t cur = entry - tbeg, cbase = jb.tile_symbase[blockIdx.x];
+        for (uint32_t j = 0; j < nsub; j++) {
+            if (!(cur & kStuck) && cur < (j + 1) * kPathSub) {
+                sub_entry[j] = cur;
+                sub_base[j] = cbase;
+                cbase += cn[cur];
+                cur = ex[cur];
+            } else sub_entry[j] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) ex[i] = 0; // ex becomes the mark array
+    __syncthreads();
+    if (lane == 0) {
+        for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) {
+            uint32_t p = sub_entry[s];
+            if (p == 0xffffffffu) continue;
+            uint32_t idx = sub_base[s];
+            const uint32_t s1 = (s + 1) * kPathSub;
+            while (p < s1) {
+                const uint32_t v = nx[p];
+                if (v & kNxtTail) break; // the tail entry is emitted by k_tail
+                ex[p] = idx + 1;
+                idx += (v >> 16) & 0xffu;
+                p += v & 0xffffu;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
+        if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = ex[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emit: every path node re-runs its macro step, writes its symbols and records the holes it leaves
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_emit(JobBufs jb)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= jb.tail_start) return;
+    const uint32_t idx = jb.symidx[p];
+    if (!idx) return;
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    uint32_t k = idx - 1, ns = 0;
+    const uint32_t long_len = 16 * jb.lp.lazy;
+    Sym *syms = jb.syms;
+    uint32_t *hn = jb.holes_new;
+    macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+        syms[k++] = s;
+        if (s.dist && (uint32_t)s.lc + 3u > long_len) {
+            // interior positions pos+1 .. pos+len-2 are never inserted (medium.rs:251-261)
+            uint32_t y0 = s.pos + 1, y1 = s.pos + s.lc + 3u - 1; // [y0, y1)
+            while (y0 < y1) {
+                const uint32_t w = y0 >> 5, lo = y0 & 31;
+                const uint32_t n = min(32u - lo, y1 - y0);
+                const uint32_t mask = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << lo;
+                atomicOr(&hn[w], mask);
+                y0 += n;
+            }
+        }
+    }, &ns);
+}
+
+// holes := holes_new; report change and the match tiles whose window saw it
+__global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, uint32_t nmtiles)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    const uint32_t a = jb.holes[w], b = jb.holes_new[w];
+    if (a != b) {
+        jb.info->holes_changed = 1;
+        const uint32_t t = (w * 32) / kMatchTile;
+        jb.tile_dirty[t] = 1;
+        if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
+        jb.holes[w] = b;
+    }
+    jb.holes_new[w] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tail: exact serial simulation from the tail entry to the end of the stream (one thread).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_tail(JobBufs jb)
+{
+    __shared__ uint32_t ins[1024];
+    if (threadIdx.x != 0) return;
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    const uint32_t p0 = jb.info->tail_entry;
+    const uint32_t n_mid = jb.info->n_mid_syms;
+    uint32_t k = 0;
+    Sym *syms = jb.syms + n_mid;
+    uint32_t *sb = jb.sym_base;
+    if (jb.N - p0 > 1024u * 32u - 64u) { atomicOr(&jb.info->error, 4u); return; }
+    const uint32_t fb = serial_medium(a, jb.N, p0, ins, 1024u, jb.lp, [&](const Sym &s, uint32_t B) {
+        syms[k] = s;
+        sb[k] = B;
+        k++;
+    });
+    jb.info->n_syms = n_mid + k;
+    jb.info->final_base = fb;
+    jb.info->n_blocks = (n_mid + k) / kBlockSyms + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// blocks
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sym_end(const Sym &s) { return s.pos + (s.dist ? (uint32_t)s.lc + 3u : 1u); }
+
+__global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /* nblocks x 320 */)
+{
+    __shared__ uint32_t lf[kLCodes], df[kDCodes];
+    const uint32_t b = blockIdx.x;
+    const uint32_t nsyms = jb.info->n_syms, nblocks = jb.info->n_blocks;
+    for (uint32_t i = threadIdx.x; i < kLCodes; i += blockDim.x) lf[i] = 0;
+    if (threadIdx.x < kDCodes) df[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t begin = b * kBlockSyms;
+    const uint32_t count = (b + 1 < nblocks) ? kBlockSyms : nsyms - begin;
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        const Sym s = jb.syms[begin + i];
+        if (s.dist == 0) atomicAdd(&lf[s.lc], 1u);
+        else {
+            atomicAdd(&lf[257 + c_tab.length_code[s.lc]], 1u);
+            atomicAdd(&df[d_code(c_tab, s.dist - 1u)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kLCodes; i += blockDim.x) freq[b * 320 + i] = lf[i];
+    if (threadIdx.x < kDCodes) freq[b * 320 + kLCodes + threadIdx.x] = df[threadIdx.x];
+    if (threadIdx.x == 0) {
+        BlockDesc &bd = jb.blocks[b];
+        const bool last = b + 1 == nblocks;
+        bd.sym_begin = begin;
+        bd.sym_count = count;
+        bd.last = last && !jb.not_last;
+        const uint32_t start = begin == 0 ? 0 : sym_end(jb.syms[begin - 1]);
+        const uint32_t end = last ? jb.N : sym_end(jb.syms[begin + count - 1]);
+        bd.in_start = start;
+        bd.in_len = end - start;
+        uint32_t Bf;
+        if (last) Bf = jb.info->final_base;
+        else {
+            const uint32_t li = begin + count - 1, n_mid = jb.info->n_mid_syms;
+            if (jb.huffman_only) {
+                const uint32_t q = jb.syms[li].pos;
+                Bf = q < 2 * kWSize ? 0 : kWSize * (1 + (q - 2 * kWSize) / kWSize);
+            } else Bf = li < n_mid ? wbase(jb.syms[li].pos) : jb.sym_base[li - n_mid];
+        }
+        bd.have_window = start >= Bf;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_build_blocks(JobBufs jb, const uint32_t *freq)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= jb.info->n_blocks) return;
+    build_block(c_tab, jb.scratch[b], jb.blocks[b], freq + b * 320, freq + b * 320 + kLCodes, jb.blocks[b].have_window != 0,
+                jb.strategy_fixed != 0);
+}
+
+__global__ void k_scan_blocks(JobBufs jb)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t nb = jb.info->n_blocks;
+    uint64_t bit = 8ull * jb.hdr_len;
+    for (uint32_t b = 0; b < nb; b++) {
+        jb.blocks[b].bit_base = bit;
+        bit = block_end_bit(jb.blocks[b], bit);
+    }
+    if (jb.not_last) { // Z_SYNC_FLUSH framing: empty stored block, byte aligned (deflate.rs:2733-2738)
+        const uint64_t p = (bit + 3 + 7) & ~7ull;
+        jb.info->marker_byte = p >> 3;
+        bit = p + 32;
+    }
+    jb.info->total_bits = bit;
+    const uint64_t bytes = ((bit + 7) >> 3) + (jb.wrap == 1 ? 4 : jb.wrap == 2 ? 8 : 0);
+    jb.info->out_bytes = bytes;
+    jb.info->data_type = jb.blocks[0].sym_count ? jb.blocks[0].data_type : 2u;
+    if (bytes > jb.out_cap) { atomicOr(&jb.info->error, 8u); return; }
+    if (jb.wrap == 1) {
+        // zlib header (deflate.rs:1572-1601)
+        const uint32_t lf = (jb.huffman_only || jb.level < 2) ? 0 : jb.level < 6 ? 1 : jb.level == 6 ? 2 : 3;
+        uint32_t h = ((8u + (7u << 4)) << 8) | (lf << 6);
+        h += 31 - (h % 31);
+        jb.out[0] = (uint8_t)(h >> 8);
+        jb.out[1] = (uint8_t)h;
+    } else if (jb.wrap == 2) {
+        // gzip header without gz_header (deflate.rs:2574-2599): 1f 8b 08 00 mtime(0) xfl os(3 = unix)
+        const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, (uint8_t)jb.xfl, 3};
+        for (int i = 0; i < 10; i++) jb.out[i] = g[i];
+    }
+}
+
+// OR `n` (<= 57) bits of `val` into the output at bit position `pos`.  The output was zeroed.
+__device__ __forceinline__ void or_bits(uint32_t *out32, uint64_t pos, uint64_t val, uint32_t n)
+{
+    if (n == 0) return;
+    const uint64_t w = pos >> 5;
+    const uint32_t sh = (uint32_t)(pos & 31);
+    atomicOr(&out32[w], (uint32_t)(val << sh));
+    if (sh + n > 32) {
+        atomicOr(&out32[w + 1], (uint32_t)(val >> (32 - sh)));
+        if (sh + n > 64) atomicOr(&out32[w + 2], (uint32_t)(val >> (64 - sh)));
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_encode(JobBufs jb)
+{
+    __shared__ HuffTables st;
+    __shared__ uint16_t s_lcode[kLCodes], s_dcode[kDCodes];
+    __shared__ uint8_t s_llen[kLCodes], s_dlen[kDCodes];
+    __shared__ uint64_t warp_sum[32];
+    if (jb.info->error) return;
+    const BlockDesc &bd = jb.blocks[blockIdx.x];
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(jb.out);
+    const uint32_t tid = threadIdx.x;
+    if (bd.type == 0) {
+        // stored block (deflate.rs:1734-1763)
+        const uint64_t p = ((bd.bit_base + 3 + 7) >> 3);
+        const uint32_t sl = (uint16_t)bd.in_len;
+        if (tid == 0) {
+            or_bits(out32, bd.bit_base, bd.hdr[0] & 7u, 3);
+            jb.out[p] = (uint8_t)sl;
+            jb.out[p + 1] = (uint8_t)(sl >> 8);
+            jb.out[p + 2] = (uint8_t)~sl;
+            jb.out[p + 3] = (uint8_t)((~sl) >> 8);
+        }
+        for (uint32_t i = tid; i < sl; i += blockDim.x) jb.out[p + 4 + i] = jb.in[bd.in_start + i];
+        return;
+    }
+    for (uint32_t i = tid; i < sizeof(HuffTables) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&st)[i] = reinterpret_cast<const uint32_t *>(&c_tab)[i];
+    for (uint32_t i = tid; i < kLCodes; i += blockDim.x) { s_lcode[i] = bd.lcode[i]; s_llen[i] = bd.llen[i]; }
+    if (tid < kDCodes) { s_dcode[tid] = bd.dcode[tid]; s_dlen[tid] = bd.dlen[tid]; }
+    __syncthreads();
+    // header bits, 32 per thread
+    for (uint32_t wi = tid; wi * 32 < bd.hdr_bits; wi += blockDim.x) {
+        uint32_t v = bd.hdr[wi * 4] | (bd.hdr[wi * 4 + 1] << 8) | (bd.hdr[wi * 4 + 2] << 16) | ((uint32_t)bd.hdr[wi * 4 + 3] << 24);
+        const uint32_t n = min(32u, bd.hdr_bits - wi * 32);
+        if (n < 32) v &= (1u << n) - 1u;
+        or_bits(out32, bd.bit_base + wi * 32ull, v, n);
+    }
+    // symbols: kSymsPerThread consecutive symbols per thread (the end-of-block code is symbol #sym_count)
+    const uint32_t first = tid * kSymsPerThread;
+    const uint32_t total = bd.sym_count + 1;
+    uint64_t vals[kSymsPerThread];
+    uint8_t lens[kSymsPerThread];
+    uint32_t mybits = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kSymsPerThread; j++) {
+        const uint32_t i = first + j;
+        uint64_t v = 0;
+        uint32_t n = 0;
+        if (i < bd.sym_count) {
+            const Sym s = jb.syms[bd.sym_begin + i];
+            if (s.dist == 0) { v = s_lcode[s.lc]; n = s_llen[s.lc]; }
+            else {
+                uint32_t code = st.length_code[s.lc];
+                v = s_lcode[code + 257];
+                n = s_llen[code + 257];
+                uint32_t extra = extra_lbits(code);
+                if (extra) { v |= (uint64_t)(s.lc - st.base_length[code]) << n; n += extra; }
+                const uint32_t d = s.dist - 1u;
+                code = st.dist_code[d < 256 ? d : 256 + (d >> 7)];
+                uint64_t dv = s_dcode[code];
+                uint32_t dn = s_dlen[code];
+                extra = extra_dbits(code);
+                if (extra) { dv |= (uint64_t)(d - st.base_dist[code]) << dn; dn += extra; }
+                v |= dv << n;
+                n += dn;
+            }
+        } else if (i + 1 == total) { v = s_lcode[kEndBlock]; n = s_llen[kEndBlock]; }
+        vals[j] = v;
+        lens[j] = (uint8_t)n;
+        mybits += n;
+    }
+    // exclusive scan of mybits over the block
+    uint64_t incl = mybits;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t ws = warp_sum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, ws, o);
+            if ((int)lane >= o) ws += t;
+        }
+        warp_sum[lane] = ws;
+    }
+    __syncthreads();
+    uint64_t pos = bd.bit_base + bd.hdr_bits + (incl - mybits) + (warp ? warp_sum[warp - 1] : 0);
+    if (tid == blockDim.x - 1 && warp_sum[31] != bd.body_bits) atomicOr(&jb.info->error, 16u);
+#pragma unroll
+    for (uint32_t j = 0; j < kSymsPerThread; j++) {
+        or_bits(out32, pos, vals[j], lens[j]);
+        pos += lens[j];
+    }
+}
+
+__global__ void k_finish(JobBufs jb, const uint32_t *check)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (jb.info->error) return;
+    const uint64_t p = (jb.info->total_bits + 7) >> 3;
+    const uint32_t a = *check;
+    if (jb.not_last) { jb.out[jb.info->marker_byte + 2] = 0xff; jb.out[jb.info->marker_byte + 3] = 0xff; }
+    if (jb.wrap == 1) { // adler32, big endian (deflate.rs:2786-2789)
+        jb.out[p] = (uint8_t)(a >> 24);
+        jb.out[p + 1] = (uint8_t)(a >> 16);
+        jb.out[p + 2] = (uint8_t)(a >> 8);
+        jb.out[p + 3] = (uint8_t)a;
+    } else if (jb.wrap == 2) { // crc32 + isize, little endian (deflate.rs:2773-2785)
+        for (int i = 0; i < 4; i++) jb.out[p + i] = (uint8_t)(a >> (8 * i));
+        for (int i = 0; i < 4; i++) jb.out[p + 4 + i] = (uint8_t)(jb.N >> (8 * i));
+    }
+    jb.info->adler = a;
+}
+
+// Z_HUFFMAN_ONLY (deflate/algorithm/huff.rs): every byte is a literal symbol.
+__global__ void __launch_bounds__(256) k_literal_syms(JobBufs jb)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) {
+        jb.info->n_mid_syms = jb.N;
+        jb.info->n_syms = jb.N;
+        jb.info->n_blocks = jb.N / kBlockSyms + 1;
+        // deflate_huff refills only when lookahead == 0: the base moves when strstart reaches 64 KiB + k*32 KiB
+        jb.info->final_base = jb.N < 2 * kWSize ? 0 : kWSize * (1 + (jb.N - 2 * kWSize) / kWSize);
+    }
+    if (p < jb.N) jb.syms[p] = Sym{0, jb.in[p], p};
+}
+
+// level 0 (deflate/algorithm/stored.rs, one-shot with ample output): stored blocks of 65535 bytes.
+__global__ void __launch_bounds__(256) k_stored(JobBufs jb)
+{
+    const uint32_t N = jb.N;
+    const uint32_t nb = N == 0 ? 1 : (N + 65534) / 65535;
+    const uint32_t b = blockIdx.x;
+    if (b >= nb) return;
+    const uint32_t start = b * 65535u;
+    const uint32_t len = min(65535u, N - start);
+    uint8_t *o = jb.out + jb.hdr_len + (uint64_t)b * (65535u + 5u);
+    if (threadIdx.x == 0) {
+        o[0] = b + 1 == nb ? 1 : 0;
+        o[1] = (uint8_t)len;
+        o[2] = (uint8_t)(len >> 8);
+        o[3] = (uint8_t)~len;
+        o[4] = (uint8_t)((~len) >> 8);
+        if (b == 0) {
+            jb.info->total_bits = 8ull * (jb.hdr_len + (uint64_t)N + 5ull * nb);
+            jb.info->out_bytes = jb.hdr_len + (uint64_t)N + 5ull * nb + (jb.wrap == 1 ? 4 : jb.wrap == 2 ? 8 : 0);
+            jb.info->data_type = 2;
+            if (jb.wrap == 1) { jb.out[0] = 0x78; jb.out[1] = 0x01; }
+            else if (jb.wrap == 2) {
+                const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, 4, 3};
+                for (int i = 0; i < 10; i++) jb.out[i] = g[i];
+            }
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) o[5 + i] = jb.in[start + i];
+}
+
+} // namespace zb

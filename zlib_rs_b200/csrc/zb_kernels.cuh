@@ -1,0 +1,74 @@
+// zb_kernels.cuh -- CUDA kernels of the B200 deflate engine (sm_100a).  See DESIGN.md for the data
+// flow.  All device logic that has reference semantics lives in zb_core.h / zb_huff.h; the kernels
+// here provide the parallel schedule, shared-memory staging and the bit packing.
+#pragma once
+#include <cuda_runtime.h>
+#include "zb_core.h"
+#include "zb_huff.h"
+
+namespace zb {
+
+constexpr uint32_t kLinkTile = 32768;   // positions per k_links CTA
+constexpr uint32_t kLinkWarm = 32512;   // warm-up positions before the tile (>= kMaxDist)
+constexpr uint32_t kMatchTile = 32768;  // positions per k_match CTA
+constexpr uint32_t kPathTile = 16384;   // positions per path tile
+constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
+constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
+constexpr uint32_t kSymsPerThread = 16;
+
+struct JobInfo {              // device-resident result / control block of one deflate job
+    uint32_t n_mid_syms;      // symbols produced by the canonical path (before the tail)
+    uint32_t tail_entry;      // canonical node where the serial tail starts
+    uint32_t n_syms;          // total symbols
+    uint32_t final_base;      // window base when the last block is flushed
+    uint32_t holes_changed;   // iteration control
+    uint32_t n_blocks;
+    uint32_t data_type;
+    uint32_t error;           // non-zero: internal invariant violated
+    uint64_t total_bits;      // bits of header + all blocks (before final alignment)
+    uint64_t out_bytes;       // final stream length
+    uint32_t adler;
+    uint32_t pad;
+    uint64_t marker_byte;     // not_last: byte offset of the empty stored block's LEN field
+};
+
+// One deflate job's device buffers (see DESIGN.md "HBM layout").
+struct JobBufs {
+    const uint8_t *in;    // N + kPad bytes, zero padded
+    uint32_t N;
+    uint32_t tail_start;
+    uint16_t *L;          // N + kPad
+    uint32_t *holes;      // bitmap, (N >> 5) + 2 words
+    uint32_t *holes_new;
+    uint32_t *M;          // N + kPad
+    uint32_t *nxt;        // N
+    uint32_t *pexit;      // N   exit position of the tile-local path from p
+    uint32_t *pcnt;       // N   symbols on that path
+    uint32_t *symidx;     // N   1 + index of the first symbol emitted by the path node at p, 0 = not on path
+    uint32_t *tile_entry; // path tiles: entry position (or 0xffffffff)
+    uint32_t *tile_symbase;
+    uint8_t *tile_dirty;  // match tiles
+    Sym *syms;            // N + 64
+    uint32_t *sym_base;   // window base per symbol (tail symbols only; index relative to n_mid_syms)
+    BlockDesc *blocks;
+    TreeScratch *scratch;
+    uint8_t *out;         // output stream
+    uint64_t out_cap;
+    JobInfo *info;
+    LevelParams lp;
+    uint32_t level;
+    uint32_t strategy_fixed;
+    uint32_t wrap;            // 0 raw deflate, 1 zlib, 2 gzip (deflate.rs:286-298)
+    uint32_t hdr_len;         // bytes before the first block: 0 / 2 / 10
+    uint32_t xfl;             // gzip extra flags byte
+    uint32_t huffman_only;    // Z_HUFFMAN_ONLY: symbols are all literals (algorithm/huff.rs)
+    uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
+};
+
+cudaError_t upload_tables();
+cudaError_t launch_adler32(const uint8_t *d_buf, uint64_t len, uint32_t start, void *d_scratch, size_t scratch_bytes, uint32_t *d_out,
+                           cudaStream_t st);
+cudaError_t launch_crc32(const uint8_t *d_buf, uint64_t len, uint32_t start, void *d_scratch, size_t scratch_bytes, uint32_t *d_out,
+                         cudaStream_t st);
+
+} // namespace zb
