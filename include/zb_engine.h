@@ -82,7 +82,7 @@ ZB_API int zb_crc32(zb_engine *e, uint32_t start, const void *buf, size_t len, i
 
 /* Per-phase device timing of the last zb_deflate call (CUDA events around each kernel group; adds a sync per
  * phase, so only for measurement).  Phases: 0 links, 1 match, 2 nxt, 3 path, 4 emit+holes, 5 tail, 6 blocks,
- * 7 encode, 8 checksum, 9 h2d, 10 d2h. */
+ * 7 encode, 8 checksum, 9 h2d, 10 d2h, 11 first (full) match launch. */
 ZB_API void zb_engine_set_profile(zb_engine *e, int on);
 ZB_API int zb_engine_get_profile(zb_engine *e, float *ms, uint32_t *launches, int n);
 

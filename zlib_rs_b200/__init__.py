@@ -369,7 +369,7 @@ class Engine:
         self._check(lib().zb_crc32(self.h, start, buf, n, int(on_device), ctypes.byref(out), ctypes.byref(ms)))
         return out.value, ms.value
 
-    PHASES = ["links", "match", "nxt", "path", "emit_holes", "tail", "blocks", "encode", "checksum", "h2d", "d2h"]
+    PHASES = ["links", "match", "nxt", "path", "emit_holes", "tail", "blocks", "encode", "checksum", "h2d", "d2h", "match_first"]
 
     def set_profile(self, on=True):
         lib().zb_engine_set_profile(self.h, int(on))

@@ -207,6 +207,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.info = d_info;
     jb.level = (uint32_t)level;
     jb.strategy_fixed = strategy == 4;
+    const bool lf_zero = strategy >= 2; // header flag rule shared by HuffmanOnly / Rle / Fixed
     jb.wrap = wrap;
     jb.hdr_len = wrap == 1 ? 2 : wrap == 2 ? 10 : 0;
     jb.huffman_only = strategy == 2 && level != 0;
@@ -223,6 +224,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     }
     jb.lp = level_params(eng_level);
     if (level != 0 && !jb.huffman_only) jb.level = (uint32_t)level; // header flag bits follow the requested level
+    if (lf_zero && !jb.strategy_fixed && !jb.huffman_only) jb.level = 1;   // Z_RLE: FLEVEL 0 like the reference
 
     CK(cudaEventRecord(ev0, st));
     if (profile) { for (int i = 0; i < kPhases; i++) { phase_ms[i] = 0; phase_launches[i] = 0; } }
@@ -268,6 +270,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     pbegin();
                     k_match<<<nmt, 1024, kMatchSmemBytes, st>>>(jb);
                     pend(1, 1);
+                    if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();
                     k_nxt<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
                     pend(2, 1);

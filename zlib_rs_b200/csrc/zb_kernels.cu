@@ -478,7 +478,8 @@ __global__ void k_scan_blocks(JobBufs jb)
     if (bytes > jb.out_cap) { atomicOr(&jb.info->error, 8u); return; }
     if (jb.wrap == 1) {
         // zlib header (deflate.rs:1572-1601)
-        const uint32_t lf = (jb.huffman_only || jb.level < 2) ? 0 : jb.level < 6 ? 1 : jb.level == 6 ? 2 : 3;
+        // level_flags (deflate.rs:1591-1601): strategy >= HuffmanOnly or level < 2 -> 0
+        const uint32_t lf = (jb.huffman_only || jb.strategy_fixed || jb.level < 2) ? 0 : jb.level < 6 ? 1 : jb.level == 6 ? 2 : 3;
         uint32_t h = ((8u + (7u << 4)) << 8) | (lf << 6);
         h += 31 - (h % 31);
         jb.out[0] = (uint8_t)(h >> 8);
