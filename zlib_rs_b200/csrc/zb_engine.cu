@@ -45,6 +45,7 @@ __global__ void k_stored(JobBufs);
 constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
 constexpr uint32_t kMatchSmemBytes = (2 * kWSize + 512) + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
+constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
 
 int Engine::init(int dev)
 {
@@ -65,6 +66,7 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
+    CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
     CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_check, 16));
@@ -132,7 +134,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -185,6 +187,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_PEXIT, ((size_t)N + 16) * 4, pexit, uint32_t *)
     RES(S_PCNT, ((size_t)N + 16) * 4, pcnt, uint32_t *)
     RES(S_SYMIDX, ((size_t)N + 16) * 4, symidx, uint32_t *)
+    RES(S_PHEAD, (size_t)npt * kPathHead * 8, phead, uint2 *)
     RES(S_TENTRY, (size_t)npt * 4, tile_entry, uint32_t *)
     RES(S_TSYMB, (size_t)npt * 4, tile_symbase, uint32_t *)
     RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
@@ -276,7 +279,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     pend(2, 1);
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
-                    k_path_chain<<<1, 32, 0, st>>>(jb, npt);
+                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt);
                     k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
                     pend(3, 3);
                     pbegin();
@@ -305,7 +308,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         if (nblocks == 0 || nblocks > max_blocks) { snprintf(g_err, sizeof g_err, "bad block count %u", nblocks); return ZB_E_INTERNAL; }
         pbegin();
         k_block_hist<<<nblocks, 256, 0, st>>>(jb, d_freq);
-        k_build_blocks<<<(nblocks + 31) / 32, 32, 0, st>>>(jb, d_freq);
+        k_build_blocks<<<nblocks, 32, 0, st>>>(jb, d_freq);
         k_scan_blocks<<<1, 32, 0, st>>>(jb);
         pend(6, 3);
         pbegin();

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
 
 #define NEED(nb) do { while (bits < (nb)) { hold |= (uint64_t)((ipos < n) ? S.in[ipos & (kInRing - 1)] : 0) << bits; ipos++; bits += 8; } } while (0)
 #define BITS(nb) ((uint32_t)(hold & ((1ull << (nb)) - 1)))
-#define DROP(nb) do { hold >>= (nb); bits -= (nb); consumed_bits += (nb); } while (0)
+#define DROP(nb) do { const uint32_t nb_ = (nb); hold >>= nb_; bits -= nb_; consumed_bits += nb_; } while (0)
 #define FAIL(code) do { err = (code); mode = 5; } while (0)
 
     for (;;) {

@@ -125,9 +125,78 @@ __global__ void __launch_bounds__(32) k_links(JobBufs jb)
 constexpr uint32_t kMatchData = 2 * kWSize + 512;
 constexpr uint32_t kMatchSmem = kMatchData + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
 
+// Unaligned little-endian 32-bit load from the staged window (two aligned LDS + funnel shift).
+__device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte_idx)
+{
+    const uint32_t w = byte_idx >> 2;
+    return __funnelshift_r(words[w], words[w + 1], (byte_idx & 3u) * 8u);
+}
+
+// Levels 5/6 (no early exit): every lane runs a uniform step loop -- one chain candidate, or one 4-byte
+// compare step, per iteration -- and moves on to its next position as soon as one is finished, so lanes
+// with short chains do not wait for lanes with long ones.  Semantics are those of lm_walk():
+// a candidate replaces the best match iff its common prefix (<= 258) is strictly longer; the walk stops
+// at nice_match, at the chain budget, or when the chain leaves the window.  The 4-byte test at offset
+// best-3 is only a filter for that condition (cf. longest_match.rs:198-234).
+__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
+                                                uint32_t ws, uint32_t ts, uint32_t te, bool tile_has_holes)
+{
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
+    const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
+    uint32_t x = ts + threadIdx.x;
+    bool have = false;
+    uint32_t cur = 0, best = 2, chain = 0, res = 0, xw = 0, clen = 0, cand = 0;
+    bool first = true, comparing = false;
+    for (;;) {
+        if (!have) {
+            if (x >= te) break;
+            if (x + kMSafe > N) { jb.M[x] = 0; x += 1024; continue; }
+            cur = x; best = 2; chain = budget; res = 0; first = true; comparing = false;
+            xw = lds_u32(words, x - ws) & 0x00ffffffu; // bytes 0..2: the filter for best == 2
+            have = true;
+        }
+        if (comparing) {
+            const uint32_t a = lds_u32(words, x - ws + clen), b = lds_u32(words, cand - ws + clen);
+            const uint32_t diff = a ^ b;
+            uint32_t len;
+            if (diff == 0 && clen + 4 < kMaxMatch) { clen += 4; continue; }
+            len = diff ? clen + ((__ffs(diff) - 1) >> 3) : clen + 4;
+            if (len > kMaxMatch) len = kMaxMatch;
+            comparing = false;
+            if (len > best) {
+                best = len;
+                res = (len << 16) | (x - cand);
+                if (best >= nice) { jb.M[x] = res; have = false; x += 1024; continue; }
+                xw = lds_u32(words, x - ws + best - 3);
+            }
+            if (--chain == 0) { jb.M[x] = res; have = false; x += 1024; }
+            continue;
+        }
+        // next chain entry
+        const uint32_t d = sL[cur - ws];
+        bool stop = d == 0;
+        if (!stop) {
+            cur -= d;
+            const uint32_t dist = x - cur;
+            stop = dist > (first ? kMaxDist : kMaxDist - 1) || cur == 0;
+        }
+        if (stop) { jb.M[x] = res; have = false; x += 1024; continue; }
+        if (tile_has_holes) {
+            const uint32_t i = cur - ws;
+            if ((sh[i >> 5] >> (i & 31)) & 1u) continue; // a hole is not on the chain
+        }
+        first = false;
+        uint32_t cw = lds_u32(words, cur - ws + (best == 2 ? 0u : best - 3u));
+        if (best == 2) cw &= 0x00ffffffu;
+        if (cw == xw) { comparing = true; cand = cur; clen = 0; continue; }
+        if (--chain == 0) { jb.M[x] = res; have = false; x += 1024; }
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_any_hole;
     const uint32_t tile = blockIdx.x;
     if (!jb.tile_dirty[tile]) return;
     uint8_t *sdata = smem;
@@ -138,6 +207,8 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     const uint32_t te = min(ts + kMatchTile, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_any_hole = 0;
+    __syncthreads();
     // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
     {
         const uint32_t n16 = (te + 512 - ws + 15) / 16;
@@ -149,11 +220,17 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
         const uint32_t nw = (te - ws + 31) / 32;
-        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
+        uint32_t any = 0;
+        for (uint32_t i = tid; i < nw; i += 1024) { const uint32_t w = jb.holes[(ws >> 5) + i]; sh[i] = w; any |= w; }
+        if (any) s_any_hole = 1;
     }
     __syncthreads();
-    SAcc a{sdata, sL, sh, ws};
     const LevelParams lp = jb.lp;
+    if (!lp.early_exit) {
+        match_tile_fast(jb, sdata, sL, sh, ws, ts, te, s_any_hole != 0);
+        return;
+    }
+    SAcc a{sdata, sL, sh, ws};
     for (uint32_t x = ts + tid; x < te; x += 1024) {
         uint32_t v = 0;
         if (x + kMSafe <= N) {
@@ -245,34 +322,58 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
     }
     for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
         const uint32_t p = tbeg + i;
+        const uint32_t t = ex[i];
+        const uint32_t xa = (t & kStuck) ? (kStuck | (tbeg + (t & ~kStuck))) : tbeg + t;
         if (p < jb.tail_start) {
-            const uint32_t t = ex[i];
-            jb.pexit[p] = (t & kStuck) ? (kStuck | (tbeg + (t & ~kStuck))) : tbeg + t;
+            jb.pexit[p] = xa;
             jb.pcnt[p] = cn[i];
         }
+        if (i < kPathHead) jb.phead[(size_t)blockIdx.x * kPathHead + i] = make_uint2(xa, cn[i]);
     }
 }
 
-// One thread follows the tile exits from position 0.
-__global__ void k_path_chain(JobBufs jb, uint32_t ntiles)
+// Follow the tile exits from position 0.  The entries a tile can be entered at are almost always within
+// the first kPathHead positions, whose (exit, count) pairs k_path_tiles also wrote to a compact table:
+// the CTA stages that table in shared memory chunk by chunk, so the serial walk only sees shared-memory
+// latency.
+constexpr uint32_t kChainChunk = 320;
+__global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t e = 0, base = 0;
-    bool done = jb.tail_start == 0;
-    uint32_t tail_entry = 0;
-    for (uint32_t t = 0; t < ntiles; t++) {
-        const uint32_t tend = (t + 1) * kPathTile;
-        jb.tile_symbase[t] = base;
-        if (done || e >= tend || e >= jb.tail_start) { jb.tile_entry[t] = 0xffffffffu; continue; }
-        jb.tile_entry[t] = e;
-        const uint32_t x = jb.pexit[e];
-        base += jb.pcnt[e];
-        if (x & kStuck) { tail_entry = x & ~kStuck; done = true; }
-        else e = x;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint2 *hd = reinterpret_cast<uint2 *>(smem);
+    __shared__ uint32_t s_e, s_base, s_done, s_tail;
+    if (threadIdx.x == 0) { s_e = 0; s_base = 0; s_done = jb.tail_start == 0; s_tail = 0; }
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < ntiles; c0 += kChainChunk) {
+        const uint32_t nt = min(kChainChunk, ntiles - c0);
+        for (uint32_t i = threadIdx.x; i < nt * kPathHead; i += blockDim.x) hd[i] = jb.phead[(size_t)c0 * kPathHead + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t e = s_e, base = s_base;
+            bool done = s_done != 0;
+            uint32_t tail_entry = s_tail;
+            for (uint32_t k = 0; k < nt; k++) {
+                const uint32_t t = c0 + k, tbeg = t * kPathTile, tend = tbeg + kPathTile;
+                jb.tile_symbase[t] = base;
+                if (done || e >= tend || e >= jb.tail_start) { jb.tile_entry[t] = 0xffffffffu; continue; }
+                jb.tile_entry[t] = e;
+                uint32_t x, c;
+                if (e - tbeg < kPathHead) { const uint2 v = hd[k * kPathHead + (e - tbeg)]; x = v.x; c = v.y; }
+                else { x = jb.pexit[e]; c = jb.pcnt[e]; }
+                base += c;
+                if (x & kStuck) { tail_entry = x & ~kStuck; done = true; }
+                else e = x;
+            }
+            s_e = e; s_base = base; s_done = done; s_tail = tail_entry;
+        }
+        __syncthreads();
     }
-    if (!done) { tail_entry = e; if (e < jb.tail_start) atomicOr(&jb.info->error, 2u); }
-    jb.info->tail_entry = tail_entry;
-    jb.info->n_mid_syms = base;
+    if (threadIdx.x == 0) {
+        uint32_t tail_entry = s_tail;
+        if (!s_done) { tail_entry = s_e; if (s_e < jb.tail_start) atomicOr(&jb.info->error, 2u); }
+        jb.info->tail_entry = tail_entry;
+        jb.info->n_mid_syms = s_base;
+    }
 }
 
 // Mark the path nodes of a tile: symidx[p] = 1 + index of the node's first symbol.
@@ -449,12 +550,22 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
     }
 }
 
+// One CTA per deflate block; the serial heap construction runs out of shared memory (zng_tr_flush_block).
 __global__ void __launch_bounds__(32) k_build_blocks(JobBufs jb, const uint32_t *freq)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ TreeScratch s;
+    __shared__ BlockDesc bd;
+    __shared__ uint32_t fr[320];
+    const uint32_t b = blockIdx.x;
     if (b >= jb.info->n_blocks) return;
-    build_block(c_tab, jb.scratch[b], jb.blocks[b], freq + b * 320, freq + b * 320 + kLCodes, jb.blocks[b].have_window != 0,
-                jb.strategy_fixed != 0);
+    for (uint32_t i = threadIdx.x; i < 320; i += 32) fr[i] = freq[b * 320 + i];
+    for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
+        reinterpret_cast<uint32_t *>(&bd)[i] = reinterpret_cast<const uint32_t *>(&jb.blocks[b])[i];
+    __syncwarp();
+    if (threadIdx.x == 0) build_block(c_tab, s, bd, fr, fr + kLCodes, bd.have_window != 0, jb.strategy_fixed != 0);
+    __syncwarp();
+    for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
+        reinterpret_cast<uint32_t *>(&jb.blocks[b])[i] = reinterpret_cast<const uint32_t *>(&bd)[i];
 }
 
 __global__ void k_scan_blocks(JobBufs jb)

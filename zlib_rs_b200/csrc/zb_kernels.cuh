@@ -13,6 +13,7 @@ constexpr uint32_t kLinkWarm = 32512;   // warm-up positions before the tile (>=
 constexpr uint32_t kMatchTile = 32768;  // positions per k_match CTA
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
 constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
+constexpr uint32_t kPathHead = 64;      // leading positions of a path tile mirrored in the compact head table
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
 constexpr uint32_t kSymsPerThread = 16;
 
@@ -44,6 +45,7 @@ struct JobBufs {
     uint32_t *nxt;        // N
     uint32_t *pexit;      // N   exit position of the tile-local path from p
     uint32_t *pcnt;       // N   symbols on that path
+    uint2 *phead;         // path tiles x kPathHead: (exit, count) of the leading positions
     uint32_t *symidx;     // N   1 + index of the first symbol emitted by the path node at p, 0 = not on path
     uint32_t *tile_entry; // path tiles: entry position (or 0xffffffff)
     uint32_t *tile_symbase;
