@@ -42,7 +42,7 @@ __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
 
-constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
+constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64) + ((kLinkTile + kLinkWarm) / 32 + 8) * 4;
 constexpr uint32_t kMatchSmemBytes = (2 * kWSize + 512) + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
@@ -263,13 +263,19 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.tile_dirty, 1, nmt, st));
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
-            pbegin();
-            k_links<<<nmt, 32, kLinksSmemBytes, st>>>(jb);
-            launches++;
-            pend(0, 1);
+            if (jb.tail_start == 0) {
+                pbegin();
+                k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
+                launches++;
+                pend(0, 1);
+            }
             if (jb.tail_start > 0) {
                 for (;;) {
                     iters++;
+                    pbegin();
+                    k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
+                    launches++;
+                    pend(0, 1);
                     pbegin();
                     k_match<<<nmt, 1024, kMatchSmemBytes, st>>>(jb);
                     pend(1, 1);

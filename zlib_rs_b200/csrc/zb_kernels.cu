@@ -65,57 +65,77 @@ struct SAcc { // shared-memory window of k_match
 };
 
 // ------------------------------------------------------------------------------------------------
-// k_links: one warp per 32 KiB tile inserts positions in order into a shared-memory head table
-// (hash_calc.rs:40-59), 32 positions per step; __match_any_sync resolves equal hashes inside a step.
+// k_links: L[x] = distance to the previous INSERTED position with the same hash (hash_calc.rs:40-59),
+// i.e. the reference's head/prev chains with the holes already taken out.  One CTA per 32 KiB tile
+// replays the insertions of the tile and of the 32512 positions before it, in order, against a
+// shared-memory head table.  The 32 warps split the hash space (warp w owns keys with key%32 == w), so
+// their head entries are disjoint and every warp can run through the positions at its own pace, 32
+// positions per step; __match_any_sync orders equal keys inside a step.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kLinksSmem = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
+constexpr uint32_t kLinksSmem = 65536 * 2 + (kLinkTile + kLinkWarm + 64) + ((kLinkTile + kLinkWarm) / 32 + 8) * 4;
 
-__global__ void __launch_bounds__(32) k_links(JobBufs jb)
+__device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte_idx)
+{
+    // unaligned little-endian 32-bit load: two aligned LDS + funnel shift
+    const uint32_t w = byte_idx >> 2;
+    return __funnelshift_r(words[w], words[w + 1], (byte_idx & 3u) * 8u);
+}
+
+__global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    if (!jb.tile_dirty[blockIdx.x]) return;
     uint16_t *head = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sd = smem + 65536 * 2;
-    const uint32_t lane = threadIdx.x;
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + 65536 * 2 + (kLinkTile + kLinkWarm + 64));
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t N = jb.N;
     const uint32_t ts = blockIdx.x * kLinkTile;
     const uint32_t te = min(ts + kLinkTile, N);
-    const uint32_t ws = ts > kLinkWarm ? ts - kLinkWarm : 0;
-    for (uint32_t i = lane; i < 32768; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
-    // stage [ws, te + 3) ; the input buffer is zero padded
-    const uint32_t nbytes = te + 3 - ws;
-    for (uint32_t i = lane * 4; i < nbytes; i += 128) {
-        uint32_t a = ws + i;
-        sd[i] = jb.in[a]; sd[i + 1] = jb.in[a + 1]; sd[i + 2] = jb.in[a + 2]; sd[i + 3] = jb.in[a + 3];
+    const uint32_t ws = ts > kLinkWarm ? ts - kLinkWarm : 0; // multiple of 32 (and of 16)
+    for (uint32_t i = tid; i < 32768; i += 1024) reinterpret_cast<uint32_t *>(head)[i] = 0;
+    {
+        const uint32_t n16 = (te + 16 - ws + 15) / 16; // the input buffer is zero padded
+        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
+        uint4 *dst = reinterpret_cast<uint4 *>(sd);
+        for (uint32_t i = tid; i < n16; i += 1024) dst[i] = src[i];
+        const uint32_t nw = (te - ws + 31) / 32;
+        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
     }
-    __syncwarp();
+    __syncthreads();
     for (uint32_t base = ws; base < te; base += 32) {
         const uint32_t x = base + lane;
         const bool valid = x < te && x + 4 <= N;
-        uint32_t key = 0x10000u + lane;
-        if (valid) {
-            const uint8_t *q = sd + (x - ws);
-            key = hash_u32(q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24));
-        }
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        uint32_t pred_rel = 0;
-        if (valid) {
-            const uint32_t lower = peers & ((1u << lane) - 1u);
+        uint32_t key = 0;
+        if (valid) key = hash_u32(lds_u32(words, x - ws));
+        const bool mine = valid && (key & 31u) == warp;
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (m == 0) continue;
+        uint32_t pred_rel = 0, peers_ins = 0;
+        bool ins = false;
+        if (mine) {
+            const uint32_t i = x - ws;
+            ins = !((sh[i >> 5] >> (i & 31)) & 1u);
+            const uint32_t insm = __ballot_sync(m, ins);
+            peers_ins = __match_any_sync(m, key) & insm;
+            const uint32_t lower = peers_ins & ((1u << lane) - 1u);
             if (lower) pred_rel = (base + (31 - __clz(lower))) - ws + 1;
             else pred_rel = head[key];
         }
         __syncwarp();
-        if (valid) {
+        if (mine) {
             const uint32_t rel = x - ws + 1;
             if (x >= ts) {
-                uint32_t d = pred_rel ? rel - pred_rel : 0;
+                const uint32_t d = pred_rel ? rel - pred_rel : 0;
                 jb.L[x] = (uint16_t)((d && d <= kMaxDist) ? d : 0);
             }
-            if ((peers >> lane) == 1u) head[key] = (uint16_t)rel;
-        } else if (x < te && x >= ts) {
-            jb.L[x] = 0;
+            if (ins && (peers_ins >> lane) == 1u) head[key] = (uint16_t)rel;
         }
         __syncwarp();
     }
+    // positions without four bytes of input are never hashed
+    for (uint32_t x = max(ts, N >= 3 ? N - 3 : 0) + tid; x < te; x += 1024) jb.L[x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -125,51 +145,46 @@ __global__ void __launch_bounds__(32) k_links(JobBufs jb)
 constexpr uint32_t kMatchData = 2 * kWSize + 512;
 constexpr uint32_t kMatchSmem = kMatchData + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
 
-// Unaligned little-endian 32-bit load from the staged window (two aligned LDS + funnel shift).
-__device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte_idx)
-{
-    const uint32_t w = byte_idx >> 2;
-    return __funnelshift_r(words[w], words[w + 1], (byte_idx & 3u) * 8u);
-}
-
-// Levels 5/6 (no early exit): every lane runs a uniform step loop -- one chain candidate, or one 4-byte
-// compare step, per iteration -- and moves on to its next position as soon as one is finished, so lanes
-// with short chains do not wait for lanes with long ones.  Semantics are those of lm_walk():
-// a candidate replaces the best match iff its common prefix (<= 258) is strictly longer; the walk stops
-// at nice_match, at the chain budget, or when the chain leaves the window.  The 4-byte test at offset
-// best-3 is only a filter for that condition (cf. longest_match.rs:198-234).
-__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
-                                                uint32_t ws, uint32_t ts, uint32_t te, bool tile_has_holes)
+// Levels 5/6 (no early exit): every lane runs a uniform step loop -- one chain candidate, or one 8-byte
+// compare step, per iteration -- and fetches its next position from a shared counter as soon as one is
+// finished, so lanes with short chains never wait for lanes with long ones.  Semantics are those of
+// lm_walk(): a candidate replaces the best match iff its common prefix (<= 258) is strictly longer; the
+// walk stops at nice_match, at the chain budget, or when the chain leaves the window.  The 4-byte test at
+// offset best-3 is only a filter for that condition (cf. longest_match.rs:198-234).  The links already
+// skip holes (k_links), so no hole test is needed here.
+__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, uint32_t ws, uint32_t te,
+                                                uint32_t *s_next)
 {
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
-    uint32_t x = ts + threadIdx.x;
+    uint32_t x = 0;
     bool have = false;
     uint32_t cur = 0, best = 2, chain = 0, res = 0, xw = 0, clen = 0, cand = 0;
     bool first = true, comparing = false;
     for (;;) {
         if (!have) {
+            x = atomicAdd(s_next, 1u);
             if (x >= te) break;
-            if (x + kMSafe > N) { jb.M[x] = 0; x += 1024; continue; }
+            if (x + kMSafe > N) { jb.M[x] = 0; continue; }
             cur = x; best = 2; chain = budget; res = 0; first = true; comparing = false;
             xw = lds_u32(words, x - ws) & 0x00ffffffu; // bytes 0..2: the filter for best == 2
             have = true;
         }
         if (comparing) {
-            const uint32_t a = lds_u32(words, x - ws + clen), b = lds_u32(words, cand - ws + clen);
-            const uint32_t diff = a ^ b;
-            uint32_t len;
-            if (diff == 0 && clen + 4 < kMaxMatch) { clen += 4; continue; }
-            len = diff ? clen + ((__ffs(diff) - 1) >> 3) : clen + 4;
+            const uint32_t ia = x - ws + clen, ib = cand - ws + clen;
+            const uint32_t d0 = lds_u32(words, ia) ^ lds_u32(words, ib);
+            const uint32_t d1 = lds_u32(words, ia + 4) ^ lds_u32(words, ib + 4);
+            if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+            uint32_t len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
             if (len > kMaxMatch) len = kMaxMatch;
             comparing = false;
             if (len > best) {
                 best = len;
                 res = (len << 16) | (x - cand);
-                if (best >= nice) { jb.M[x] = res; have = false; x += 1024; continue; }
+                if (best >= nice) { jb.M[x] = res; have = false; continue; }
                 xw = lds_u32(words, x - ws + best - 3);
             }
-            if (--chain == 0) { jb.M[x] = res; have = false; x += 1024; }
+            if (--chain == 0) { jb.M[x] = res; have = false; }
             continue;
         }
         // next chain entry
@@ -180,23 +195,19 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             const uint32_t dist = x - cur;
             stop = dist > (first ? kMaxDist : kMaxDist - 1) || cur == 0;
         }
-        if (stop) { jb.M[x] = res; have = false; x += 1024; continue; }
-        if (tile_has_holes) {
-            const uint32_t i = cur - ws;
-            if ((sh[i >> 5] >> (i & 31)) & 1u) continue; // a hole is not on the chain
-        }
+        if (stop) { jb.M[x] = res; have = false; continue; }
         first = false;
         uint32_t cw = lds_u32(words, cur - ws + (best == 2 ? 0u : best - 3u));
         if (best == 2) cw &= 0x00ffffffu;
         if (cw == xw) { comparing = true; cand = cur; clen = 0; continue; }
-        if (--chain == 0) { jb.M[x] = res; have = false; x += 1024; }
+        if (--chain == 0) { jb.M[x] = res; have = false; }
     }
 }
 
 __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_any_hole;
+    __shared__ uint32_t s_next;
     const uint32_t tile = blockIdx.x;
     if (!jb.tile_dirty[tile]) return;
     uint8_t *sdata = smem;
@@ -207,8 +218,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     const uint32_t te = min(ts + kMatchTile, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_any_hole = 0;
-    __syncthreads();
+    if (tid == 0) s_next = ts;
     // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
     {
         const uint32_t n16 = (te + 512 - ws + 15) / 16;
@@ -220,14 +230,12 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
         const uint32_t nw = (te - ws + 31) / 32;
-        uint32_t any = 0;
-        for (uint32_t i = tid; i < nw; i += 1024) { const uint32_t w = jb.holes[(ws >> 5) + i]; sh[i] = w; any |= w; }
-        if (any) s_any_hole = 1;
+        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = 0; // the links are hole-aware: nothing to skip
     }
     __syncthreads();
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
-        match_tile_fast(jb, sdata, sL, sh, ws, ts, te, s_any_hole != 0);
+        match_tile_fast(jb, sdata, sL, ws, te, &s_next);
         return;
     }
     SAcc a{sdata, sL, sh, ws};
