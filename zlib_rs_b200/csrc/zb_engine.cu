@@ -27,11 +27,13 @@ static void set_err(const char *what, cudaError_t e)
 // kernels (zb_kernels.cu)
 __global__ void k_links(JobBufs);
 __global__ void k_match(JobBufs);
+__global__ void k_skip(JobBufs, uint32_t);
 __global__ void k_nxt(JobBufs);
 __global__ void k_path_tiles(JobBufs);
 __global__ void k_path_chain(JobBufs, uint32_t);
 __global__ void k_path_mark(JobBufs);
 __global__ void k_emit(JobBufs);
+__global__ void k_holes(JobBufs);
 __global__ void k_holes_cmp(JobBufs, uint32_t, uint32_t);
 __global__ void k_tail(JobBufs);
 __global__ void k_block_hist(JobBufs, uint32_t *);
@@ -42,8 +44,8 @@ __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
 
-constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64) + ((kLinkTile + kLinkWarm) / 32 + 8) * 4;
-constexpr uint32_t kMatchSmemBytes = (2 * kWSize + 512) + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
+constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
+constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
 
@@ -134,7 +136,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -180,6 +182,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.N = N;
     jb.tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
     RES(S_L, npad * 2, L, uint16_t *)
+    RES(S_SK, npad * 2, SK, uint16_t *)
     RES(S_HOLES, (size_t)nwords * 4, holes, uint32_t *)
     RES(S_HOLESN, (size_t)nwords * 4, holes_new, uint32_t *)
     RES(S_M, npad * 4, M, uint32_t *)
@@ -263,21 +266,17 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.tile_dirty, 1, nmt, st));
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
-            if (jb.tail_start == 0) {
-                pbegin();
-                k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
-                launches++;
-                pend(0, 1);
-            }
+            pbegin();
+            k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
+            launches++;
+            pend(0, 1);
             if (jb.tail_start > 0) {
+                const uint32_t nsub = (N + kMatchSub - 1) / kMatchSub;
                 for (;;) {
                     iters++;
                     pbegin();
-                    k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
-                    launches++;
-                    pend(0, 1);
-                    pbegin();
-                    k_match<<<nmt, 1024, kMatchSmemBytes, st>>>(jb);
+                    if (iters > 1) { k_skip<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords); launches++; }
+                    k_match<<<nsub, 1024, kMatchSmemBytes, st>>>(jb);
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();
@@ -289,7 +288,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
                     pend(3, 3);
                     pbegin();
-                    k_emit<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                    k_holes<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
                     CK(cudaMemsetAsync(jb.tile_dirty, 0, nmt, st));
                     CK(cudaMemsetAsync(&d_info->holes_changed, 0, 4, st));
                     k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
@@ -301,6 +300,12 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     if (!h_info->holes_changed) break;
                     if (iters > 4096) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; }
                 }
+            }
+            if (jb.tail_start > 0) {
+                pbegin();
+                k_emit<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                launches++;
+                pend(4, 1);
             }
             pbegin();
             k_tail<<<1, 32, 0, st>>>(jb);

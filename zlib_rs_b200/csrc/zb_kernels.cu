@@ -65,8 +65,9 @@ struct SAcc { // shared-memory window of k_match
 };
 
 // ------------------------------------------------------------------------------------------------
-// k_links: L[x] = distance to the previous INSERTED position with the same hash (hash_calc.rs:40-59),
-// i.e. the reference's head/prev chains with the holes already taken out.  One CTA per 32 KiB tile
+// k_links: L[x] = distance to the previous position with the same hash (hash_calc.rs:40-59): the
+// reference's head/prev chains as if every position were inserted (holes are bridged by k_skip's skip
+// pointers when the chains are staged in k_match).  One CTA per 32 KiB tile
 // replays the insertions of the tile and of the 32512 positions before it, in order, against a
 // shared-memory head table.  The 32 warps split the hash space (warp w owns keys with key%32 == w), so
 // their head entries are disjoint and every warp can run through the positions at its own pace, 32
@@ -84,10 +85,8 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte
 __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    if (!jb.tile_dirty[blockIdx.x]) return;
     uint16_t *head = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sd = smem + 65536 * 2;
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + 65536 * 2 + (kLinkTile + kLinkWarm + 64));
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t N = jb.N;
@@ -100,8 +99,6 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
         const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
         uint4 *dst = reinterpret_cast<uint4 *>(sd);
         for (uint32_t i = tid; i < n16; i += 1024) dst[i] = src[i];
-        const uint32_t nw = (te - ws + 31) / 32;
-        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
     }
     __syncthreads();
     for (uint32_t base = ws; base < te; base += 32) {
@@ -113,12 +110,8 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
         const uint32_t m = __ballot_sync(0xffffffffu, mine);
         if (m == 0) continue;
         uint32_t pred_rel = 0, peers_ins = 0;
-        bool ins = false;
         if (mine) {
-            const uint32_t i = x - ws;
-            ins = !((sh[i >> 5] >> (i & 31)) & 1u);
-            const uint32_t insm = __ballot_sync(m, ins);
-            peers_ins = __match_any_sync(m, key) & insm;
+            peers_ins = __match_any_sync(m, key);
             const uint32_t lower = peers_ins & ((1u << lane) - 1u);
             if (lower) pred_rel = (base + (31 - __clz(lower))) - ws + 1;
             else pred_rel = head[key];
@@ -130,7 +123,7 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
                 const uint32_t d = pred_rel ? rel - pred_rel : 0;
                 jb.L[x] = (uint16_t)((d && d <= kMaxDist) ? d : 0);
             }
-            if (ins && (peers_ins >> lane) == 1u) head[key] = (uint16_t)rel;
+            if ((peers_ins >> lane) == 1u) head[key] = (uint16_t)rel;
         }
         __syncwarp();
     }
@@ -142,102 +135,167 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 // k_match: M[x] for every x of a 32 KiB tile.  The tile plus the 32 KiB before it (data, chain links,
 // hole bits) are staged in shared memory; 1024 threads walk their chains independently.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kMatchData = 2 * kWSize + 512;
-constexpr uint32_t kMatchSmem = kMatchData + 2 * kWSize * 2 + (2 * kWSize / 32) * 4;
+constexpr uint32_t kMatchData = kWSize + kMatchSub + 512;
+constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4;
 
-// Levels 5/6 (no early exit): every lane runs a uniform step loop -- one chain candidate, or one 8-byte
-// compare step, per iteration -- and fetches its next position from a shared counter as soon as one is
-// finished, so lanes with short chains never wait for lanes with long ones.  Semantics are those of
-// lm_walk(): a candidate replaces the best match iff its common prefix (<= 258) is strictly longer; the
-// walk stops at nice_match, at the chain budget, or when the chain leaves the window.  The 4-byte test at
-// offset best-3 is only a filter for that condition (cf. longest_match.rs:198-234).  The links already
-// skip holes (k_links), so no hole test is needed here.
-__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, uint32_t ws, uint32_t te,
-                                                uint32_t *s_next)
+// k_skip: for every hole y (a position the parser never inserted), SK[y] = distance from y to the nearest
+// INSERTED position further down its chain (0 = none within the window).  k_match stages SK instead of L
+// at hole positions, so a chain walk bridges a whole run of holes in one extra step.
+__global__ void __launch_bounds__(256) k_skip(JobBufs jb, uint32_t nwords)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t bits = jb.holes[w];
+    while (bits) {
+        const uint32_t b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t y = w * 32 + b;
+        uint32_t cur = y, sk = 0;
+        for (;;) {
+            const uint32_t d = cur + 4 <= jb.N ? jb.L[cur] : 0;
+            if (d == 0 || (y - cur) + d > kMaxDist) { sk = 0; break; }
+            cur -= d;
+            if (!((jb.holes[cur >> 5] >> (cur & 31)) & 1u)) { sk = y - cur; break; }
+        }
+        jb.SK[y] = (uint16_t)sk;
+    }
+}
+
+// Levels 5/6 (no early exit).  Semantics are those of lm_walk(): a candidate replaces the best match iff
+// its common prefix (<= 258) is strictly longer; the walk stops at nice_match, at the chain budget, or when
+// the chain leaves the window.  The 4-byte test at offset best-3 is only a filter for that condition (cf.
+// longest_match.rs:198-234).
+// Schedule: a lane is IDLE (needs a position), WALKing its chain one candidate per step, or PENDing a full
+// compare.  Position fetches and compares are batched -- they run only when at least kBatch lanes want them
+// (or nobody can walk) -- so the common walk step is not diluted by the rarer, longer code paths, and lanes
+// with short chains never wait for lanes with long ones.
+constexpr uint32_t kBatch = 8;
+enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
+
+__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
+                                                bool has_holes, uint32_t ws, uint32_t te, uint32_t *s_next)
 {
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
-    uint32_t x = 0;
-    bool have = false;
-    uint32_t cur = 0, best = 2, chain = 0, res = 0, xw = 0, clen = 0, cand = 0;
-    bool first = true, comparing = false;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t x = 0, cur = 0, best = 2, chain = 0, res = 0, xw = 0, cand = 0;
+    uint32_t state = LS_IDLE;
+    bool first = true;
     for (;;) {
-        if (!have) {
-            x = atomicAdd(s_next, 1u);
-            if (x >= te) break;
-            if (x + kMSafe > N) { jb.M[x] = 0; continue; }
-            cur = x; best = 2; chain = budget; res = 0; first = true; comparing = false;
-            xw = lds_u32(words, x - ws) & 0x00ffffffu; // bytes 0..2: the filter for best == 2
-            have = true;
-        }
-        if (comparing) {
-            const uint32_t ia = x - ws + clen, ib = cand - ws + clen;
-            const uint32_t d0 = lds_u32(words, ia) ^ lds_u32(words, ib);
-            const uint32_t d1 = lds_u32(words, ia + 4) ^ lds_u32(words, ib + 4);
-            if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
-            uint32_t len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
-            if (len > kMaxMatch) len = kMaxMatch;
-            comparing = false;
-            if (len > best) {
-                best = len;
-                res = (len << 16) | (x - cand);
-                if (best >= nice) { jb.M[x] = res; have = false; continue; }
-                xw = lds_u32(words, x - ws + best - 3);
+        const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
+        const uint32_t m_walk = __ballot_sync(0xffffffffu, state == LS_WALK);
+        const uint32_t m_pend = __ballot_sync(0xffffffffu, state == LS_PEND);
+        if ((m_idle | m_walk | m_pend) == 0) break;
+        if (m_idle && (__popc(m_idle) >= (int)kBatch || m_walk == 0)) {
+            // warp-aggregated fetch of consecutive positions
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(m_idle) - 1;
+            if (lane == leader) base = atomicAdd(s_next, (uint32_t)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (state == LS_IDLE) {
+                x = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (x >= te) state = LS_DONE;
+                else if (x + kMSafe > N) { jb.M[x] = 0; }
+                else {
+                    cur = x; best = 2; chain = budget; res = 0; first = true;
+                    xw = lds_u32(words, x - ws) & 0x00ffffffu; // bytes 0..2: the filter for best == 2
+                    state = LS_WALK;
+                }
             }
-            if (--chain == 0) { jb.M[x] = res; have = false; }
             continue;
         }
-        // next chain entry
-        const uint32_t d = sL[cur - ws];
-        bool stop = d == 0;
-        if (!stop) {
-            cur -= d;
-            const uint32_t dist = x - cur;
-            stop = dist > (first ? kMaxDist : kMaxDist - 1) || cur == 0;
+        if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
+            if (state == LS_PEND) {
+                uint32_t clen = 0, len;
+                const uint32_t ia = x - ws, ib = cand - ws;
+                for (;;) {
+                    const uint32_t d0 = lds_u32(words, ia + clen) ^ lds_u32(words, ib + clen);
+                    const uint32_t d1 = lds_u32(words, ia + clen + 4) ^ lds_u32(words, ib + clen + 4);
+                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                    break;
+                }
+                if (len > kMaxMatch) len = kMaxMatch;
+                state = LS_WALK;
+                if (len > best) {
+                    best = len;
+                    res = (len << 16) | (x - cand);
+                    if (best >= nice) { jb.M[x] = res; state = LS_IDLE; }
+                    else xw = lds_u32(words, x - ws + best - 3);
+                }
+                if (state == LS_WALK && --chain == 0) { jb.M[x] = res; state = LS_IDLE; }
+            }
+            continue;
         }
-        if (stop) { jb.M[x] = res; have = false; continue; }
-        first = false;
-        uint32_t cw = lds_u32(words, cur - ws + (best == 2 ? 0u : best - 3u));
-        if (best == 2) cw &= 0x00ffffffu;
-        if (cw == xw) { comparing = true; cand = cur; clen = 0; continue; }
-        if (--chain == 0) { jb.M[x] = res; have = false; }
+        if (state == LS_WALK) {
+            // next chain entry
+            uint32_t d = sL[cur - ws];
+            bool stop = d == 0;
+            cur -= d;
+            if (has_holes && !stop) {
+                const uint32_t i = cur - ws;
+                if ((sh[i >> 5] >> (i & 31)) & 1u) { d = sL[i]; stop = d == 0; cur -= d; } // skip pointer over the holes
+            }
+            if (!stop) {
+                const uint32_t dist = x - cur;
+                stop = dist > (first ? kMaxDist : kMaxDist - 1) || cur == 0 || cur < ws;
+            }
+            if (stop) { jb.M[x] = res; state = LS_IDLE; }
+            else {
+                first = false;
+                uint32_t cw = lds_u32(words, cur - ws + (best == 2 ? 0u : best - 3u));
+                if (best == 2) cw &= 0x00ffffffu;
+                if (cw == xw) { cand = cur; state = LS_PEND; }
+                else if (--chain == 0) { jb.M[x] = res; state = LS_IDLE; }
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_next;
-    const uint32_t tile = blockIdx.x;
-    if (!jb.tile_dirty[tile]) return;
+    __shared__ uint32_t s_next, s_any_hole;
+    const uint32_t ts = blockIdx.x * kMatchSub;
+    if (ts >= jb.N || !jb.tile_dirty[ts / kMatchTile]) return;
     uint8_t *sdata = smem;
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kMatchData);
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kMatchData + 2 * kWSize * 2);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kMatchData + (kWSize + kMatchSub) * 2);
     const uint32_t N = jb.N;
-    const uint32_t ts = tile * kMatchTile;
-    const uint32_t te = min(ts + kMatchTile, N);
+    const uint32_t te = min(ts + kMatchSub, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_next = ts;
-    // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
+    if (tid == 0) { s_next = ts; s_any_hole = 0; }
+    __syncthreads();
     {
+        // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
         const uint32_t n16 = (te + 512 - ws + 15) / 16;
         const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
         uint4 *dst = reinterpret_cast<uint4 *>(sdata);
         for (uint32_t i = tid; i < n16 && i < kMatchData / 16; i += 1024) dst[i] = src[i];
+        // hole bits, then the chain links with the skip pointers substituted at hole positions
+        const uint32_t nw = (te - ws + 31) / 32;
+        uint32_t any = 0;
+        for (uint32_t i = tid; i < nw; i += 1024) { const uint32_t w = jb.holes[(ws >> 5) + i]; sh[i] = w; any |= w; }
+        if (any) s_any_hole = 1;
         const uint32_t nl = (te - ws + 7) / 8; // 8 links per uint4
         const uint4 *ls = reinterpret_cast<const uint4 *>(jb.L + ws);
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
-        const uint32_t nw = (te - ws + 31) / 32;
-        for (uint32_t i = tid; i < nw; i += 1024) sh[i] = 0; // the links are hole-aware: nothing to skip
     }
     __syncthreads();
+    const bool has_holes = s_any_hole != 0;
+    if (has_holes) {
+        for (uint32_t i = tid; i < te - ws; i += 1024)
+            if ((sh[i >> 5] >> (i & 31)) & 1u) sL[i] = jb.SK[ws + i];
+        __syncthreads();
+    }
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
-        match_tile_fast(jb, sdata, sL, ws, te, &s_next);
+        match_tile_fast(jb, sdata, sL, sh, has_holes, ws, te, &s_next);
         return;
     }
+    // levels 3/4 (early exit): generic walk; a hole's staged link already bridges to an inserted position
     SAcc a{sdata, sL, sh, ws};
     for (uint32_t x = ts + tid; x < te; x += 1024) {
         uint32_t v = 0;
@@ -259,10 +317,14 @@ __global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
     if (p >= jb.tail_start) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     uint32_t ns = 0;
-    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [](const Sym &) {}, &ns);
+    const uint32_t long_len = 16 * jb.lp.lazy;
+    bool is_long = false;
+    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+        if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
+    }, &ns);
     const uint32_t delta = np - p;
     if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
-    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (np >= jb.tail_start ? kNxtTail : 0u);
+    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -440,21 +502,19 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_emit: every path node re-runs its macro step, writes its symbols and records the holes it leaves
+// k_holes: the hole set implied by the current path (only nodes whose macro step contains a long match
+// need to be re-evaluated; k_nxt flagged them).  k_emit: the symbols of the final path.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emit(JobBufs jb)
+__global__ void __launch_bounds__(256) k_holes(JobBufs jb)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= jb.tail_start) return;
-    const uint32_t idx = jb.symidx[p];
-    if (!idx) return;
+    if (!jb.symidx[p] || !(jb.nxt[p] & kNxtLong)) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
-    uint32_t k = idx - 1, ns = 0;
+    uint32_t ns = 0;
     const uint32_t long_len = 16 * jb.lp.lazy;
-    Sym *syms = jb.syms;
     uint32_t *hn = jb.holes_new;
     macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
-        syms[k++] = s;
         if (s.dist && (uint32_t)s.lc + 3u > long_len) {
             // interior positions pos+1 .. pos+len-2 are never inserted (medium.rs:251-261)
             uint32_t y0 = s.pos + 1, y1 = s.pos + s.lc + 3u - 1; // [y0, y1)
@@ -467,6 +527,18 @@ __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
             }
         }
     }, &ns);
+}
+
+__global__ void __launch_bounds__(256) k_emit(JobBufs jb)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= jb.tail_start) return;
+    const uint32_t idx = jb.symidx[p];
+    if (!idx) return;
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    uint32_t k = idx - 1, ns = 0;
+    Sym *syms = jb.syms;
+    macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) { syms[k++] = s; }, &ns);
 }
 
 // holes := holes_new; report change and the match tiles whose window saw it

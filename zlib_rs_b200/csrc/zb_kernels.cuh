@@ -10,11 +10,13 @@ namespace zb {
 
 constexpr uint32_t kLinkTile = 32768;   // positions per k_links CTA
 constexpr uint32_t kLinkWarm = 32512;   // warm-up positions before the tile (>= kMaxDist)
-constexpr uint32_t kMatchTile = 32768;  // positions per k_match CTA
+constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the match phase
+constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
 constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
 constexpr uint32_t kPathHead = 64;      // leading positions of a path tile mirrored in the compact head table
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
+constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
 constexpr uint32_t kSymsPerThread = 16;
 
 struct JobInfo {              // device-resident result / control block of one deflate job
@@ -39,6 +41,7 @@ struct JobBufs {
     uint32_t N;
     uint32_t tail_start;
     uint16_t *L;          // N + kPad
+    uint16_t *SK;         // N + kPad: skip pointers of hole positions
     uint32_t *holes;      // bitmap, (N >> 5) + 2 words
     uint32_t *holes_new;
     uint32_t *M;          // N + kPad
