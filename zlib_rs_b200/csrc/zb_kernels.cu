@@ -232,13 +232,16 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             uint32_t d = sL[cur - ws];
             bool stop = d == 0;
             cur -= d;
+            const uint32_t lim = first ? kMaxDist : kMaxDist - 1;
+            if (!stop) stop = x - cur > lim || cur == 0; // beyond the window (also keeps cur inside the staged range)
             if (has_holes && !stop) {
                 const uint32_t i = cur - ws;
-                if ((sh[i >> 5] >> (i & 31)) & 1u) { d = sL[i]; stop = d == 0; cur -= d; } // skip pointer over the holes
-            }
-            if (!stop) {
-                const uint32_t dist = x - cur;
-                stop = dist > (first ? kMaxDist : kMaxDist - 1) || cur == 0 || cur < ws;
+                if ((sh[i >> 5] >> (i & 31)) & 1u) { // a hole: its staged link is the skip pointer to an inserted position
+                    d = sL[i];
+                    stop = d == 0;
+                    cur -= d;
+                    if (!stop) stop = x - cur > lim || cur == 0;
+                }
             }
             if (stop) { jb.M[x] = res; state = LS_IDLE; }
             else {
