@@ -27,7 +27,6 @@ static void set_err(const char *what, cudaError_t e)
 // kernels (zb_kernels.cu)
 __global__ void k_links(JobBufs);
 __global__ void k_match(JobBufs);
-__global__ void k_skip(JobBufs, uint32_t);
 __global__ void k_nxt(JobBufs);
 __global__ void k_path_tiles(JobBufs);
 __global__ void k_path_chain(JobBufs, uint32_t);
@@ -275,7 +274,6 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 for (;;) {
                     iters++;
                     pbegin();
-                    if (iters > 1) { k_skip<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords); launches++; }
                     k_match<<<nsub, 1024, kMatchSmemBytes, st>>>(jb);
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass

@@ -138,29 +138,6 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 constexpr uint32_t kMatchData = kWSize + kMatchSub + 512;
 constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4;
 
-// k_skip: for every hole y (a position the parser never inserted), SK[y] = distance from y to the nearest
-// INSERTED position further down its chain (0 = none within the window).  k_match stages SK instead of L
-// at hole positions, so a chain walk bridges a whole run of holes in one extra step.
-__global__ void __launch_bounds__(256) k_skip(JobBufs jb, uint32_t nwords)
-{
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwords) return;
-    uint32_t bits = jb.holes[w];
-    while (bits) {
-        const uint32_t b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const uint32_t y = w * 32 + b;
-        uint32_t cur = y, sk = 0;
-        for (;;) {
-            const uint32_t d = cur + 4 <= jb.N ? jb.L[cur] : 0;
-            if (d == 0 || (y - cur) + d > kMaxDist) { sk = 0; break; }
-            cur -= d;
-            if (!((jb.holes[cur >> 5] >> (cur & 31)) & 1u)) { sk = y - cur; break; }
-        }
-        jb.SK[y] = (uint16_t)sk;
-    }
-}
-
 // Levels 5/6 (no early exit).  Semantics are those of lm_walk(): a candidate replaces the best match iff
 // its common prefix (<= 258) is strictly longer; the walk stops at nice_match, at the chain budget, or when
 // the chain leaves the window.  The 4-byte test at offset best-3 is only a filter for that condition (cf.
@@ -289,8 +266,29 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     __syncthreads();
     const bool has_holes = s_any_hole != 0;
     if (has_holes) {
-        for (uint32_t i = tid; i < te - ws; i += 1024)
-            if ((sh[i >> 5] >> (i & 31)) & 1u) sL[i] = jb.SK[ws + i];
+        // Skip pointers: at a hole (a position the parser never inserted) the staged link is replaced by the
+        // distance to the nearest INSERTED position further down the chain, by pointer jumping over the staged
+        // window.  A chain walk then bridges any run of holes in one extra step.
+        __shared__ uint32_t s_changed;
+        for (uint32_t round = 0; round < 24; round++) {
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (uint32_t i = tid; i < te - ws; i += 1024) {
+                if (!((sh[i >> 5] >> (i & 31)) & 1u)) continue;
+                const uint32_t d = sL[i];
+                if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
+                const uint32_t t = i - d;
+                if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
+                const uint32_t d2 = sL[t];
+                const uint32_t nd = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
+                sL[i] = (uint16_t)nd;
+                ch = true;
+            }
+            if (ch) s_changed = 1;
+            __syncthreads();
+            if (!s_changed) break;
+        }
         __syncthreads();
     }
     const LevelParams lp = jb.lp;
