@@ -135,7 +135,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -179,6 +179,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     else { if ((rc = reserve(S_IN, npad + 16, &p)) != ZB_OK) return rc; d_in = static_cast<uint8_t *>(p); }
     jb.in = d_in;
     jb.N = N;
+    jb.nmt = nmt;
     jb.tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
     RES(S_L, npad * 2, L, uint16_t *)
     RES(S_SK, npad * 2, SK, uint16_t *)
@@ -192,6 +193,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_PHEAD, (size_t)npt * kPathHead * 8, phead, uint2 *)
     RES(S_TENTRY, (size_t)npt * 4, tile_entry, uint32_t *)
     RES(S_TSYMB, (size_t)npt * 4, tile_symbase, uint32_t *)
+    RES(S_MARKN, (size_t)npt + 16, mark_needed, uint8_t *)
     RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
     RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
@@ -263,6 +265,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.holes, 0, (size_t)nwords * 4, st));
             CK(cudaMemsetAsync(jb.holes_new, 0, (size_t)nwords * 4, st));
             CK(cudaMemsetAsync(jb.tile_dirty, 1, nmt, st));
+            CK(cudaMemsetAsync(jb.tile_entry, 0xee, (size_t)npt * 4, st)); // "never seen": forces the first marking
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
             pbegin();
@@ -270,11 +273,15 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             launches++;
             pend(0, 1);
             if (jb.tail_start > 0) {
-                const uint32_t nsub = (N + kMatchSub - 1) / kMatchSub;
                 for (;;) {
                     iters++;
+                    // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
+                    // them over more SMs
+                    jb.match_sub = iters == 1 ? kMatchSub : 2048;
+                    const uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
+                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4;
                     pbegin();
-                    k_match<<<nsub, 1024, kMatchSmemBytes, st>>>(jb);
+                    k_match<<<nsub, 1024, msmem, st>>>(jb);
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();

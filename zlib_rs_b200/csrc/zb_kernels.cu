@@ -147,6 +147,7 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 // (or nobody can walk) -- so the common walk step is not diluted by the rarer, longer code paths, and lanes
 // with short chains never wait for lanes with long ones.
 constexpr uint32_t kBatch = 8;
+constexpr uint32_t kWalkBurst = 4; // walk steps between two schedule checks
 enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
 
 __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
@@ -155,9 +156,11 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t x = 0, cur = 0, best = 2, chain = 0, res = 0, xw = 0, cand = 0;
+    // per-lane state, all positions relative to ws
+    uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, xw = 0, cand = 0;
+    uint32_t foff = 0, fmask = 0x00ffffffu; // filter: 4 bytes at offset best-3 (3 bytes at 0 while best == 2)
+    uint32_t lowr = 0;                       // lowest admissible candidate (relative): x - lim
     uint32_t state = LS_IDLE;
-    bool first = true;
     for (;;) {
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
         const uint32_t m_walk = __ballot_sync(0xffffffffu, state == LS_WALK);
@@ -170,12 +173,17 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             if (lane == leader) base = atomicAdd(s_next, (uint32_t)__popc(m_idle));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (state == LS_IDLE) {
-                x = base + __popc(m_idle & ((1u << lane) - 1u));
+                const uint32_t x = base + __popc(m_idle & ((1u << lane) - 1u));
                 if (x >= te) state = LS_DONE;
                 else if (x + kMSafe > N) { jb.M[x] = 0; }
                 else {
-                    cur = x; best = 2; chain = budget; res = 0; first = true;
-                    xw = lds_u32(words, x - ws) & 0x00ffffffu; // bytes 0..2: the filter for best == 2
+                    xr = x - ws; cr = xr; best = 2; chain = budget; res = 0;
+                    foff = 0; fmask = 0x00ffffffu;
+                    xw = lds_u32(words, xr) & fmask;
+                    // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
+                    // absolute position 0 is never a candidate
+                    lowr = xr > kMaxDist ? xr - kMaxDist : 0;
+                    if (ws == 0 && lowr == 0) lowr = 1;
                     state = LS_WALK;
                 }
             }
@@ -184,10 +192,9 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
         if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
             if (state == LS_PEND) {
                 uint32_t clen = 0, len;
-                const uint32_t ia = x - ws, ib = cand - ws;
                 for (;;) {
-                    const uint32_t d0 = lds_u32(words, ia + clen) ^ lds_u32(words, ib + clen);
-                    const uint32_t d1 = lds_u32(words, ia + clen + 4) ^ lds_u32(words, ib + clen + 4);
+                    const uint32_t d0 = lds_u32(words, xr + clen) ^ lds_u32(words, cand + clen);
+                    const uint32_t d1 = lds_u32(words, xr + clen + 4) ^ lds_u32(words, cand + clen + 4);
                     if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
                     len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
                     break;
@@ -196,37 +203,34 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 state = LS_WALK;
                 if (len > best) {
                     best = len;
-                    res = (len << 16) | (x - cand);
-                    if (best >= nice) { jb.M[x] = res; state = LS_IDLE; }
-                    else xw = lds_u32(words, x - ws + best - 3);
+                    res = (len << 16) | (xr - cand);
+                    if (best >= nice) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                    else { foff = best - 3; fmask = 0xffffffffu; xw = lds_u32(words, xr + foff); }
                 }
-                if (state == LS_WALK && --chain == 0) { jb.M[x] = res; state = LS_IDLE; }
+                if (state == LS_WALK && --chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
             }
             continue;
         }
-        if (state == LS_WALK) {
-            // next chain entry
-            uint32_t d = sL[cur - ws];
-            bool stop = d == 0;
-            cur -= d;
-            const uint32_t lim = first ? kMaxDist : kMaxDist - 1;
-            if (!stop) stop = x - cur > lim || cur == 0; // beyond the window (also keeps cur inside the staged range)
-            if (has_holes && !stop) {
-                const uint32_t i = cur - ws;
-                if ((sh[i >> 5] >> (i & 31)) & 1u) { // a hole: its staged link is the skip pointer to an inserted position
-                    d = sL[i];
-                    stop = d == 0;
-                    cur -= d;
-                    if (!stop) stop = x - cur > lim || cur == 0;
+#pragma unroll
+        for (uint32_t burst = 0; burst < kWalkBurst; burst++) {
+            if (state == LS_WALK) {
+                uint32_t d = sL[cr];
+                bool stop = d == 0 || cr < lowr + d; // chain ends or leaves the window
+                cr -= d;
+                if (has_holes && !stop) {
+                    if ((sh[cr >> 5] >> (cr & 31)) & 1u) { // a hole: its staged link is the skip pointer to an inserted position
+                        d = sL[cr];
+                        stop = d == 0 || cr < lowr + d;
+                        cr -= d;
+                    }
                 }
-            }
-            if (stop) { jb.M[x] = res; state = LS_IDLE; }
-            else {
-                first = false;
-                uint32_t cw = lds_u32(words, cur - ws + (best == 2 ? 0u : best - 3u));
-                if (best == 2) cw &= 0x00ffffffu;
-                if (cw == xw) { cand = cur; state = LS_PEND; }
-                else if (--chain == 0) { jb.M[x] = res; state = LS_IDLE; }
+                if (stop) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                else {
+                    if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
+                    const uint32_t cw = lds_u32(words, cr + foff) & fmask;
+                    if (cw == xw) { cand = cr; state = LS_PEND; }
+                    else if (--chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                }
             }
         }
     }
@@ -236,13 +240,15 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_next, s_any_hole;
-    const uint32_t ts = blockIdx.x * kMatchSub;
+    const uint32_t sub = jb.match_sub;
+    const uint32_t ts = blockIdx.x * sub;
     if (ts >= jb.N || !jb.tile_dirty[ts / kMatchTile]) return;
+    const uint32_t data_bytes = kWSize + sub + 512;
     uint8_t *sdata = smem;
-    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kMatchData);
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kMatchData + (kWSize + kMatchSub) * 2);
+    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + data_bytes);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + data_bytes + (kWSize + sub) * 2);
     const uint32_t N = jb.N;
-    const uint32_t te = min(ts + kMatchSub, N);
+    const uint32_t te = min(ts + sub, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) { s_next = ts; s_any_hole = 0; }
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         const uint32_t n16 = (te + 512 - ws + 15) / 16;
         const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
         uint4 *dst = reinterpret_cast<uint4 *>(sdata);
-        for (uint32_t i = tid; i < n16 && i < kMatchData / 16; i += 1024) dst[i] = src[i];
+        for (uint32_t i = tid; i < n16 && i < data_bytes / 16; i += 1024) dst[i] = src[i];
         // hole bits, then the chain links with the skip pointers substituted at hole positions
         const uint32_t nw = (te - ws + 31) / 32;
         uint32_t any = 0;
@@ -316,6 +322,7 @@ __global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= jb.tail_start) return;
+    if (!path_tile_dirty(jb, p / kPathTile)) return; // nothing this step can read has changed
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     uint32_t ns = 0;
     const uint32_t long_len = 16 * jb.lp.lazy;
@@ -332,6 +339,18 @@ __global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
 // path: tile-local resolution of "where does the parser leave this sub-tile/tile when it enters at p"
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kStuck = 0x80000000u;
+constexpr uint32_t kMacroReach = 22016; // a macro step starting at p reads M no further than p + kMacroReach
+
+// nxt[] of a path tile must be recomputed when M changed in the tile or within reach after it.
+__device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
+{
+    const uint32_t m0 = (pt * kPathTile) / kMatchTile;
+    uint32_t m1 = ((pt + 1) * kPathTile + kMacroReach - 1) / kMatchTile;
+    if (m1 >= jb.nmt) m1 = jb.nmt - 1;
+    bool d = false;
+    for (uint32_t m = m0; m <= m1; m++) d = d || jb.tile_dirty[m];
+    return d;
+}
 
 // Level 0 for one sub-tile [s0, s1) (tile-relative), executed by one warp.  nx: packed nxt values.
 // ex[p]: first path position >= s1 (tile-relative) or kStuck | tail-entry position; cn[p]: symbols on the way.
@@ -376,6 +395,7 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
     uint32_t *ex = nx + kPathTile;
     uint32_t *cn = ex + kPathTile;
     const uint32_t tbeg = blockIdx.x * kPathTile;
+    if (!path_tile_dirty(jb, blockIdx.x)) return; // nxt of this tile is unchanged: exits stay valid
     path_load(jb, tbeg, nx);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,8 +446,10 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
             for (uint32_t k = 0; k < nt; k++) {
                 const uint32_t t = c0 + k, tbeg = t * kPathTile, tend = tbeg + kPathTile;
                 jb.tile_symbase[t] = base;
-                if (done || e >= tend || e >= jb.tail_start) { jb.tile_entry[t] = 0xffffffffu; continue; }
-                jb.tile_entry[t] = e;
+                const uint32_t ne = (done || e >= tend || e >= jb.tail_start) ? 0xffffffffu : e;
+                jb.mark_needed[t] = (jb.tile_entry[t] != ne) || path_tile_dirty(jb, t);
+                jb.tile_entry[t] = ne;
+                if (ne == 0xffffffffu) continue;
                 uint32_t x, c;
                 if (e - tbeg < kPathHead) { const uint2 v = hd[k * kPathHead + (e - tbeg)]; x = v.x; c = v.y; }
                 else { x = jb.pexit[e]; c = jb.pcnt[e]; }
@@ -456,6 +478,7 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
     uint32_t *cn = ex + kPathTile;
     __shared__ uint32_t sub_entry[kPathTile / kPathSub], sub_base[kPathTile / kPathSub];
     const uint32_t tbeg = blockIdx.x * kPathTile;
+    if (!jb.mark_needed[blockIdx.x]) return; // same entry, same nxt: the marks of this tile are still right
     const uint32_t entry = jb.tile_entry[blockIdx.x];
     constexpr uint32_t nsub = kPathTile / kPathSub;
     if (entry == 0xffffffffu) { // no path node starts in this tile
@@ -469,7 +492,7 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
     for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t cur = entry - tbeg, cbase = jb.tile_symbase[blockIdx.x];
+        uint32_t cur = entry - tbeg, cbase = 0; // symbol indices are relative to the tile's symbol base
         for (uint32_t j = 0; j < nsub; j++) {
             if (!(cur & kStuck) && cur < (j + 1) * kPathSub) {
                 sub_entry[j] = cur;
@@ -537,7 +560,7 @@ __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
     const uint32_t idx = jb.symidx[p];
     if (!idx) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
-    uint32_t k = idx - 1, ns = 0;
+    uint32_t k = jb.tile_symbase[p / kPathTile] + idx - 1, ns = 0;
     Sym *syms = jb.syms;
     macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) { syms[k++] = s; }, &ns);
 }

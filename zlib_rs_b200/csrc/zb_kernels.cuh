@@ -67,6 +67,9 @@ struct JobBufs {
     uint32_t hdr_len;         // bytes before the first block: 0 / 2 / 10
     uint32_t xfl;             // gzip extra flags byte
     uint32_t huffman_only;    // Z_HUFFMAN_ONLY: symbols are all literals (algorithm/huff.rs)
+    uint32_t match_sub;       // positions per k_match CTA in this launch (multiple of 512)
+    uint32_t nmt;             // number of 32 KiB match tiles
+    uint8_t *mark_needed;     // path tiles whose marks must be recomputed
     uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
 };
 
