@@ -314,6 +314,19 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     }
 }
 
+constexpr uint32_t kMacroReach = 22016; // a macro step starting at p reads M no further than p + kMacroReach
+
+// nxt[] of a path tile must be recomputed when M changed in the tile or within reach after it.
+__device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
+{
+    const uint32_t m0 = (pt * kPathTile) / kMatchTile;
+    uint32_t m1 = ((pt + 1) * kPathTile + kMacroReach - 1) / kMatchTile;
+    if (m1 >= jb.nmt) m1 = jb.nmt - 1;
+    bool d = false;
+    for (uint32_t m = m0; m <= m1; m++) d = d || jb.tile_dirty[m];
+    return d;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_nxt: canonical macro step from every position below the tail zone.
 // nxt[p] = delta (16 bits) | symbols emitted (8 bits) << 16 | kNxtTail
@@ -339,19 +352,6 @@ __global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
 // path: tile-local resolution of "where does the parser leave this sub-tile/tile when it enters at p"
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kStuck = 0x80000000u;
-constexpr uint32_t kMacroReach = 22016; // a macro step starting at p reads M no further than p + kMacroReach
-
-// nxt[] of a path tile must be recomputed when M changed in the tile or within reach after it.
-__device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
-{
-    const uint32_t m0 = (pt * kPathTile) / kMatchTile;
-    uint32_t m1 = ((pt + 1) * kPathTile + kMacroReach - 1) / kMatchTile;
-    if (m1 >= jb.nmt) m1 = jb.nmt - 1;
-    bool d = false;
-    for (uint32_t m = m0; m <= m1; m++) d = d || jb.tile_dirty[m];
-    return d;
-}
-
 // Level 0 for one sub-tile [s0, s1) (tile-relative), executed by one warp.  nx: packed nxt values.
 // ex[p]: first path position >= s1 (tile-relative) or kStuck | tail-entry position; cn[p]: symbols on the way.
 __device__ __forceinline__ void path_subtile(const uint32_t *nx, uint32_t *ex, uint32_t *cn, uint32_t s0, uint32_t s1, uint32_t lane)
