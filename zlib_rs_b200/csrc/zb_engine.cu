@@ -32,7 +32,7 @@ __global__ void k_path_tiles(JobBufs);
 __global__ void k_path_chain(JobBufs, uint32_t);
 __global__ void k_path_mark(JobBufs);
 __global__ void k_emit(JobBufs);
-__global__ void k_holes(JobBufs);
+__global__ void k_holes(JobBufs, uint32_t);
 __global__ void k_holes_cmp(JobBufs, uint32_t, uint32_t);
 __global__ void k_tail(JobBufs);
 __global__ void k_block_hist(JobBufs, uint32_t *);
@@ -135,7 +135,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -171,6 +171,8 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
     const uint32_t max_blocks = N / kBlockSyms + 2;
     const size_t out_cap = (deflate_bound(n) + 15) & ~(size_t)15;
+    if ((rc = stage(nmt + 64)) != ZB_OK) return rc;
+    uint8_t *h_dirty = static_cast<uint8_t *>(h_stage);
 #define RES(slot, bytes, field, type)                                   \
     if ((rc = reserve(slot, bytes, &p)) != ZB_OK) return rc;            \
     jb.field = static_cast<type>(p);
@@ -194,6 +196,9 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_TENTRY, (size_t)npt * 4, tile_entry, uint32_t *)
     RES(S_TSYMB, (size_t)npt * 4, tile_symbase, uint32_t *)
     RES(S_MARKN, (size_t)npt + 16, mark_needed, uint8_t *)
+    const uint32_t nlists = npt * (kPathTile / kPathSub);
+    RES(S_LLIST, (size_t)nlists * kLongPerSub * 4, long_list, uint32_t *)
+    RES(S_LCNT, (size_t)nlists * 4, long_cnt, uint32_t *)
     RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
     RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
@@ -273,11 +278,12 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             launches++;
             pend(0, 1);
             if (jb.tail_start > 0) {
+                uint32_t n_dirty = nmt;
                 for (;;) {
                     iters++;
                     // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
                     // them over more SMs
-                    jb.match_sub = iters == 1 ? kMatchSub : 2048;
+                    jb.match_sub = n_dirty > 48 ? kMatchSub : 2048;
                     const uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4;
                     pbegin();
@@ -285,7 +291,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();
-                    k_nxt<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                    k_nxt<<<npt, 1024, 0, st>>>(jb);
                     pend(2, 1);
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
@@ -293,16 +299,19 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
                     pend(3, 3);
                     pbegin();
-                    k_holes<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
+                    k_holes<<<(nlists * kLongPerSub + 255) / 256, 256, 0, st>>>(jb, nlists);
                     CK(cudaMemsetAsync(jb.tile_dirty, 0, nmt, st));
                     CK(cudaMemsetAsync(&d_info->holes_changed, 0, 4, st));
                     k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
                     pend(4, 2);
                     launches += 7;
                     CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(h_dirty, jb.tile_dirty, nmt, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                     if (h_info->error) { snprintf(g_err, sizeof g_err, "engine error flags 0x%x (parse)", h_info->error); return ZB_E_INTERNAL; }
                     if (!h_info->holes_changed) break;
+                    n_dirty = 0;
+                    for (uint32_t i = 0; i < nmt; i++) n_dirty += h_dirty[i] != 0;
                     if (iters > 4096) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; }
                 }
             }

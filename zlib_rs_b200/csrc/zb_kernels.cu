@@ -331,21 +331,23 @@ __device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
 // k_nxt: canonical macro step from every position below the tail zone.
 // nxt[p] = delta (16 bits) | symbols emitted (8 bits) << 16 | kNxtTail
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_nxt(JobBufs jb)
+__global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= jb.tail_start) return;
-    if (!path_tile_dirty(jb, p / kPathTile)) return; // nothing this step can read has changed
+    if (!path_tile_dirty(jb, blockIdx.x)) return; // nothing a step of this tile can read has changed
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
-    uint32_t ns = 0;
     const uint32_t long_len = 16 * jb.lp.lazy;
-    bool is_long = false;
-    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
-        if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
-    }, &ns);
-    const uint32_t delta = np - p;
-    if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
-    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
+    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
+        const uint32_t p = blockIdx.x * kPathTile + i;
+        if (p >= jb.tail_start) break;
+        uint32_t ns = 0;
+        bool is_long = false;
+        const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+            if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
+        }, &ns);
+        const uint32_t delta = np - p;
+        if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
+        jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
     extern __shared__ __align__(16) uint8_t smem[];
     uint2 *hd = reinterpret_cast<uint2 *>(smem);
     __shared__ uint32_t s_e, s_base, s_done, s_tail;
+    __shared__ uint32_t c_entry[kChainChunk], c_base[kChainChunk];
     if (threadIdx.x == 0) { s_e = 0; s_base = 0; s_done = jb.tail_start == 0; s_tail = 0; }
     __syncthreads();
     for (uint32_t c0 = 0; c0 < ntiles; c0 += kChainChunk) {
@@ -444,12 +447,10 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
             bool done = s_done != 0;
             uint32_t tail_entry = s_tail;
             for (uint32_t k = 0; k < nt; k++) {
-                const uint32_t t = c0 + k, tbeg = t * kPathTile, tend = tbeg + kPathTile;
-                jb.tile_symbase[t] = base;
-                const uint32_t ne = (done || e >= tend || e >= jb.tail_start) ? 0xffffffffu : e;
-                jb.mark_needed[t] = (jb.tile_entry[t] != ne) || path_tile_dirty(jb, t);
-                jb.tile_entry[t] = ne;
-                if (ne == 0xffffffffu) continue;
+                const uint32_t tbeg = (c0 + k) * kPathTile, tend = tbeg + kPathTile;
+                c_base[k] = base;
+                if (done || e >= tend || e >= jb.tail_start) { c_entry[k] = 0xffffffffu; continue; }
+                c_entry[k] = e;
                 uint32_t x, c;
                 if (e - tbeg < kPathHead) { const uint2 v = hd[k * kPathHead + (e - tbeg)]; x = v.x; c = v.y; }
                 else { x = jb.pexit[e]; c = jb.pcnt[e]; }
@@ -458,6 +459,13 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
                 else e = x;
             }
             s_e = e; s_base = base; s_done = done; s_tail = tail_entry;
+        }
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
+            const uint32_t t = c0 + k;
+            jb.tile_symbase[t] = c_base[k];
+            jb.mark_needed[t] = (jb.tile_entry[t] != c_entry[k]) || path_tile_dirty(jb, t);
+            jb.tile_entry[t] = c_entry[k];
         }
         __syncthreads();
     }
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
     if (!jb.mark_needed[blockIdx.x]) return; // same entry, same nxt: the marks of this tile are still right
     const uint32_t entry = jb.tile_entry[blockIdx.x];
     constexpr uint32_t nsub = kPathTile / kPathSub;
+    if (threadIdx.x < nsub) jb.long_cnt[blockIdx.x * nsub + threadIdx.x] = 0;
     if (entry == 0xffffffffu) { // no path node starts in this tile
         for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
             if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = 0;
@@ -509,15 +518,18 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
         for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) {
             uint32_t p = sub_entry[s];
             if (p == 0xffffffffu) continue;
-            uint32_t idx = sub_base[s];
+            uint32_t idx = sub_base[s], nlong = 0;
             const uint32_t s1 = (s + 1) * kPathSub;
+            uint32_t *ll = jb.long_list + (size_t)(blockIdx.x * nsub + s) * kLongPerSub;
             while (p < s1) {
                 const uint32_t v = nx[p];
                 if (v & kNxtTail) break; // the tail entry is emitted by k_tail
+                if ((v & kNxtLong) && nlong < kLongPerSub) ll[nlong++] = tbeg + p; // its macro step leaves holes
                 ex[p] = idx + 1;
                 idx += (v >> 16) & 0xffu;
                 p += v & 0xffffu;
             }
+            jb.long_cnt[blockIdx.x * nsub + s] = nlong;
         }
     }
     __syncthreads();
@@ -529,11 +541,12 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
 // k_holes: the hole set implied by the current path (only nodes whose macro step contains a long match
 // need to be re-evaluated; k_nxt flagged them).  k_emit: the symbols of the final path.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_holes(JobBufs jb)
+__global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= jb.tail_start) return;
-    if (!jb.symidx[p] || !(jb.nxt[p] & kNxtLong)) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t list = t / kLongPerSub, slot = t % kLongPerSub;
+    if (list >= nlists || slot >= jb.long_cnt[list]) return;
+    const uint32_t p = jb.long_list[(size_t)list * kLongPerSub + slot];
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     uint32_t ns = 0;
     const uint32_t long_len = 16 * jb.lp.lazy;
@@ -572,8 +585,8 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
     if (w >= nwords) return;
     const uint32_t a = jb.holes[w], b = jb.holes_new[w];
     if (a != b) {
-        jb.info->holes_changed = 1;
         const uint32_t t = (w * 32) / kMatchTile;
+        atomicAdd(&jb.info->holes_changed, 1u); // number of changed bitmap words
         jb.tile_dirty[t] = 1;
         if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
         jb.holes[w] = b;

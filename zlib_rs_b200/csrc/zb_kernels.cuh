@@ -14,6 +14,7 @@ constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the mat
 constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
 constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
+constexpr uint32_t kLongPerSub = 8;     // a 1 KiB sub-tile holds at most 1024/257+1 long-match nodes
 constexpr uint32_t kPathHead = 64;      // leading positions of a path tile mirrored in the compact head table
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
 constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
@@ -70,6 +71,8 @@ struct JobBufs {
     uint32_t match_sub;       // positions per k_match CTA in this launch (multiple of 512)
     uint32_t nmt;             // number of 32 KiB match tiles
     uint8_t *mark_needed;     // path tiles whose marks must be recomputed
+    uint32_t *long_list;      // per path sub-tile: positions of path nodes whose macro step emits a long match
+    uint32_t *long_cnt;
     uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
 };
 
