@@ -291,7 +291,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();
-                    k_nxt<<<npt, 1024, 0, st>>>(jb);
+                    k_nxt<<<npt * (kPathTile / 1024), 1024, 0, st>>>(jb);
                     pend(2, 1);
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);

@@ -333,21 +333,20 @@ __device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
 {
-    if (!path_tile_dirty(jb, blockIdx.x)) return; // nothing a step of this tile can read has changed
+    // 16 CTAs per path tile, one position per thread; CTAs of clean tiles exit at once
+    if (!path_tile_dirty(jb, blockIdx.x / (kPathTile / 1024))) return;
+    const uint32_t p = blockIdx.x * 1024 + threadIdx.x;
+    if (p >= jb.tail_start) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     const uint32_t long_len = 16 * jb.lp.lazy;
-    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
-        const uint32_t p = blockIdx.x * kPathTile + i;
-        if (p >= jb.tail_start) break;
-        uint32_t ns = 0;
-        bool is_long = false;
-        const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
-            if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
-        }, &ns);
-        const uint32_t delta = np - p;
-        if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
-        jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
-    }
+    uint32_t ns = 0;
+    bool is_long = false;
+    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+        if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
+    }, &ns);
+    const uint32_t delta = np - p;
+    if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
+    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
