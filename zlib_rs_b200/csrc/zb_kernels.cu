@@ -140,26 +140,27 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 
 // Levels 5/6 (no early exit).  Semantics are those of lm_walk(): a candidate replaces the best match iff
 // its common prefix (<= 258) is strictly longer; the walk stops at nice_match, at the chain budget, or when
-// the chain leaves the window.  The 4-byte test at offset best-3 is only a filter for that condition (cf.
-// longest_match.rs:198-234).
+// the chain leaves the window.  The one-byte test at index `best` is only a filter for that condition (cf. the
+// 8-byte pre-checks at longest_match.rs:198-234); candidates that pass get the full word-wise compare.
 // Schedule: a lane is IDLE (needs a position), WALKing its chain one candidate per step, or PENDing a full
 // compare.  Position fetches and compares are batched -- they run only when at least kBatch lanes want them
 // (or nobody can walk) -- so the common walk step is not diluted by the rarer, longer code paths, and lanes
 // with short chains never wait for lanes with long ones.
 constexpr uint32_t kBatch = 8;
-constexpr uint32_t kWalkBurst = 4; // walk steps between two schedule checks
+constexpr uint32_t kWalkBurst = 8; // walk steps between two schedule checks
 enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
 
+template <bool kHoles>
 __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
-                                                bool has_holes, uint32_t ws, uint32_t te, uint32_t *s_next)
+                                                uint32_t ws, uint32_t te, uint32_t *s_next)
 {
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
     const uint32_t lane = threadIdx.x & 31;
     // per-lane state, all positions relative to ws
-    uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, xw = 0, cand = 0;
-    uint32_t foff = 0, fmask = 0x00ffffffu; // filter: 4 bytes at offset best-3 (3 bytes at 0 while best == 2)
-    uint32_t lowr = 0;                       // lowest admissible candidate (relative): x - lim
+    uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, cand = 0;
+    uint32_t xb = 0;   // byte of x at index `best`: a longer match must reproduce it (one-byte filter, then full compare)
+    uint32_t lowr = 0; // lowest admissible candidate (relative): x - lim
     uint32_t state = LS_IDLE;
     for (;;) {
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
@@ -178,8 +179,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 else if (x + kMSafe > N) { jb.M[x] = 0; }
                 else {
                     xr = x - ws; cr = xr; best = 2; chain = budget; res = 0;
-                    foff = 0; fmask = 0x00ffffffu;
-                    xw = lds_u32(words, xr) & fmask;
+                    xb = sdata[xr + 2];
                     // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
                     // absolute position 0 is never a candidate
                     lowr = xr > kMaxDist ? xr - kMaxDist : 0;
@@ -205,7 +205,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     best = len;
                     res = (len << 16) | (xr - cand);
                     if (best >= nice) { jb.M[ws + xr] = res; state = LS_IDLE; }
-                    else { foff = best - 3; fmask = 0xffffffffu; xw = lds_u32(words, xr + foff); }
+                    else xb = sdata[xr + best];
                 }
                 if (state == LS_WALK && --chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
             }
@@ -217,7 +217,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 uint32_t d = sL[cr];
                 bool stop = d == 0 || cr < lowr + d; // chain ends or leaves the window
                 cr -= d;
-                if (has_holes && !stop) {
+                if (kHoles && !stop) {
                     if ((sh[cr >> 5] >> (cr & 31)) & 1u) { // a hole: its staged link is the skip pointer to an inserted position
                         d = sL[cr];
                         stop = d == 0 || cr < lowr + d;
@@ -227,8 +227,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 if (stop) { jb.M[ws + xr] = res; state = LS_IDLE; }
                 else {
                     if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
-                    const uint32_t cw = lds_u32(words, cr + foff) & fmask;
-                    if (cw == xw) { cand = cr; state = LS_PEND; }
+                    if (sdata[cr + best] == xb) { cand = cr; state = LS_PEND; }
                     else if (--chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
                 }
             }
@@ -299,7 +298,8 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     }
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
-        match_tile_fast(jb, sdata, sL, sh, has_holes, ws, te, &s_next);
+        if (has_holes) match_tile_fast<true>(jb, sdata, sL, sh, ws, te, &s_next);
+        else match_tile_fast<false>(jb, sdata, sL, sh, ws, te, &s_next);
         return;
     }
     // levels 3/4 (early exit): generic walk; a hole's staged link already bridges to an inserted position
