@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         // window.  A chain walk then bridges any run of holes in one extra step.
         __shared__ uint32_t s_changed;
         for (uint32_t round = 0; round < 24; round++) {
+            __syncthreads(); // everybody has read s_changed of the previous round
             if (tid == 0) s_changed = 0;
             __syncthreads();
             bool ch = false;
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             }
             if (ch) s_changed = 1;
             __syncthreads();
-            if (!s_changed) break;
+            const bool any = s_changed != 0;
+            if (!any) break;
         }
         __syncthreads();
     }
