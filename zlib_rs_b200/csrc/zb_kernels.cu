@@ -150,17 +150,31 @@ constexpr uint32_t kBatch = 8;
 constexpr uint32_t kWalkBurst = 8; // walk steps between two schedule checks
 enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
 
+// explicit shared-space loads on 32-bit shared addresses (keeps address-space conversions out of the hot loop)
+__device__ __forceinline__ uint32_t sld_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sld_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sld_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t sld_u32u(uint32_t a) // unaligned
+{
+    const uint32_t al = a & ~3u;
+    return __funnelshift_r(sld_u32(al), sld_u32(al + 4), (a & 3u) * 8u);
+}
+
 template <bool kHoles>
 __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
                                                 uint32_t ws, uint32_t te, uint32_t *s_next)
 {
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(sdata);
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(sdata);
+    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(sL);
+    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
     const uint32_t lane = threadIdx.x & 31;
+    uint32_t *const Mout = jb.M + ws;
     // per-lane state, all positions relative to ws
     uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, cand = 0;
-    uint32_t xb = 0;   // byte of x at index `best`: a longer match must reproduce it (one-byte filter, then full compare)
-    uint32_t lowr = 0; // lowest admissible candidate (relative): x - lim
+    uint32_t xb = 0;    // byte of x at index `best`: a longer match must reproduce it (one-byte filter, then full compare)
+    uint32_t fbase = 0; // dbase + best
+    uint32_t lowr = 0;  // lowest admissible candidate (relative): x - lim
     uint32_t state = LS_IDLE;
     for (;;) {
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
@@ -179,7 +193,8 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 else if (x + kMSafe > N) { jb.M[x] = 0; }
                 else {
                     xr = x - ws; cr = xr; best = 2; chain = budget; res = 0;
-                    xb = sdata[xr + 2];
+                    fbase = dbase + 2;
+                    xb = sld_u8(fbase + xr);
                     // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
                     // absolute position 0 is never a candidate
                     lowr = xr > kMaxDist ? xr - kMaxDist : 0;
@@ -192,9 +207,10 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
         if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
             if (state == LS_PEND) {
                 uint32_t clen = 0, len;
+                const uint32_t pa = dbase + xr, pb = dbase + cand;
                 for (;;) {
-                    const uint32_t d0 = lds_u32(words, xr + clen) ^ lds_u32(words, cand + clen);
-                    const uint32_t d1 = lds_u32(words, xr + clen + 4) ^ lds_u32(words, cand + clen + 4);
+                    const uint32_t d0 = sld_u32u(pa + clen) ^ sld_u32u(pb + clen);
+                    const uint32_t d1 = sld_u32u(pa + clen + 4) ^ sld_u32u(pb + clen + 4);
                     if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
                     len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
                     break;
@@ -204,31 +220,31 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 if (len > best) {
                     best = len;
                     res = (len << 16) | (xr - cand);
-                    if (best >= nice) { jb.M[ws + xr] = res; state = LS_IDLE; }
-                    else xb = sdata[xr + best];
+                    if (best >= nice) { Mout[xr] = res; state = LS_IDLE; }
+                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
                 }
-                if (state == LS_WALK && --chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; state = LS_IDLE; }
             }
             continue;
         }
 #pragma unroll
         for (uint32_t burst = 0; burst < kWalkBurst; burst++) {
             if (state == LS_WALK) {
-                uint32_t d = sL[cr];
+                uint32_t d = sld_u16(lbase + 2 * cr);
                 bool stop = d == 0 || cr < lowr + d; // chain ends or leaves the window
                 cr -= d;
                 if (kHoles && !stop) {
-                    if ((sh[cr >> 5] >> (cr & 31)) & 1u) { // a hole: its staged link is the skip pointer to an inserted position
-                        d = sL[cr];
+                    if ((sld_u32(hbase + 4 * (cr >> 5)) >> (cr & 31)) & 1u) { // a hole: its staged link is the skip pointer
+                        d = sld_u16(lbase + 2 * cr);
                         stop = d == 0 || cr < lowr + d;
                         cr -= d;
                     }
                 }
-                if (stop) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                if (stop) { Mout[xr] = res; state = LS_IDLE; }
                 else {
                     if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
-                    if (sdata[cr + best] == xb) { cand = cr; state = LS_PEND; }
-                    else if (--chain == 0) { jb.M[ws + xr] = res; state = LS_IDLE; }
+                    if (sld_u8(fbase + cr) == xb) { cand = cr; state = LS_PEND; }
+                    else if (--chain == 0) { Mout[xr] = res; state = LS_IDLE; }
                 }
             }
         }
