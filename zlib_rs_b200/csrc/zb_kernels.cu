@@ -147,7 +147,7 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 // (or nobody can walk) -- so the common walk step is not diluted by the rarer, longer code paths, and lanes
 // with short chains never wait for lanes with long ones.
 constexpr uint32_t kBatch = 8;
-constexpr uint32_t kWalkBurst = 8; // walk steps between two schedule checks
+constexpr uint32_t kWalkBurst = 4; // walk steps between two schedule checks
 enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
 
 // explicit shared-space loads on 32-bit shared addresses (keeps address-space conversions out of the hot loop)
@@ -172,7 +172,8 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     uint32_t *const Mout = jb.M + ws;
     // per-lane state, all positions relative to ws
     uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, cand = 0;
-    uint32_t xb = 0;    // byte of x at index `best`: a longer match must reproduce it (one-byte filter, then full compare)
+    uint32_t xb = 0;    // byte of x at index `best`: a longer match must reproduce it (one-byte filter first)
+    uint32_t xw0 = 0;   // first four bytes of x: second-stage filter before a full compare is scheduled
     uint32_t fbase = 0; // dbase + best
     uint32_t lowr = 0;  // lowest admissible candidate (relative): x - lim
     uint32_t state = LS_IDLE;
@@ -195,6 +196,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     xr = x - ws; cr = xr; best = 2; chain = budget; res = 0;
                     fbase = dbase + 2;
                     xb = sld_u8(fbase + xr);
+                    xw0 = sld_u32u(dbase + xr);
                     // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
                     // absolute position 0 is never a candidate
                     lowr = xr > kMaxDist ? xr - kMaxDist : 0;
@@ -243,7 +245,12 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 if (stop) { Mout[xr] = res; state = LS_IDLE; }
                 else {
                     if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
-                    if (sld_u8(fbase + cr) == xb) { cand = cr; state = LS_PEND; }
+                    bool pass = sld_u8(fbase + cr) == xb;
+                    if (pass) { // the first 3 (best == 2) / 4 bytes must match as well
+                        const uint32_t dw = sld_u32u(dbase + cr) ^ xw0;
+                        pass = (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+                    }
+                    if (pass) { cand = cr; state = LS_PEND; }
                     else if (--chain == 0) { Mout[xr] = res; state = LS_IDLE; }
                 }
             }
