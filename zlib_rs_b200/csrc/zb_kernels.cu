@@ -264,7 +264,11 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     __shared__ uint32_t s_next, s_any_hole;
     const uint32_t sub = jb.match_sub;
     const uint32_t ts = blockIdx.x * sub;
-    if (ts >= jb.N || !jb.tile_dirty[ts / kMatchTile]) return;
+    if (ts >= jb.N) return;
+    {
+        const uint32_t t0 = ts / kMatchTile, t1 = (min(ts + sub, jb.N) - 1) / kMatchTile;
+        if (!jb.tile_dirty[t0] && !jb.tile_dirty[t1]) return;
+    }
     const uint32_t data_bytes = kWSize + sub + 512;
     uint8_t *sdata = smem;
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem + data_bytes);
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) { s_next = ts; s_any_hole = 0; }
+    const uint32_t nw = (te - ws + 31) / 32;
     __syncthreads();
     {
         // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
@@ -282,7 +287,6 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         uint4 *dst = reinterpret_cast<uint4 *>(sdata);
         for (uint32_t i = tid; i < n16 && i < data_bytes / 16; i += 1024) dst[i] = src[i];
         // hole bits, then the chain links with the skip pointers substituted at hole positions
-        const uint32_t nw = (te - ws + 31) / 32;
         uint32_t any = 0;
         for (uint32_t i = tid; i < nw; i += 1024) { const uint32_t w = jb.holes[(ws >> 5) + i]; sh[i] = w; any |= w; }
         if (any) s_any_hole = 1;
@@ -303,16 +307,21 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             if (tid == 0) s_changed = 0;
             __syncthreads();
             bool ch = false;
-            for (uint32_t i = tid; i < te - ws; i += 1024) {
-                if (!((sh[i >> 5] >> (i & 31)) & 1u)) continue;
-                const uint32_t d = sL[i];
-                if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
-                const uint32_t t = i - d;
-                if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
-                const uint32_t d2 = sL[t];
-                const uint32_t nd = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
-                sL[i] = (uint16_t)nd;
-                ch = true;
+            for (uint32_t w = tid; w < nw; w += 1024) { // one bitmap word (32 positions) at a time: work ~ number of holes
+                uint32_t bits = sh[w];
+                while (bits) {
+                    const uint32_t i = w * 32 + (__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    if (i >= te - ws) break;
+                    const uint32_t d = sL[i];
+                    if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
+                    const uint32_t t = i - d;
+                    if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
+                    const uint32_t d2 = sL[t];
+                    const uint32_t nd = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
+                    sL[i] = (uint16_t)nd;
+                    ch = true;
+                }
             }
             if (ch) s_changed = 1;
             __syncthreads();
