@@ -283,7 +283,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     iters++;
                     // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
                     // them over more SMs
-                    jb.match_sub = n_dirty > 16 ? kMatchSub : 1024;
+                    jb.match_sub = n_dirty > 48 ? kMatchSub : 2048;
                     const uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4;
                     pbegin();

@@ -11,7 +11,7 @@ namespace zb {
 constexpr uint32_t kLinkTile = 32768;   // positions per k_links CTA
 constexpr uint32_t kLinkWarm = 32512;   // warm-up positions before the tile (>= kMaxDist)
 constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the match phase
-constexpr uint32_t kMatchSub = 3072;    // positions per k_match CTA: 110 KiB of shared memory, two CTAs per SM
+constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA (126 KiB of shared memory)
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
 constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
 constexpr uint32_t kLongPerSub = 8;     // a 1 KiB sub-tile holds at most 1024/257+1 long-match nodes
