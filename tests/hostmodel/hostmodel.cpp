@@ -276,3 +276,91 @@ extern "C" int hm_deflate(const uint8_t *data, uint32_t N, int level, uint8_t *d
     *data_type_out = data_type;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Block-parallel inflate: header scout (zb_inflate_core.h) against a serial walk of the stream.
+// ------------------------------------------------------------------------------------------
+#include "../../zlib_rs_b200/csrc/zb_inflate_core.h"
+
+namespace {
+struct Canon { uint16_t cnt[16], first[16], offs[16], sorted[320]; };
+void canon_build(Canon &c, const uint16_t *lens, uint32_t n)
+{
+    for (int i = 0; i < 16; i++) c.cnt[i] = 0;
+    for (uint32_t i = 0; i < n; i++) c.cnt[lens[i]]++;
+    c.cnt[0] = 0;
+    uint32_t code = 0, o = 0;
+    uint16_t nx[16];
+    for (int len = 1; len <= 15; len++) { c.first[len] = (uint16_t)code; c.offs[len] = (uint16_t)o; nx[len] = (uint16_t)o; code = (code + c.cnt[len]) << 1; o += c.cnt[len]; }
+    for (uint32_t s = 0; s < n; s++) if (lens[s]) c.sorted[nx[lens[s]]++] = (uint16_t)s;
+}
+int canon_decode(const Canon &c, const BitSrc &s, uint64_t &pos)
+{
+    uint32_t bits = s.peek32(pos), code = 0;
+    for (int len = 1; len <= 15; len++) {
+        code = (code << 1) | (bits & 1u);
+        bits >>= 1;
+        if (c.cnt[len] && code >= c.first[len] && code - c.first[len] < c.cnt[len]) { pos += len; return c.sorted[c.offs[len] + code - c.first[len]]; }
+    }
+    return -1;
+}
+}
+
+// Serial walk: returns the bit positions of all dynamic block headers, -1 on a stream this simple walker cannot follow.
+extern "C" int hm_inflate_walk(const uint8_t *src, uint32_t n, uint64_t start_bit, uint64_t *dyn_starts, uint32_t cap, uint32_t *ndyn,
+                               uint64_t *out_len)
+{
+    BitSrc s{src, n};
+    uint64_t pos = start_bit, out = 0;
+    uint32_t k = 0;
+    std::vector<uint16_t> lens(320);
+    for (;;) {
+        const uint32_t w = s.peek32(pos);
+        const uint32_t last = w & 1, type = (w >> 1) & 3;
+        if (type == 0) {
+            uint64_t p = (pos + 3 + 7) & ~7ull;
+            const uint32_t v = s.peek32(p);
+            out += v & 0xffff;
+            pos = p + 32 + 8ull * (v & 0xffff);
+        } else if (type == 2) {
+            DynHeader h;
+            if (!parse_dynamic_header(s, pos, h, lens.data())) return -2;
+            if (k < cap) dyn_starts[k] = pos;
+            k++;
+            Canon L, D;
+            canon_build(L, lens.data(), h.hlit);
+            canon_build(D, lens.data() + h.hlit, h.hdist);
+            pos = h.body_bit;
+            for (;;) {
+                int sym = canon_decode(L, s, pos);
+                if (sym < 0) return -3;
+                if (sym < 256) { out++; continue; }
+                if (sym == 256) break;
+                const uint32_t c = sym - 257;
+                uint32_t len = len_base(c) + (s.peek32(pos) & ((1u << len_extra(c)) - 1));
+                pos += len_extra(c);
+                int ds = canon_decode(D, s, pos);
+                if (ds < 0) return -4;
+                pos += dist_extra(ds);
+                out += len;
+            }
+        } else return -1;
+        if (last) break;
+    }
+    *ndyn = k;
+    *out_len = out;
+    return 0;
+}
+
+extern "C" int hm_inflate_scout(const uint8_t *src, uint32_t n, uint64_t *cands, uint32_t cap, uint32_t *ncand)
+{
+    BitSrc s{src, n};
+    std::vector<uint16_t> lens(320);
+    uint32_t k = 0;
+    for (uint64_t b = 0; b + 40 < (uint64_t)n * 8; b++) {
+        DynHeader h;
+        if (parse_dynamic_header(s, b, h, lens.data())) { if (k < cap) cands[k] = b; k++; }
+    }
+    *ncand = k;
+    return 0;
+}

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "zb_engine_internal.h"
+#include "zb_inflate_core.h"
 
 namespace zb {
 
@@ -403,6 +404,416 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
 #undef FAIL
 }
 
+// ================================================================================================
+// Block-parallel inflate (see zb_inflate_core.h for the scheme)
+// ================================================================================================
+constexpr uint32_t kMaxCand = 1u << 16;
+constexpr uint32_t kMaxBlocks = 1u << 16;
+constexpr uint32_t kHashSize = 1u << 18;
+enum { PS_OK = 0, PS_FALLBACK = 1 };
+
+struct InfCand { uint64_t start_bit, end_bit; uint32_t out_len, valid, bfinal, pad; };
+struct InfBlock { uint64_t start_bit, out_off; uint32_t out_len, type, src_byte, pad; };
+struct InfPar {
+    uint32_t ncand, nblocks, status, kind;
+    uint64_t first_bit, total_out, end_bit;
+    uint32_t trailer_check, trailer_len, decode_err, pad;
+};
+
+// stream header (inflate.rs:926-1010 Head .. :1222 HCrc): zlib 2 bytes, gzip 10 + optional fields
+__global__ void k_inf_header(const uint8_t *src, uint64_t n, int window_bits, InfPar *par)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    par->status = PS_OK;
+    if (window_bits < 0) { par->kind = 0; par->first_bit = 0; return; }
+    if (n < 2) { par->status = PS_FALLBACK; return; }
+    const uint32_t h = src[0] | (src[1] << 8);
+    if (window_bits > 15 && h == 0x8b1f) {
+        if (n < 18) { par->status = PS_FALLBACK; return; }
+        const uint32_t fl = src[3];
+        if (src[2] != 8 || (fl & 0xe0)) { par->status = PS_FALLBACK; return; }
+        uint64_t p = 10;
+        if (fl & 4) { if (p + 2 > n) { par->status = PS_FALLBACK; return; } p += 2 + (src[p] | (src[p + 1] << 8)); }
+        if (fl & 8) { while (p < n && src[p]) p++; p++; }
+        if (fl & 16) { while (p < n && src[p]) p++; p++; }
+        if (fl & 2) p += 2;
+        if (p >= n) { par->status = PS_FALLBACK; return; }
+        par->kind = 2;
+        par->first_bit = p * 8;
+        return;
+    }
+    if ((window_bits > 15 && window_bits < 32) || (((h & 0xff) << 8) + (h >> 8)) % 31 || (h & 0xf) != 8 || (h & 0x2000)) { par->status = PS_FALLBACK; return; }
+    const uint32_t wb = ((h >> 4) & 0xf) + 8, want = (uint32_t)(window_bits & 15);
+    if (wb > 15 || (want != 0 && wb > want)) { par->status = PS_FALLBACK; return; }
+    par->kind = 1;
+    par->first_bit = 16;
+}
+
+// 1. every bit position: valid dynamic block header?  A CTA stages 1 KiB of the stream (+ halo) in shared memory and
+// tests its 8192 bit positions.  The test of the code-length code's completeness runs on registers; only positions
+// that pass it (about one in a thousand) run the full header parse.
+constexpr uint32_t kScoutBytes = 1024, kScoutHalo = 16;
+__global__ void __launch_bounds__(256) k_inf_scout(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand, uint32_t *htab)
+{
+    __shared__ uint32_t sw[(kScoutBytes + kScoutHalo) / 4 + 1];
+    if (par->status != PS_OK) return;
+    const uint64_t first_byte = par->first_bit >> 3;
+    const uint64_t base = first_byte + (uint64_t)blockIdx.x * kScoutBytes;
+    if (base >= n) return;
+    uint8_t *sb = reinterpret_cast<uint8_t *>(sw);
+    for (uint32_t i = threadIdx.x; i < kScoutBytes + kScoutHalo; i += 256) sb[i] = base + i < n ? src[base + i] : 0;
+    __syncthreads();
+    const uint64_t nbits = n * 8;
+    for (uint32_t r = 0; r < kScoutBytes * 8 / 256; r++) {
+        const uint32_t rb = r * 256 + threadIdx.x; // bit inside the chunk
+        const uint64_t b = base * 8 + rb;
+        if (b < par->first_bit || b + 64 > nbits) continue;
+        const uint32_t wi = rb >> 5, sh = rb & 31;
+        const uint32_t w0 = sw[wi], w1 = sw[wi + 1], w2 = sw[wi + 2], w3 = sw[wi + 3];
+        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+        if (((a0 >> 1) & 3u) != 2u || ((a0 >> 3) & 31u) > 29u || ((a0 >> 8) & 31u) > 29u) continue;
+        const uint32_t hclen = ((a0 >> 13) & 15u) + 4u;
+        // 3-bit code lengths start at bit 17: Kraft sum in units of 2^-7 must be exactly 128
+        uint64_t f = ((uint64_t)a2 << 47) | ((uint64_t)a1 << 15) | (a0 >> 17); // 57 bits are enough: 19 * 3
+        uint32_t sum = 0;
+        for (uint32_t i = 0; i < hclen; i++) {
+            const uint32_t v = (uint32_t)(f & 7u);
+            f >>= 3;
+            sum += v ? (128u >> v) : 0u;
+        }
+        if (sum != 128u) continue;
+        uint16_t lens[320];
+        DynHeader h;
+        BitSrc s{src, n};
+        if (!parse_dynamic_header(s, b, h, lens)) continue;
+        const uint32_t k = atomicAdd(&par->ncand, 1u);
+        if (k < kMaxCand) {
+            cand[k].start_bit = b;
+            cand[k].valid = 0;
+            uint32_t hsh = (uint32_t)((b * 0x9E3779B97F4A7C15ull) >> 47) & (kHashSize - 1);
+            while (atomicCAS(&htab[hsh], 0u, k + 1) != 0u) hsh = (hsh + 1) & (kHashSize - 1);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t cand_lookup(const uint32_t *htab, const InfCand *cand, uint64_t b)
+{
+    uint32_t hsh = (uint32_t)((b * 0x9E3779B97F4A7C15ull) >> 47) & (kHashSize - 1);
+    for (;;) {
+        const uint32_t v = htab[hsh];
+        if (v == 0) return 0xffffffffu;
+        if (cand[v - 1].start_bit == b) return v - 1;
+        hsh = (hsh + 1) & (kHashSize - 1);
+    }
+}
+
+struct DecShared {
+    ICode lencode[kEnoughLens], distcode[kEnoughDists];
+    uint16_t lens[320], work[288];
+    uint32_t q[32];
+    uint32_t qn, done, err;
+    uint64_t end_bit;
+};
+
+// bit reader of the decoding lane: 64-bit hold, refilled 32 bits at a time with aligned loads
+struct BitRd {
+    const uint32_t *w;
+    const uint8_t *src;
+    uint64_t n, ipos, hold;
+    uint32_t off, bits;
+    __device__ __forceinline__ uint32_t load32(uint64_t bi) const
+    {
+        if (bi + 8 <= n) {
+            const uint64_t g = bi + off;
+            const uint32_t *q = w + (g >> 2);
+            return __funnelshift_r(__ldg(q), __ldg(q + 1), (uint32_t)(g & 3) * 8);
+        }
+        uint32_t v = 0;
+        for (int i = 0; i < 4; i++) v |= (uint32_t)(bi + i < n ? src[bi + i] : 0) << (8 * i);
+        return v;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (bits < 32) { hold |= (uint64_t)load32(ipos) << bits; ipos += 4; bits += 32; }
+    }
+    __device__ __forceinline__ void drop(uint32_t k) { hold >>= k; bits -= k; }
+    __device__ void init(const uint8_t *s, uint64_t n_, uint64_t bitpos)
+    {
+        src = s; n = n_;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        off = (uint32_t)(a & 3);
+        ipos = bitpos >> 3; hold = 0; bits = 0;
+        refill();
+        drop((uint32_t)(bitpos & 7));
+    }
+    __device__ __forceinline__ uint64_t consumed() const { return ipos * 8 - bits; }
+};
+
+// Build the tables of the dynamic block at start_bit (decoding lane only).  0 ok.
+__device__ int dec_setup(DecShared &S, const uint8_t *src, uint64_t n, uint64_t start_bit, BitRd &br, uint32_t &lenbits, uint32_t &distbits,
+                         uint32_t *bfinal)
+{
+    BitSrc bs{src, n};
+    DynHeader h;
+    if (!parse_dynamic_header(bs, start_bit, h, S.lens)) return 1;
+    if (inflate_table(1, S.lens, h.hlit, S.lencode, 10, S.work, &lenbits)) return 2;
+    if (inflate_table(2, S.lens + h.hlit, h.hdist, S.distcode, 9, S.work, &distbits)) return 3;
+    *bfinal = h.bfinal;
+    br.init(src, n, h.body_bit);
+    return 0;
+}
+
+// One symbol: returns 0 literal (val), 1 match (len, dist), 2 end of block, <0 error.
+__device__ __forceinline__ int dec_symbol(const DecShared &S, BitRd &br, uint32_t lenmask, uint32_t distmask, uint32_t &val, uint32_t &dist)
+{
+    br.refill();
+    ICode here = S.lencode[(uint32_t)br.hold & lenmask];
+    if (here.op && (here.op & 0xf0) == 0) {
+        const ICode l = here;
+        here = S.lencode[l.val + (((uint32_t)br.hold & ((1u << (l.bits + l.op)) - 1)) >> l.bits)];
+        br.drop(l.bits);
+    }
+    br.drop(here.bits);
+    if (here.op == 0) { val = here.val; return 0; }
+    if (here.op & 32) return 2;
+    if (here.op & 64) return -4;
+    uint32_t len = here.val;
+    uint32_t ex = here.op & 15;
+    if (ex) { len += (uint32_t)br.hold & ((1u << ex) - 1); br.drop(ex); }
+    br.refill();
+    here = S.distcode[(uint32_t)br.hold & distmask];
+    if ((here.op & 0xf0) == 0) {
+        const ICode l = here;
+        here = S.distcode[l.val + (((uint32_t)br.hold & ((1u << (l.bits + l.op)) - 1)) >> l.bits)];
+        br.drop(l.bits);
+    }
+    br.drop(here.bits);
+    if (here.op & 64) return -5;
+    uint32_t d = here.val;
+    ex = here.op & 15;
+    if (ex) { d += (uint32_t)br.hold & ((1u << ex) - 1); br.drop(ex); }
+    val = len;
+    dist = d;
+    return 1;
+}
+
+constexpr uint32_t kMaxBlockOut = 256u << 20;
+
+// 2. measure every candidate (one decoding lane per candidate, no output)
+__global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand)
+{
+    __shared__ DecShared S;
+    const uint32_t k = blockIdx.x;
+    if (k >= par->ncand || k >= kMaxCand || threadIdx.x != 0) return;
+    BitRd br;
+    uint32_t lenbits, distbits, bf = 0;
+    int rc = dec_setup(S, src, n, cand[k].start_bit, br, lenbits, distbits, &bf);
+    uint32_t o = 0;
+    if (rc == 0) {
+        const uint32_t lm = (1u << lenbits) - 1, dm = (1u << distbits) - 1;
+        const uint64_t nbits = n * 8;
+        for (;;) {
+            uint32_t v, d;
+            const int t = dec_symbol(S, br, lm, dm, v, d);
+            if (t == 0) { o++; continue; }
+            if (t == 1) {
+                o += v;
+                if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; break; }
+                continue;
+            }
+            if (t < 0) rc = -t;
+            break;
+        }
+        if (rc == 0 && br.consumed() > nbits) rc = 8;
+    }
+    cand[k].end_bit = br.consumed();
+    cand[k].out_len = o;
+    cand[k].bfinal = bf;
+    cand[k].valid = rc == 0;
+}
+
+// 3. follow the chain of blocks from the first one
+__global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const InfCand *cand, const uint32_t *htab, InfBlock *blocks)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (par->status != PS_OK) return;
+    BitSrc s{src, n};
+    uint64_t pos = par->first_bit, out = 0;
+    uint32_t nb = 0;
+    for (;;) {
+        if (pos + 3 > n * 8 || nb >= kMaxBlocks) { par->status = PS_FALLBACK; return; }
+        const uint32_t w = s.peek32(pos);
+        const uint32_t last = w & 1u, type = (w >> 1) & 3u;
+        InfBlock &b = blocks[nb];
+        b.start_bit = pos;
+        b.out_off = out;
+        b.type = type;
+        if (type == 0) {
+            const uint64_t p = (pos + 3 + 7) & ~7ull;
+            if (p + 32 > n * 8) { par->status = PS_FALLBACK; return; }
+            const uint32_t v = s.peek32(p);
+            if ((v & 0xffff) != ((v >> 16) ^ 0xffff)) { par->status = PS_FALLBACK; return; }
+            b.out_len = v & 0xffff;
+            b.src_byte = (uint32_t)((p >> 3) + 4);
+            pos = p + 32 + 8ull * b.out_len;
+            if (pos > n * 8) { par->status = PS_FALLBACK; return; }
+        } else if (type == 2) {
+            const uint32_t f = cand_lookup(htab, cand, pos);
+            if (f == 0xffffffffu || !cand[f].valid) { par->status = PS_FALLBACK; return; }
+            b.out_len = cand[f].out_len;
+            pos = cand[f].end_bit;
+        } else { par->status = PS_FALLBACK; return; } // fixed-code blocks / invalid type: serial decoder
+        out += b.out_len;
+        nb++;
+        if (last) break;
+    }
+    par->nblocks = nb;
+    par->total_out = out;
+    // trailer (inflate.rs:1398-1430, 1779-1795)
+    const uint64_t tb = (pos + 7) >> 3;
+    par->end_bit = tb * 8;
+    uint32_t chk = 0, isz = 0;
+    if (par->kind == 1) {
+        if (tb + 4 > n) { par->status = PS_FALLBACK; return; }
+        chk = ((uint32_t)src[tb] << 24) | ((uint32_t)src[tb + 1] << 16) | ((uint32_t)src[tb + 2] << 8) | src[tb + 3];
+        par->end_bit = (tb + 4) * 8;
+    } else if (par->kind == 2) {
+        if (tb + 8 > n) { par->status = PS_FALLBACK; return; }
+        chk = src[tb] | ((uint32_t)src[tb + 1] << 8) | ((uint32_t)src[tb + 2] << 16) | ((uint32_t)src[tb + 3] << 24);
+        isz = src[tb + 4] | ((uint32_t)src[tb + 5] << 8) | ((uint32_t)src[tb + 6] << 16) | ((uint32_t)src[tb + 7] << 24);
+        par->end_bit = (tb + 8) * 8;
+    }
+    par->trailer_check = chk;
+    par->trailer_len = isz;
+}
+
+// 4. all chained blocks in parallel -> 16-bit symbols.  One warp per block: lane 0 decodes 32 symbols at a time into a
+// queue, then the warp replays them on a 32 Ki-symbol ring in shared memory (a run of literals in one step, a match in
+// ceil(len/32) steps) and streams the ring out to global memory in coalesced pieces.
+struct DecodeShared {
+    DecShared d;
+    uint16_t win[kWSize];
+};
+
+__global__ void __launch_bounds__(32) k_inf_decode(const uint8_t *src, uint64_t n, InfPar *par, const InfBlock *blocks, uint16_t *tmp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecodeShared &S = *reinterpret_cast<DecodeShared *>(smem_raw);
+    const uint32_t k = blockIdx.x;
+    if (k >= par->nblocks) return;
+    const InfBlock b = blocks[k];
+    const uint32_t lane = threadIdx.x;
+    uint16_t *dst = tmp + b.out_off;
+    if (b.type == 0) {
+        for (uint32_t i = lane; i < b.out_len; i += 32) dst[i] = src[b.src_byte + i];
+        return;
+    }
+    BitRd br;
+    uint32_t lm = 0, dm = 0;
+    if (lane == 0) {
+        uint32_t lenbits, distbits, bf;
+        const int rc = dec_setup(S.d, src, n, b.start_bit, br, lenbits, distbits, &bf);
+        S.d.err = rc != 0;
+        S.d.done = rc != 0;
+        lm = (1u << lenbits) - 1;
+        dm = (1u << distbits) - 1;
+    }
+    __syncwarp();
+    uint32_t o = 0, flushed = 0;
+    bool bad = false;
+    const uint64_t reach = b.out_off; // bytes of output in front of this block
+    while (true) {
+        if (lane == 0 && !S.d.done) {
+            uint32_t cnt = 0;
+            while (cnt < 32) {
+                uint32_t v, d;
+                const int t = dec_symbol(S.d, br, lm, dm, v, d);
+                if (t == 0) S.d.q[cnt++] = v;
+                else if (t == 1) S.d.q[cnt++] = (v << 16) | d;
+                else { S.d.done = 1; if (t < 0) S.d.err = 1; break; }
+            }
+            S.d.qn = cnt;
+        } else if (lane == 0) S.d.qn = 0;
+        __syncwarp();
+        const uint32_t cnt = S.d.qn;
+        const uint32_t e = lane < cnt ? S.d.q[lane] : 0;
+        const uint32_t len = e >> 16;
+        const bool islit = lane < cnt && len == 0;
+        uint32_t l = lane < cnt ? (len ? len : 1u) : 0u;
+        uint32_t incl = l;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        const uint32_t start = o + incl - l;
+        const uint32_t litmask = __ballot_sync(0xffffffffu, islit);
+        uint32_t i = 0;
+        while (i < cnt) {
+            if ((litmask >> i) & 1u) {
+                const uint32_t t = ~(litmask >> i);
+                const uint32_t run = t ? (uint32_t)__ffs((int)t) - 1u : 32u - i;
+                if (lane >= i && lane < i + run) S.win[start & (kWSize - 1)] = (uint16_t)e;
+                i += run;
+            } else {
+                const uint32_t L = __shfl_sync(0xffffffffu, len, i);
+                const uint32_t D = __shfl_sync(0xffffffffu, e & 0xffffu, i);
+                const uint32_t P = __shfl_sync(0xffffffffu, start, i);
+                if ((uint64_t)D > reach + P) bad = true; // "invalid distance too far back"
+                for (uint32_t j = lane; j < L; j += 32) {
+                    const uint32_t jj = D < L ? j % D : j;
+                    const int32_t sidx = (int32_t)(P + jj) - (int32_t)D;
+                    const uint16_t v = sidx < 0 ? (uint16_t)(0x8000u | (uint32_t)((int32_t)kWSize + sidx)) : S.win[(uint32_t)sidx & (kWSize - 1)];
+                    S.win[(P + j) & (kWSize - 1)] = v;
+                }
+                i++;
+            }
+            __syncwarp();
+        }
+        o += __shfl_sync(0xffffffffu, incl, 31);
+        const bool fin = S.d.done != 0;
+        if (o - flushed >= kWSize / 2 || fin) {
+            for (uint32_t idx = flushed + lane; idx < o; idx += 32) dst[idx] = S.win[idx & (kWSize - 1)];
+            flushed = o;
+        }
+        if (o > kMaxBlockOut) { bad = true; break; }
+        __syncwarp();
+        if (fin) break;
+    }
+    if (__any_sync(0xffffffffu, bad) || S.d.err || o != b.out_len) { if (lane == 0) atomicOr(&par->decode_err, 1u); }
+}
+
+// 5. markers -> bytes.  A marker names a byte in the 32 KiB in front of its block, which may itself be a marker of an
+// earlier block: every output byte chases its own chain, no order between blocks is needed.
+__global__ void __launch_bounds__(256) k_inf_resolve(InfPar *par, const InfBlock *__restrict__ blocks, const uint16_t *__restrict__ tmp, uint8_t *out)
+{
+    const uint64_t total = par->total_out;
+    const uint32_t nb = par->nblocks;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4; i0 < total; i0 += (uint64_t)gridDim.x * 1024) {
+        uint32_t packed = 0;
+        for (uint32_t c = 0; c < 4 && i0 + c < total; c++) {
+            uint64_t i = i0 + c;
+            uint16_t v = tmp[i];
+            uint32_t hi = nb; // blocks[hi] starts beyond i
+            while (v & 0x8000u) {
+                // block containing i: last block with out_off <= i
+                uint32_t lo = 0, h2 = hi;
+                while (h2 - lo > 1) { const uint32_t mid = (lo + h2) >> 1; if (blocks[mid].out_off <= i) lo = mid; else h2 = mid; }
+                const uint64_t off = blocks[lo].out_off;
+                const uint64_t idx = v & 0x7fffu;
+                if (off + idx < kWSize) { atomicOr(&par->decode_err, 2u); v = 0; break; }
+                i = off - kWSize + idx;
+                hi = lo + 1;
+                v = tmp[i];
+            }
+            packed |= (uint32_t)(v & 0xffu) << (8 * c);
+        }
+        if (i0 + 4 <= total && ((reinterpret_cast<uintptr_t>(out) + i0) & 3) == 0) *reinterpret_cast<uint32_t *>(out + i0) = packed;
+        else for (uint32_t c = 0; c < 4 && i0 + c < total; c++) out[i0 + c] = (uint8_t)(packed >> (8 * c));
+    }
+}
+
 static const char *inf_msg(uint32_t e)
 {
     switch (e) {
@@ -467,11 +878,66 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         d_dst = static_cast<uint8_t *>(p);
     }
     InfState *dis = static_cast<InfState *>(d_inf_state), *his = static_cast<InfState *>(h_inf_state);
-    k_inflate<<<1, 32, sizeof(InfShared), st>>>(d_src, n, d_dst, dst_cap, window_bits, dis);
-    launches = 1;
-    CKI(cudaMemcpyAsync(his, dis, sizeof(InfState), cudaMemcpyDeviceToHost, st));
-    CKI(cudaStreamSynchronize(st));
-    CKI(cudaGetLastError());
+    launches = 0;
+    bool done = false;
+    if (n >= 65536 && !getenv("ZB_INFLATE_SERIAL")) {
+        // block-parallel path; anything it cannot follow falls through to the serial decoder below
+        InfPar *dpar, hpar;
+        if ((rc = reserve(23 /*S_MARKN*/, sizeof(InfPar) + 64, &p)) != ZB_OK) return rc;
+        dpar = static_cast<InfPar *>(p);
+        InfCand *dcand;
+        if ((rc = reserve(24 /*S_LLIST*/, sizeof(InfCand) * kMaxCand, &p)) != ZB_OK) return rc;
+        dcand = static_cast<InfCand *>(p);
+        InfBlock *dblk;
+        if ((rc = reserve(25 /*S_LCNT*/, sizeof(InfBlock) * kMaxBlocks, &p)) != ZB_OK) return rc;
+        dblk = static_cast<InfBlock *>(p);
+        uint32_t *dhtab;
+        if ((rc = reserve(21 /*S_PHEAD*/, sizeof(uint32_t) * kHashSize, &p)) != ZB_OK) return rc;
+        dhtab = static_cast<uint32_t *>(p);
+        CKI(cudaMemsetAsync(dpar, 0, sizeof(InfPar), st));
+        CKI(cudaMemsetAsync(dhtab, 0, sizeof(uint32_t) * kHashSize, st));
+        k_inf_header<<<1, 32, 0, st>>>(d_src, n, window_bits, dpar);
+        k_inf_scout<<<(unsigned)((n + kScoutBytes - 1) / kScoutBytes), 256, 0, st>>>(d_src, n, dpar, dcand, dhtab);
+        launches += 2;
+        CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
+        CKI(cudaStreamSynchronize(st));
+        if (hpar.status == PS_OK && hpar.ncand > 0 && hpar.ncand <= kMaxCand) {
+            k_inf_scan<<<hpar.ncand, 32, 0, st>>>(d_src, n, dpar, dcand);
+            k_inf_chain<<<1, 32, 0, st>>>(d_src, n, dpar, dcand, dhtab, dblk);
+            launches += 2;
+            CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
+            CKI(cudaStreamSynchronize(st));
+            if (hpar.status == PS_OK && hpar.nblocks > 0 && hpar.total_out <= dst_cap) {
+                uint16_t *dtmp;
+                if ((rc = reserve(4 /*S_M*/, (hpar.total_out + 64) * 2, &p)) != ZB_OK) return rc;
+                dtmp = static_cast<uint16_t *>(p);
+                CKI(cudaFuncSetAttribute(k_inf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
+                k_inf_decode<<<hpar.nblocks, 32, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp);
+                const uint64_t quads = (hpar.total_out + 1023) / 1024;
+                k_inf_resolve<<<(unsigned)(quads < 148 * 16 ? (quads ? quads : 1) : 148 * 16), 256, 0, st>>>(dpar, dblk, dtmp, d_dst);
+                launches += 2;
+                CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
+                CKI(cudaStreamSynchronize(st));
+                CKI(cudaGetLastError());
+                if (hpar.decode_err == 0) {
+                    his->out_bytes = hpar.total_out;
+                    his->in_bytes = hpar.end_bit / 8;
+                    his->err = IE_OK;
+                    his->trailer_check = hpar.trailer_check;
+                    his->trailer_len = hpar.trailer_len;
+                    his->kind = hpar.kind;
+                    done = true;
+                }
+            }
+        }
+    }
+    if (!done) {
+        k_inflate<<<1, 32, sizeof(InfShared), st>>>(d_src, n, d_dst, dst_cap, window_bits, dis);
+        launches += 1;
+        CKI(cudaMemcpyAsync(his, dis, sizeof(InfState), cudaMemcpyDeviceToHost, st));
+        CKI(cudaStreamSynchronize(st));
+        CKI(cudaGetLastError());
+    }
     res->out_bytes = his->out_bytes;
     res->in_bytes = his->in_bytes;
     int status = ZB_OK;
