@@ -10,6 +10,9 @@ p = e.alloc(len(d)); e.to_device(p, d)
 cap = Z.lib().zb_deflate_bound(len(d)) + 64
 q = e.alloc(cap)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+level = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+e.set_profile(True)
 for _ in range(reps):
-    _, r = e.deflate(p, n=len(d), level=6, src_on_device=True, dst=q, dst_cap=cap, dst_on_device=True)
-print("out", r.out_bytes, "gpu_ms", r.gpu_ms, "iters", r.iterations, "launches", r.gpu_launches)
+    _, r = e.deflate(p, n=len(d), level=level, src_on_device=True, dst=q, dst_cap=cap, dst_on_device=True)
+print("level", level, "out", r.out_bytes, "gpu_ms", r.gpu_ms, "iters", r.iterations, "launches", r.gpu_launches)
+print("phases", e.get_profile())

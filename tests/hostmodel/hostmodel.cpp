@@ -364,3 +364,46 @@ extern "C" int hm_inflate_scout(const uint8_t *src, uint32_t n, uint64_t *cands,
     *ncand = k;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Level 7..9 (deflate_slow) model: static chains + slow_step() from fresh loop-top to fresh loop-top.
+// ------------------------------------------------------------------------------------------
+#include "../../zlib_rs_b200/csrc/zb_slow.h"
+
+struct SlowAcc {
+    const uint8_t *data; uint32_t N; const uint16_t *L; uint32_t need;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 65536) return 0; y -= 32768; }
+        return data[y];
+    }
+    uint32_t link(uint32_t y) const { return y + need <= N ? L[y] : 0; }
+};
+
+static void build_links_roll(const uint8_t *d, uint32_t N, std::vector<uint16_t> &L)
+{
+    L.assign(N + 8, 0);
+    std::vector<int64_t> head(32768, -1);
+    for (uint32_t x = 0; x + 3 <= N; x++) {
+        uint32_t h = hash_roll3(d[x], d[x + 1], d[x + 2]);
+        if (head[h] >= 0 && x - head[h] <= kLinkCapSlow) L[x] = (uint16_t)(x - head[h]);
+        head[h] = x;
+    }
+}
+
+extern "C" int hm_parse_slow(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    SlowParams sp = slow_params(level);
+    std::vector<uint16_t> L;
+    if (sp.slow) build_links_roll(data, N, L); else build_links(data, N, L);
+    SlowAcc a{data, N, L.data(), sp.slow ? 3u : 4u};
+    uint32_t n = 0, p = 0;
+    while (p < N) {
+        SlowStep s = slow_step(a, p, N, sp);
+        for (uint32_t i = 0; i < s.nlit; i++) { if (n < cap) out[n] = SymOut{p + i, 0, data[p + i]}; n++; }
+        if (s.len) { if (n < cap) out[n] = SymOut{p + s.nlit, (uint16_t)s.dist, (uint16_t)(s.len - 3)}; n++; }
+        if (s.next <= p) return -3;
+        p = s.next;
+    }
+    *nsyms = n;
+    return 0;
+}

@@ -118,6 +118,50 @@ def test_silesia_tar_level6_golden(eng):
     assert zlib.decompress(out) == d
 
 
+L9_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["level"] in (7, 8, 9) and v["window_bits"] in (15, 31)
+           and v["mem_level"] == 8 and v["strategy"] == 0 and v["flush"] == 4]
+
+
+@pytest.mark.parametrize("v", L9_KATS, ids=[v["name"] for v in L9_KATS])
+def test_reference_golden_vectors_level9(v, eng):
+    out, res = eng.deflate(bytes.fromhex(v["input_hex"]), level=v["level"], window_bits=v["window_bits"])
+    assert out == bytes.fromhex(v["expected_hex"])
+
+
+@pytest.mark.parametrize("level", [7, 8, 9])
+def test_slow_levels_bit_exact(level, eng):
+    """deflate_slow (lazy matching; level 9 with the rolling hash and longest_match_slow): bytes equal the oracle's."""
+    rng = np.random.default_rng(level)
+    cases = [synthetic_mix(n, seed=n + level) for n in (0, 1, 2, 3, 4, 5, 261, 262, 263, 5000, 16383, 65535, 65536, 65537, 131072, 400000)]
+    cases += [bytes(300000), b"a" * 100000, b"abc" * 50000, rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+              rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(), (b"x" * 65274 + synthetic_mix(1000, 1)) * 3,
+              bytes(65274) + b"\x01" + bytes(70000)]
+    cases += [silesia_member(k)[:300000] for k in (1, 5, 9)]
+    for d in cases:
+        out, res = eng.deflate(d, level=level)
+        assert res.exact_parity == 1
+        assert out == O.compress(d, level)[1], (level, len(d))
+    d = silesia_member(2)[:200000]
+    out, res = eng.deflate(d, level=level, strategy=1)
+    assert out == O.compress(d, level, 15, 8, 1)[1]
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_silesia_members_level9_bit_exact(k):
+    d = silesia_member(k)
+    out = Z.compress2(d, 9)
+    assert out == O.compress(d, 9)[1]
+    assert zlib.decompress(out) == d
+
+
+def test_silesia_tar_level9_equals_reference_file(eng):
+    """The reference repo's silesia-small.tar.gz is the level-9 zlib stream of silesia-small.tar: reproduce it byte for byte."""
+    d = silesia_tar()
+    out, res = eng.deflate(d, level=9)
+    assert res.exact_parity == 1
+    assert out == silesia_gz()
+
+
 def test_other_levels_and_strategies_valid_streams(eng):
     d = silesia_member(3)[:200000]
     for level in (0, 1, 2, 7, 8, 9):

@@ -80,3 +80,12 @@ def test_window_base_schedule():
     o = _syms("hm_oracle_trace", data, 6)
     p = _syms("hm_parse_parallel", data, 6, True)
     assert (o == p).all()
+
+
+@pytest.mark.parametrize("level", [7, 8, 9])
+def test_slow_levels_parse_matches_reference_parser(level):
+    """slow_step() (zb_slow.h) from fresh loop-top to fresh loop-top reproduces every symbol deflate_slow tallies."""
+    for name, data in CASES + [("dickens", silesia_member(3)[:400000]), ("mix1M", synthetic_mix(1 << 20, 21))]:
+        o = _syms("hm_oracle_trace", data, level)
+        s = _syms("hm_parse_slow", data, level)
+        assert len(o) == len(s) and (o == s).all(), name

@@ -42,10 +42,16 @@ __global__ void k_encode(JobBufs);
 __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
+__global__ void k_links_roll(JobBufs);
+__global__ void k_slow(JobBufs);
+__global__ void k_emit_slow(JobBufs);
+__global__ void k_tail_slow(JobBufs);
 
 constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
+constexpr uint32_t kRollSmemBytes = 32768 * 4 + (kLinkTile + 32768 + 64);
+constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
 
 int Engine::init(int dev)
@@ -65,6 +71,8 @@ int Engine::init(int dev)
     CK(upload_tables());
     CK(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmemBytes));
     CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
+    CK(cudaFuncSetAttribute(k_links_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmemBytes));
+    CK(cudaFuncSetAttribute(k_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlowSmemBytes));
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
@@ -231,9 +239,13 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     bool exact = wb == 15;
     if (level != 0 && !jb.huffman_only) {
         if (level < 3) { eng_level = 3; exact = false; }
-        if (level > 6) { eng_level = 6; exact = false; }
         if (strategy == 3) exact = false; // Z_RLE parser not implemented: medium parser instead
+        if (level > 6) {
+            if (strategy == 3) eng_level = 6;
+            else { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
+        }
     }
+    if (jb.slow_mode) jb.tail_start = N; // the lazy path needs no serial tail: every step knows the end of the input
     jb.lp = level_params(eng_level);
     if (level != 0 && !jb.huffman_only) jb.level = (uint32_t)level; // header flag bits follow the requested level
     if (lf_zero && !jb.strategy_fixed && !jb.huffman_only) jb.level = 1;   // Z_RLE: FLEVEL 0 like the reference
@@ -274,9 +286,32 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
             pbegin();
-            k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
+            if (jb.slow_mode && jb.sp.slow) k_links_roll<<<nmt, 1024, kRollSmemBytes, st>>>(jb);
+            else k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
             launches++;
             pend(0, 1);
+            if (jb.slow_mode) {
+                if (N > 0) {
+                    iters = 1;
+                    pbegin();
+                    k_slow<<<(N + kSlowSub - 1) / kSlowSub, 1024, kSlowSmemBytes, st>>>(jb);
+                    pend(1, 1);
+                    if (profile) phase_ms[11] = phase_ms[1];
+                    pbegin();
+                    k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt);
+                    k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    pend(3, 3);
+                    pbegin();
+                    k_emit_slow<<<(N + 255) / 256, 256, 0, st>>>(jb);
+                    pend(4, 1);
+                    launches += 5;
+                }
+                pbegin();
+                k_tail_slow<<<1, 32, 0, st>>>(jb);
+                launches++;
+                pend(5, 1);
+            } else {
             if (jb.tail_start > 0) {
                 uint32_t n_dirty = nmt;
                 for (;;) {
@@ -325,6 +360,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             k_tail<<<1, 32, 0, st>>>(jb);
             launches++;
             pend(5, 1);
+            }
         }
         CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "zb_core.h"
 #include "zb_huff.h"
+#include "zb_slow.h"
 
 namespace zb {
 
@@ -19,6 +20,8 @@ constexpr uint32_t kPathHead = 64;      // leading positions of a path tile mirr
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
 constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
 constexpr uint32_t kSymsPerThread = 16;
+constexpr uint32_t kSlowSub = 8192;     // positions per k_slow CTA
+constexpr uint32_t kSlowAhead = 1024;   // bytes/links staged behind the last position of a k_slow CTA (<= kPad)
 
 struct JobInfo {              // device-resident result / control block of one deflate job
     uint32_t n_mid_syms;      // symbols produced by the canonical path (before the tail)
@@ -73,6 +76,8 @@ struct JobBufs {
     uint8_t *mark_needed;     // path tiles whose marks must be recomputed
     uint32_t *long_list;      // per path sub-tile: positions of path nodes whose macro step emits a long match
     uint32_t *long_cnt;
+    SlowParams sp;            // level 7..9 parameters
+    uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9)
     uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
 };
 
