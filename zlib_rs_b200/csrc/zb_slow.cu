@@ -82,6 +82,27 @@ __device__ __forceinline__ uint32_t pack_step(const SlowStep &s)
     return (s.nlit << 24) | (s.len ? ((s.len - 3u) << 16) | 0x8000u | (s.dist - 1u) : 0u);
 }
 
+// explicit shared-space loads on 32-bit shared addresses
+__device__ __forceinline__ uint32_t qld_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t qld_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t qld_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t qld_u32u(uint32_t a) // unaligned
+{
+    const uint32_t al = a & ~3u;
+    return __funnelshift_r(qld_u32(al), qld_u32(al + 4), (a & 3u) * 8u);
+}
+
+constexpr uint32_t kSlowSafe = 1024; // nodes this close to the end of the input take the generic slow_step()
+constexpr uint32_t kSlowBatch = 8;
+constexpr uint32_t kSlowBurst = 4;
+enum { SS_IDLE = 0, SS_START = 1, SS_WALK = 2, SS_PEND = 3, SS_DONE = 4 };
+
+// The lanes of a warp run the macro steps of different fresh loop-tops.  A lane is IDLE (needs a node), at the
+// START of a search (preconditions, the level-9 re-rooting of longest_match.rs:87-124), WALKing its chain one
+// candidate per step, or PENDing a full compare (+ the re-rooting of :281-333).  The rarer, longer code paths run
+// only when enough lanes want them, so the walk step -- two filter loads and a link load -- stays dense.
+// Semantics are those of lm_slow()/slow_step() in zb_slow.h: a candidate replaces the best match iff its common
+// prefix is strictly longer; the reference's 8-byte pre-checks only filter for that.
 __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -95,7 +116,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
     const uint32_t span = te + kSlowAhead - ws; // <= kWSize + sub + kSlowAhead
     uint8_t *sdata = smem;
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kWSize + kSlowSub + kSlowAhead);
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_next = ts;
     {
         // the input and L allocations are padded with kPad (>= kSlowAhead) zero entries
@@ -109,16 +130,190 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
     }
     __syncthreads();
-    const SlowSAcc a{sdata, sL, ws, N, jb.sp.slow ? 3u : 4u};
+    const SlowSAcc acc{sdata, sL, ws, N, jb.sp.slow ? 3u : 4u};
     const SlowParams sp = jb.sp;
-    for (;;) {
-        const uint32_t p = atomicAdd(&s_next, 1u);
-        if (p >= te) break;
-        const SlowStep s = slow_step(a, p, N, sp);
-        const uint32_t delta = s.next - p, ns = s.nlit + (s.len ? 1u : 0u);
+    // shared addresses of absolute position 0 (only positions >= ws are ever dereferenced)
+    const uint32_t dadj = (uint32_t)__cvta_generic_to_shared(sdata) - ws;
+    const uint32_t ladj = (uint32_t)__cvta_generic_to_shared(sL) - 2 * ws;
+
+    // node state
+    uint32_t p = 0, q = 0, l = 0, ms = 0, B = 0;
+    // search state
+    uint32_t best = 2, chain = 0, cur = 0, mo = 0, limit_base = 0, limit = 0, mstart = 0, xb = 0, xw0 = 0, cand = 0;
+    uint32_t state = SS_IDLE;
+
+    auto write_node = [&](uint32_t next, uint32_t nlit, uint32_t len, uint32_t dist) {
+        const uint32_t delta = next - p, ns = nlit + (len ? 1u : 0u);
         if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
-        jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (s.next >= N ? kNxtTail : 0u);
-        jb.M[p] = pack_step(s);
+        jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (next >= N ? kNxtTail : 0u);
+        jb.M[p] = pack_step(SlowStep{next, nlit, len, dist});
+        state = SS_IDLE;
+    };
+    // the search at loop-top q ended with (rlen, rstart): slow.rs:84-136
+    auto finish_search = [&](uint32_t rlen, uint32_t rstart, bool searched) {
+        if (searched && sp.filtered && rlen <= 5) rlen = 2;
+        if (l == 0) {
+            if (rlen < 3) { write_node(p + 1, 1, 0, 0); return; }
+            l = rlen; ms = rstart; q = p + 1;
+        } else {
+            if (rlen <= l) { write_node(q - 1 + l, q - 1 - p, l, q - 1 - ms); return; }
+            l = rlen; ms = rstart; q++;
+        }
+        const uint32_t Bq = base_at(q, N);
+        if (Bq != B) {
+            B = Bq;
+            if (ms < Bq) { write_node(q, q - p, 0, 0); return; } // pending match dropped by the slide (deflate.rs:1792-1797)
+        }
+        state = SS_START;
+    };
+    // head[] of the bucket of position x as the parser at q sees it
+    auto head_at = [&](uint32_t x) -> uint32_t {
+        while (x > q) {
+            const uint32_t d = qld_u16(ladj + 2 * x);
+            if (!d) return B;
+            x -= d;
+        }
+        return x > B ? x : B;
+    };
+    auto next_in_chain = [&]() {
+        if (--chain == 0) { finish_search(best, mstart, true); return; }
+        const uint32_t d = qld_u16(ladj + 2 * cur);
+        if (d == 0 || d >= cur - limit) { finish_search(best, mstart, true); return; }
+        cur -= d;
+    };
+
+    for (;;) {
+        const uint32_t m_idle = __ballot_sync(0xffffffffu, state == SS_IDLE);
+        const uint32_t m_start = __ballot_sync(0xffffffffu, state == SS_START);
+        const uint32_t m_walk = __ballot_sync(0xffffffffu, state == SS_WALK);
+        const uint32_t m_pend = __ballot_sync(0xffffffffu, state == SS_PEND);
+        if ((m_idle | m_start | m_walk | m_pend) == 0) break;
+        if (m_idle && (__popc(m_idle) >= (int)kSlowBatch || (m_start | m_walk | m_pend) == 0)) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(m_idle) - 1;
+            if (lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (state == SS_IDLE) {
+                const uint32_t x = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (x >= te) state = SS_DONE;
+                else if (x + kSlowSafe > N) {
+                    p = x;
+                    const SlowStep s = slow_step(acc, x, N, sp);
+                    write_node(s.next, s.nlit, s.len, s.dist);
+                } else {
+                    p = q = x; l = 0; ms = 0;
+                    B = base_at(x, N);
+                    state = SS_START;
+                }
+            }
+            continue;
+        }
+        if (m_start && (__popc(m_start) >= (int)kSlowBatch || m_walk == 0)) {
+            if (state == SS_START) {
+                // slow.rs:56-82 preconditions (lookahead >= 262 here)
+                bool search = l < sp.lazy;
+                uint32_t hh = 0;
+                if (search) {
+                    const uint32_t d = qld_u16(ladj + 2 * q);
+                    hh = q - d;
+                    search = d != 0 && d <= kMaxDist && hh > B;
+                }
+                if (!search) finish_search(2, ms, false);
+                else {
+                    best = l ? l : 2;
+                    mstart = ms;
+                    chain = best >= sp.good ? sp.chain >> 2 : sp.chain;
+                    limit_base = (q - B > kMaxDist) ? q - kMaxDist : B;
+                    limit = limit_base;
+                    mo = 0;
+                    cur = hh;
+                    bool ended = false;
+                    if (sp.slow && best >= 3) {
+                        for (uint32_t i = 0; i + 3 <= best; i++) {
+                            const uint32_t pos = head_at(q + i + 1);
+                            if (pos < cur) { mo = i + 1; cur = pos; }
+                        }
+                        limit = limit_base + mo;
+                        ended = cur <= limit;
+                    }
+                    if (ended) finish_search(best, mstart, true);
+                    else {
+                        xb = qld_u8(dadj + q + best);
+                        xw0 = qld_u32u(dadj + q);
+                        state = SS_WALK;
+                    }
+                }
+            }
+            continue;
+        }
+        if (m_pend && (__popc(m_pend) >= (int)kSlowBatch || m_walk == 0)) {
+            if (state == SS_PEND) {
+                uint32_t clen = 0, len;
+                const uint32_t pa = dadj + q, pb = dadj + cand;
+                for (;;) {
+                    const uint32_t d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
+                    const uint32_t d1 = qld_u32u(pa + clen + 4) ^ qld_u32u(pb + clen + 4);
+                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                    break;
+                }
+                if (len > kMaxMatch) len = kMaxMatch;
+                state = SS_WALK;
+                if (len > best) {
+                    mstart = cand;
+                    best = len;
+                    if (best >= sp.nice) finish_search(best, mstart, true);
+                    else {
+                        xb = qld_u8(dadj + q + best);
+                        if (sp.slow && len > 3 && mstart + len < q) {
+                            // longest_match.rs:281-333
+                            cur = cand;
+                            mo = 0;
+                            uint32_t next_pos = cur;
+                            bool ended = false;
+                            for (uint32_t i = 0; i + 3 <= len; i++) {
+                                const uint32_t y = cur + i;
+                                const uint32_t d = qld_u16(ladj + 2 * y);
+                                const uint32_t pos = (d && y - d > B) ? y - d : B;
+                                if (pos < next_pos) {
+                                    if (pos <= limit_base + i) { ended = true; break; }
+                                    next_pos = pos;
+                                    mo = i;
+                                }
+                            }
+                            if (!ended) {
+                                cur = next_pos;
+                                const uint32_t pos = head_at(q + len - 4);
+                                if (pos < cur) {
+                                    mo = len - 4;
+                                    if (pos <= limit_base + mo) ended = true;
+                                    else cur = pos;
+                                }
+                            }
+                            if (ended) finish_search(best, mstart, true);
+                            else limit = limit_base + mo;
+                        } else next_in_chain();
+                    }
+                } else next_in_chain();
+            }
+            continue;
+        }
+#pragma unroll
+        for (uint32_t burst = 0; burst < kSlowBurst; burst++) {
+            if (state == SS_WALK) {
+                if (cur >= q) finish_search(best, mstart, true);
+                else {
+                    const uint32_t c = cur - mo;
+                    bool pass = qld_u8(dadj + c + best) == xb;
+                    if (pass) {
+                        const uint32_t dw = qld_u32u(dadj + c) ^ xw0;
+                        pass = (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+                    }
+                    if (pass) { cand = c; state = SS_PEND; }
+                    else next_in_chain();
+                }
+            }
+        }
     }
 }
 
