@@ -29,7 +29,7 @@ __global__ void k_links(JobBufs);
 __global__ void k_match(JobBufs);
 __global__ void k_nxt(JobBufs);
 __global__ void k_path_tiles(JobBufs);
-__global__ void k_path_chain(JobBufs, uint32_t);
+__global__ void k_path_chain(JobBufs, uint32_t, uint32_t);
 __global__ void k_path_mark(JobBufs);
 __global__ void k_emit(JobBufs);
 __global__ void k_holes(JobBufs, uint32_t);
@@ -48,7 +48,7 @@ __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
 
 constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
-constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4;
+constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4 * 3 + 8192 + 16;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kRollSmemBytes = 32768 * 4 + (kLinkTile + 32768 + 64);
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
@@ -143,7 +143,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -179,8 +179,9 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
     const uint32_t max_blocks = N / kBlockSyms + 2;
     const size_t out_cap = (deflate_bound(n) + 15) & ~(size_t)15;
-    if ((rc = stage(nmt + 64)) != ZB_OK) return rc;
+    if ((rc = stage((size_t)nmt + 64 + ((size_t)N / 2048 + 2 + npt + 8) * 4 + 64)) != ZB_OK) return rc;
     uint8_t *h_dirty = static_cast<uint8_t *>(h_stage);
+    uint32_t *h_lists = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(h_stage) + (((size_t)nmt + 64 + 15) & ~(size_t)15));
 #define RES(slot, bytes, field, type)                                   \
     if ((rc = reserve(slot, bytes, &p)) != ZB_OK) return rc;            \
     jb.field = static_cast<type>(p);
@@ -210,6 +211,14 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
     RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
+    RES(S_BMAP, 8192, bucket_map, uint32_t *)
+    RES(S_CSTATE, (size_t)(npt + 1) * 16, chain_state, uint4 *)
+    uint32_t *d_lists;
+    const uint32_t max_list = N / 2048 + 2;
+    if ((rc = reserve(S_LISTS, ((size_t)max_list + npt + 8) * 4, &p)) != ZB_OK) return rc;
+    d_lists = static_cast<uint32_t *>(p);
+    RES(S_HDIFF, (size_t)nwords * 4, hdiff, uint32_t *)
+    RES(S_HCOARSE, (size_t)(N >> 10) + 16, hcoarse, uint8_t *)
     RES(S_BLOCKS, (size_t)max_blocks * sizeof(BlockDesc), blocks, BlockDesc *)
     RES(S_SCRATCH, (size_t)max_blocks * sizeof(TreeScratch), scratch, TreeScratch *)
     uint32_t *d_freq;
@@ -299,7 +308,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     if (profile) phase_ms[11] = phase_ms[1];
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
-                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt);
+                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt, 0);
                     k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
                     pend(3, 3);
                     pbegin();
@@ -319,23 +328,57 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
                     // them over more SMs
                     jb.match_sub = n_dirty > 48 ? kMatchSub : 2048;
-                    const uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
-                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4;
+                    uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
+                    uint32_t n_ptiles = npt, first_ptile = 0;
+                    jb.match_list = nullptr;
+                    jb.nxt_list = nullptr;
+                    if (iters > 1) {
+                        // launch only the pieces a changed hole can reach (the kernels re-check the flags themselves)
+                        uint32_t nm = 0, np_ = 0;
+                        const uint32_t per = kMatchTile / jb.match_sub;
+                        for (uint32_t t = 0; t < nmt; t++) {
+                            if (!h_dirty[t]) continue;
+                            for (uint32_t k = 0; k < per; k++) if ((uint64_t)(t * per + k) * jb.match_sub < N) h_lists[nm++] = t * per + k;
+                        }
+                        uint32_t *pl = h_lists + max_list;
+                        first_ptile = npt;
+                        for (uint32_t pt = 0; pt < npt; pt++) {
+                            const uint32_t m0 = (pt * kPathTile) / kMatchTile;
+                            uint32_t m1 = ((pt + 1) * kPathTile + 22016 - 1) / kMatchTile;
+                            if (m1 >= nmt) m1 = nmt - 1;
+                            bool d = false;
+                            for (uint32_t m = m0; m <= m1; m++) d = d || h_dirty[m];
+                            if (d) { pl[np_++] = pt; if (first_ptile == npt) first_ptile = pt; }
+                        }
+                        if (first_ptile == npt) first_ptile = 0;
+                        if (!nm) h_lists[0] = 0;
+                        if (!np_) pl[0] = 0;
+                        CK(cudaMemcpyAsync(d_lists, h_lists, (size_t)(nm ? nm : 1) * 4, cudaMemcpyHostToDevice, st));
+                        CK(cudaMemcpyAsync(d_lists + max_list, pl, (size_t)(np_ ? np_ : 1) * 4, cudaMemcpyHostToDevice, st));
+                        jb.match_list = d_lists;
+                        jb.nxt_list = d_lists + max_list;
+                        nsub = nm ? nm : 1;
+                        n_ptiles = np_ ? np_ : 1;
+                    }
+                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4 * 3 + 8192 + 16;
+                    jb.use_bucket_map = iters > 1;
                     pbegin();
                     k_match<<<nsub, 1024, msmem, st>>>(jb);
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();
-                    k_nxt<<<npt * (kPathTile / 1024), 1024, 0, st>>>(jb);
+                    k_nxt<<<n_ptiles * (kPathTile / 1024), 1024, 0, st>>>(jb);
                     pend(2, 1);
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
-                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt);
+                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt, first_ptile);
                     k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
                     pend(3, 3);
                     pbegin();
                     k_holes<<<(nlists * kLongPerSub + 255) / 256, 256, 0, st>>>(jb, nlists);
                     CK(cudaMemsetAsync(jb.tile_dirty, 0, nmt, st));
+                    CK(cudaMemsetAsync(jb.bucket_map, 0, 8192, st));
+                    CK(cudaMemsetAsync(jb.hcoarse, 0, (size_t)(N >> 10) + 16, st));
                     CK(cudaMemsetAsync(&d_info->holes_changed, 0, 4, st));
                     k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
                     pend(4, 2);
@@ -344,6 +387,16 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     CK(cudaMemcpyAsync(h_dirty, jb.tile_dirty, nmt, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                     if (h_info->error) { snprintf(g_err, sizeof g_err, "engine error flags 0x%x (parse)", h_info->error); return ZB_E_INTERNAL; }
+                    if (getenv("ZB_DEBUG")) {
+                        static unsigned long long last[8];
+                        if (iters == 1) memset(last, 0, sizeof last);
+                        fprintf(stderr, "iter %u dirty %u: ctas %llu stage %.1f skip %.1f walk %.1f kcyc/cta, rounds/cta %.1f, holes_changed %u\n", iters, n_dirty,
+                                h_info->dbg[0] - last[0], (h_info->dbg[1] - last[1]) / 1e3 / (double)(h_info->dbg[0] - last[0] + 1e-9),
+                                (h_info->dbg[2] - last[2]) / 1e3 / (double)(h_info->dbg[0] - last[0] + 1e-9),
+                                (h_info->dbg[3] - last[3]) / 1e3 / (double)(h_info->dbg[0] - last[0] + 1e-9),
+                                (h_info->dbg[4] - last[4]) / (double)(h_info->dbg[0] - last[0] + 1e-9), h_info->holes_changed);
+                        memcpy(last, h_info->dbg, sizeof last);
+                    }
                     if (!h_info->holes_changed) break;
                     n_dirty = 0;
                     for (uint32_t i = 0; i < nmt; i++) n_dirty += h_dirty[i] != 0;

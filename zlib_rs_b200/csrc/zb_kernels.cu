@@ -160,18 +160,19 @@ __device__ __forceinline__ uint32_t sld_u32u(uint32_t a) // unaligned
     return __funnelshift_r(sld_u32(al), sld_u32(al + 4), (a & 3u) * 8u);
 }
 
-template <bool kHoles>
-__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sh,
-                                                uint32_t ws, uint32_t te, uint32_t *s_next)
+__device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sbm,
+                                                const uint32_t *sdf, const uint32_t *spf, uint32_t ws, uint32_t te, uint32_t *s_next)
 {
+    const bool filt = jb.use_bucket_map != 0;
     const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(sdata);
     const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(sL);
-    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(sh);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t *const Mout = jb.M + ws;
+    uint16_t *const RDout = jb.SK + ws;
     // per-lane state, all positions relative to ws
     uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, cand = 0;
+    uint32_t dn = 0;    // staged link of cr, loaded one step ahead (the staged links never lead to a hole, see k_match)
     uint32_t xb = 0;    // byte of x at index `best`: a longer match must reproduce it (one-byte filter first)
     uint32_t xw0 = 0;   // first four bytes of x: second-stage filter before a full compare is scheduled
     uint32_t fbase = 0; // dbase + best
@@ -193,15 +194,32 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 if (x >= te) state = LS_DONE;
                 else if (x + kMSafe > N) { jb.M[x] = 0; }
                 else {
-                    xr = x - ws; cr = xr; best = 2; chain = budget; res = 0;
-                    fbase = dbase + 2;
-                    xb = sld_u8(fbase + xr);
+                    xr = x - ws;
                     xw0 = sld_u32u(dbase + xr);
-                    // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
-                    // absolute position 0 is never a candidate
-                    lowr = xr > kMaxDist ? xr - kMaxDist : 0;
-                    if (ws == 0 && lowr == 0) lowr = 1;
-                    state = LS_WALK;
+                    bool skip = false;
+                    if (filt) { // only buckets in which a hole changed can have a different M ...
+                        const uint32_t h = hash_u32(xw0);
+                        skip = !((sbm[h >> 5] >> (h & 31)) & 1u);
+                        if (!skip) {
+                            // ... and only if a changed hole lies within the reach of the previous walk
+                            const uint32_t rd = RDout[xr];
+                            const uint32_t lo = rd == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - rd;
+                            const uint32_t c_hi = spf[xr >> 5] + __popc(sdf[xr >> 5] & ((1u << (xr & 31)) - 1u));
+                            const uint32_t c_lo = spf[lo >> 5] + __popc(sdf[lo >> 5] & ((1u << (lo & 31)) - 1u));
+                            skip = c_hi == c_lo;
+                        }
+                    }
+                    if (!skip) {
+                        cr = xr; best = 2; chain = budget; res = 0;
+                        dn = sld_u16(lbase + 2 * cr);
+                        fbase = dbase + 2;
+                        xb = sld_u8(fbase + xr);
+                        // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
+                        // absolute position 0 is never a candidate
+                        lowr = xr > kMaxDist ? xr - kMaxDist : 0;
+                        if (ws == 0 && lowr == 0) lowr = 1;
+                        state = LS_WALK;
+                    }
                 }
             }
             continue;
@@ -222,36 +240,27 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 if (len > best) {
                     best = len;
                     res = (len << 16) | (xr - cand);
-                    if (best >= nice) { Mout[xr] = res; state = LS_IDLE; }
+                    if (best >= nice) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cand); state = LS_IDLE; }
                     else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
                 }
-                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; state = LS_IDLE; }
+                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cand); state = LS_IDLE; }
             }
             continue;
         }
 #pragma unroll
         for (uint32_t burst = 0; burst < kWalkBurst; burst++) {
             if (state == LS_WALK) {
-                uint32_t d = sld_u16(lbase + 2 * cr);
-                bool stop = d == 0 || cr < lowr + d; // chain ends or leaves the window
-                cr -= d;
-                if (kHoles && !stop) {
-                    if ((sld_u32(hbase + 4 * (cr >> 5)) >> (cr & 31)) & 1u) { // a hole: its staged link is the skip pointer
-                        d = sld_u16(lbase + 2 * cr);
-                        stop = d == 0 || cr < lowr + d;
-                        cr -= d;
-                    }
-                }
-                if (stop) { Mout[xr] = res; state = LS_IDLE; }
+                // dn = link of cr (loaded during the previous step); the three loads below are independent of each other
+                if (dn == 0 || cr < lowr + dn) { Mout[xr] = res; RDout[xr] = 0xffffu; state = LS_IDLE; } // chain ends or leaves the window
                 else {
+                    cr -= dn;
+                    dn = sld_u16(lbase + 2 * cr);
+                    const uint32_t fb = sld_u8(fbase + cr);
+                    const uint32_t dw = sld_u32u(dbase + cr) ^ xw0;
                     if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
-                    bool pass = sld_u8(fbase + cr) == xb;
-                    if (pass) { // the first 3 (best == 2) / 4 bytes must match as well
-                        const uint32_t dw = sld_u32u(dbase + cr) ^ xw0;
-                        pass = (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
-                    }
-                    if (pass) { cand = cr; state = LS_PEND; }
-                    else if (--chain == 0) { Mout[xr] = res; state = LS_IDLE; }
+                    // the byte at `best` and the first 3 (best == 2) / 4 bytes must match for a longer match
+                    if (fb == xb && (best == 2 ? (dw & 0x00ffffffu) : dw) == 0) { cand = cr; state = LS_PEND; }
+                    else if (--chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cr); state = LS_IDLE; }
                 }
             }
         }
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_next, s_any_hole;
     const uint32_t sub = jb.match_sub;
-    const uint32_t ts = blockIdx.x * sub;
+    const uint32_t ts = (jb.match_list ? jb.match_list[blockIdx.x] : blockIdx.x) * sub;
     if (ts >= jb.N) return;
     {
         const uint32_t t0 = ts / kMatchTile, t1 = (min(ts + sub, jb.N) - 1) / kMatchTile;
@@ -273,12 +282,53 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     uint8_t *sdata = smem;
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem + data_bytes);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem + data_bytes + (kWSize + sub) * 2);
+    uint32_t *sbm = sh + (kWSize + sub) / 32; // 2048 words
+    uint32_t *sdf = sbm + 2048;               // changed-hole bits of the staged window
+    uint32_t *spf = sdf + (kWSize + sub) / 32 + 1; // exclusive prefix popcounts of sdf
+    __shared__ uint32_t s_wsum[32];
     const uint32_t N = jb.N;
     const uint32_t te = min(ts + sub, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x;
+    if (jb.use_bucket_map) {
+        // nothing to do unless a position of this piece hashes into a bucket with a changed hole
+        int hit = 0;
+        for (uint32_t x = ts + tid; x < te; x += 1024) {
+            const uint8_t *q = jb.in + x; // zero padded behind N
+            const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+            if ((jb.bucket_map[h >> 5] >> (h & 31)) & 1u) {
+                const uint32_t rd = jb.SK[x];
+                const uint32_t lo = rd == 0xffffu ? (x > kMaxDist ? x - kMaxDist : 0u) : x - rd;
+                for (uint32_t b = lo >> 10; b <= (x >> 10); b++) hit |= jb.hcoarse[b];
+            }
+        }
+        if (!__syncthreads_or(hit)) return;
+        for (uint32_t i = tid; i < 2048; i += 1024) sbm[i] = jb.bucket_map[i];
+        // changed-hole bitmap of [ws, te) and its prefix counts (two words per thread at most)
+        const uint32_t nwd = (te - ws + 31) / 32;
+        const uint32_t w0 = 2 * tid, w1 = 2 * tid + 1;
+        const uint32_t v0 = w0 < nwd ? jb.hdiff[(ws >> 5) + w0] : 0u, v1 = w1 < nwd ? jb.hdiff[(ws >> 5) + w1] : 0u;
+        if (w0 <= nwd) sdf[w0] = v0;
+        if (w1 <= nwd) sdf[w1] = v1;
+        const uint32_t mine = __popc(v0) + __popc(v1);
+        uint32_t incl = mine;
+        const uint32_t lane_ = tid & 31, warp_ = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_ >= (uint32_t)d) incl += t;
+        }
+        if (lane_ == 31) s_wsum[warp_] = incl;
+        __syncthreads();
+        uint32_t wbase_cnt = 0;
+        for (uint32_t k = 0; k < warp_; k++) wbase_cnt += s_wsum[k];
+        const uint32_t excl = wbase_cnt + incl - mine;
+        if (w0 <= nwd) spf[w0] = excl;
+        if (w1 <= nwd) spf[w1] = excl + __popc(v0);
+    }
     if (tid == 0) { s_next = ts; s_any_hole = 0; }
     const uint32_t nw = (te - ws + 31) / 32;
+    const long long t_0 = clock64();
     __syncthreads();
     {
         // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
@@ -296,6 +346,8 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
     }
     __syncthreads();
+    const long long t_1 = clock64();
+    uint32_t dbg_rounds = 0;
     const bool has_holes = s_any_hole != 0;
     if (has_holes) {
         // Skip pointers: at a hole (a position the parser never inserted) the staged link is replaced by the
@@ -326,25 +378,51 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             if (ch) s_changed = 1;
             __syncthreads();
             const bool any = s_changed != 0;
+            dbg_rounds++;
             if (!any) break;
         }
         __syncthreads();
+        // links INTO a hole are extended by the hole's skip distance, so that a walk never lands on a hole
+        for (uint32_t i = tid; i < te - ws; i += 1024) {
+            if ((sh[i >> 5] >> (i & 31)) & 1u) continue; // a hole's own entry is its skip distance already
+            const uint32_t d = sL[i];
+            if (d == 0 || d > i) continue;
+            const uint32_t t = i - d;
+            if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue;
+            const uint32_t d2 = sL[t];
+            sL[i] = (uint16_t)((d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2);
+        }
+        __syncthreads();
     }
+    const long long t_2 = clock64();
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
-        if (has_holes) match_tile_fast<true>(jb, sdata, sL, sh, ws, te, &s_next);
-        else match_tile_fast<false>(jb, sdata, sL, sh, ws, te, &s_next);
+        match_tile_fast(jb, sdata, sL, sbm, sdf, spf, ws, te, &s_next);
+        __syncthreads();
+        if (tid == 0) {
+            const long long t_3 = clock64();
+            atomicAdd(&jb.info->dbg[0], 1ull);
+            atomicAdd(&jb.info->dbg[1], (unsigned long long)(t_1 - t_0));
+            atomicAdd(&jb.info->dbg[2], (unsigned long long)(t_2 - t_1));
+            atomicAdd(&jb.info->dbg[3], (unsigned long long)(t_3 - t_2));
+            atomicAdd(&jb.info->dbg[4], (unsigned long long)dbg_rounds);
+        }
         return;
     }
     // levels 3/4 (early exit): generic walk; a hole's staged link already bridges to an inserted position
     SAcc a{sdata, sL, sh, ws};
     for (uint32_t x = ts + tid; x < te; x += 1024) {
         uint32_t v = 0;
+        if (jb.use_bucket_map && x + 4 <= N) {
+            const uint32_t h = hash_u32(a.byte(x) | (a.byte(x + 1) << 8) | (a.byte(x + 2) << 16) | (a.byte(x + 3) << 24));
+            if (!((sbm[h >> 5] >> (h & 31)) & 1u)) continue;
+        }
         if (x + kMSafe <= N) {
             Match m = lm_walk(a, x, 0xffffffffu, lp);
             if (m.len) v = (m.len << 16) | (x - m.start);
         }
         jb.M[x] = v;
+        jb.SK[x] = 0xffffu; // reach unknown: any changed hole of the bucket in the window invalidates
     }
 }
 
@@ -368,8 +446,10 @@ __device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
 __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
 {
     // 16 CTAs per path tile, one position per thread; CTAs of clean tiles exit at once
-    if (!path_tile_dirty(jb, blockIdx.x / (kPathTile / 1024))) return;
-    const uint32_t p = blockIdx.x * 1024 + threadIdx.x;
+    constexpr uint32_t per = kPathTile / 1024;
+    const uint32_t tile = jb.nxt_list ? jb.nxt_list[blockIdx.x / per] : blockIdx.x / per;
+    if (!path_tile_dirty(jb, tile)) return;
+    const uint32_t p = tile * kPathTile + (blockIdx.x % per) * 1024 + threadIdx.x;
     if (p >= jb.tail_start) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     const uint32_t long_len = 16 * jb.lp.lazy;
@@ -463,15 +543,20 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
 // the CTA stages that table in shared memory chunk by chunk, so the serial walk only sees shared-memory
 // latency.
 constexpr uint32_t kChainChunk = 320;
-__global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles)
+__global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles, uint32_t first_tile)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint2 *hd = reinterpret_cast<uint2 *>(smem);
     __shared__ uint32_t s_e, s_base, s_done, s_tail;
     __shared__ uint32_t c_entry[kChainChunk], c_base[kChainChunk];
-    if (threadIdx.x == 0) { s_e = 0; s_base = 0; s_done = jb.tail_start == 0; s_tail = 0; }
+    // tiles before first_tile kept their nxt: the walk resumes from the state saved at that tile's boundary
+    if (threadIdx.x == 0) {
+        if (first_tile == 0) { s_e = 0; s_base = 0; s_done = jb.tail_start == 0; s_tail = 0; }
+        else { const uint4 v = jb.chain_state[first_tile]; s_e = v.x; s_base = v.y; s_done = v.z; s_tail = v.w; }
+    }
+    for (uint32_t t = threadIdx.x; t < first_tile; t += blockDim.x) jb.mark_needed[t] = 0;
     __syncthreads();
-    for (uint32_t c0 = 0; c0 < ntiles; c0 += kChainChunk) {
+    for (uint32_t c0 = first_tile; c0 < ntiles; c0 += kChainChunk) {
         const uint32_t nt = min(kChainChunk, ntiles - c0);
         for (uint32_t i = threadIdx.x; i < nt * kPathHead; i += blockDim.x) hd[i] = jb.phead[(size_t)c0 * kPathHead + i];
         __syncthreads();
@@ -481,6 +566,7 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
             uint32_t tail_entry = s_tail;
             for (uint32_t k = 0; k < nt; k++) {
                 const uint32_t tbeg = (c0 + k) * kPathTile, tend = tbeg + kPathTile;
+                jb.chain_state[c0 + k] = make_uint4(e, base, done ? 1u : 0u, tail_entry);
                 c_base[k] = base;
                 if (done || e >= tend || e >= jb.tail_start) { c_entry[k] = 0xffffffffu; continue; }
                 c_entry[k] = e;
@@ -617,12 +703,24 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t a = jb.holes[w], b = jb.holes_new[w];
+    jb.hdiff[w] = a ^ b;
     if (a != b) {
+        jb.hcoarse[w >> 5] = 1;
         const uint32_t t = (w * 32) / kMatchTile;
         atomicAdd(&jb.info->holes_changed, 1u); // number of changed bitmap words
         jb.tile_dirty[t] = 1;
         if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
         jb.holes[w] = b;
+        uint32_t diff = a ^ b;
+        while (diff) {
+            const uint32_t y = w * 32 + (__ffs(diff) - 1);
+            diff &= diff - 1;
+            if (y + 4 <= jb.N) {
+                const uint8_t *q = jb.in + y;
+                const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+                atomicOr(&jb.bucket_map[h >> 5], 1u << (h & 31));
+            }
+        }
     }
     jb.holes_new[w] = 0;
 }

@@ -37,6 +37,7 @@ struct JobInfo {              // device-resident result / control block of one d
     uint32_t adler;
     uint32_t pad;
     uint64_t marker_byte;     // not_last: byte offset of the empty stored block's LEN field
+    unsigned long long dbg[8]; // ZB_DEBUG counters (k_match: CTAs, stage, skip, walk cycles, rounds, positions)
 };
 
 // One deflate job's device buffers (see DESIGN.md "HBM layout").
@@ -45,7 +46,9 @@ struct JobBufs {
     uint32_t N;
     uint32_t tail_start;
     uint16_t *L;          // N + kPad
-    uint16_t *SK;         // N + kPad: skip pointers of hole positions
+    uint16_t *SK;         // N + kPad: reach of the chain walk of M[x]: x - (lowest position examined), 0xffff = to the end of the window
+    uint32_t *hdiff;      // bitmap: holes that changed in the last iteration
+    uint8_t *hcoarse;     // one flag per 1024 positions: some hole changed there
     uint32_t *holes;      // bitmap, (N >> 5) + 2 words
     uint32_t *holes_new;
     uint32_t *M;          // N + kPad
@@ -78,6 +81,11 @@ struct JobBufs {
     uint32_t *long_cnt;
     SlowParams sp;            // level 7..9 parameters
     uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9)
+    const uint32_t *match_list; // k_match: sub-tile index per CTA (nullptr: all sub-tiles)
+    const uint32_t *nxt_list;   // k_nxt: path tile per 16 CTAs (nullptr: all tiles)
+    uint4 *chain_state;       // k_path_chain: (entry, symbol base, done, tail entry) at every tile boundary
+    uint32_t *bucket_map;     // 65536 bits: hash buckets in which a hole changed in the last iteration
+    uint32_t use_bucket_map;  // k_match recomputes only positions of those buckets (later iterations)
     uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
 };
 

@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
             }
             continue;
         }
-        if (m_start && (__popc(m_start) >= (int)kSlowBatch || m_walk == 0)) {
+        // START/PEND lanes do not wait for the walkers when few lanes are busy at all
+        const uint32_t thr = min(kSlowBatch, max(1u, (uint32_t)__popc(m_start | m_walk | m_pend) / 4u));
+        if (m_start && (__popc(m_start) >= (int)thr || m_walk == 0)) {
             if (state == SS_START) {
                 // slow.rs:56-82 preconditions (lookahead >= 262 here)
                 bool search = l < sp.lazy;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
             }
             continue;
         }
-        if (m_pend && (__popc(m_pend) >= (int)kSlowBatch || m_walk == 0)) {
+        if (m_pend && (__popc(m_pend) >= (int)thr || m_walk == 0)) {
             if (state == SS_PEND) {
                 uint32_t clen = 0, len;
                 const uint32_t pa = dadj + q, pb = dadj + cand;
