@@ -27,6 +27,7 @@ static void set_err(const char *what, cudaError_t e)
 // kernels (zb_kernels.cu)
 __global__ void k_links(JobBufs);
 __global__ void k_match(JobBufs);
+__global__ void k_skip(JobBufs);
 __global__ void k_nxt(JobBufs);
 __global__ void k_path_tiles(JobBufs);
 __global__ void k_path_chain(JobBufs, uint32_t, uint32_t);
@@ -48,8 +49,9 @@ __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
 
 constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
-constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32) * 4 * 3 + 8192 + 16;
+constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
+constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kRollSmemBytes = 32768 * 4 + (kLinkTile + 32768 + 64);
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
@@ -71,6 +73,7 @@ int Engine::init(int dev)
     CK(upload_tables());
     CK(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmemBytes));
     CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
+    CK(cudaFuncSetAttribute(k_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkipSmemBytes));
     CK(cudaFuncSetAttribute(k_links_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmemBytes));
     CK(cudaFuncSetAttribute(k_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlowSmemBytes));
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
@@ -143,7 +146,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -179,7 +182,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
     const uint32_t max_blocks = N / kBlockSyms + 2;
     const size_t out_cap = (deflate_bound(n) + 15) & ~(size_t)15;
-    if ((rc = stage((size_t)nmt + 64 + ((size_t)N / 2048 + 2 + npt + 8) * 4 + 64)) != ZB_OK) return rc;
+    if ((rc = stage((size_t)nmt + 64 + ((size_t)N / 512 + 2 + npt + nmt + 8) * 4 + 64)) != ZB_OK) return rc;
     uint8_t *h_dirty = static_cast<uint8_t *>(h_stage);
     uint32_t *h_lists = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(h_stage) + (((size_t)nmt + 64 + 15) & ~(size_t)15));
 #define RES(slot, bytes, field, type)                                   \
@@ -212,12 +215,14 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
     RES(S_BMAP, 8192, bucket_map, uint32_t *)
+    RES(S_LR, npad * 2, Lr, uint16_t *)
     RES(S_CSTATE, (size_t)(npt + 1) * 16, chain_state, uint4 *)
     uint32_t *d_lists;
-    const uint32_t max_list = N / 2048 + 2;
-    if ((rc = reserve(S_LISTS, ((size_t)max_list + npt + 8) * 4, &p)) != ZB_OK) return rc;
+    const uint32_t max_list = N / 512 + 2;
+    if ((rc = reserve(S_LISTS, ((size_t)max_list + npt + nmt + 8) * 4, &p)) != ZB_OK) return rc;
     d_lists = static_cast<uint32_t *>(p);
-    RES(S_HDIFF, (size_t)nwords * 4, hdiff, uint32_t *)
+    RES(S_HDIFF, (size_t)nwords * 8, hdiff, uint32_t *)
+    jb.hdiff_words = nwords;
     RES(S_HCOARSE, (size_t)(N >> 10) + 16, hcoarse, uint8_t *)
     RES(S_BLOCKS, (size_t)max_blocks * sizeof(BlockDesc), blocks, BlockDesc *)
     RES(S_SCRATCH, (size_t)max_blocks * sizeof(TreeScratch), scratch, TreeScratch *)
@@ -298,6 +303,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             if (jb.slow_mode && jb.sp.slow) k_links_roll<<<nmt, 1024, kRollSmemBytes, st>>>(jb);
             else k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
             launches++;
+            if (!jb.slow_mode) CK(cudaMemcpyAsync(jb.Lr, jb.L, npad * 2, cudaMemcpyDeviceToDevice, st));
             pend(0, 1);
             if (jb.slow_mode) {
                 if (N > 0) {
@@ -327,7 +333,10 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     iters++;
                     // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
                     // them over more SMs
-                    jb.match_sub = n_dirty > 48 ? kMatchSub : 2048;
+                    // few dirty tiles: small pieces on many SMs, few warps each (the walk of a sparse piece is issue-bound per warp)
+                    // one wave of CTAs if possible: the per-piece latency, not the throughput, bounds a sparse pass
+                    jb.match_sub = n_dirty > 9 ? kMatchSub : n_dirty > 2 ? 2048 : 512;
+                    const uint32_t mthreads = n_dirty > 2 ? 1024 : 256;
                     uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     uint32_t n_ptiles = npt, first_ptile = 0;
                     jb.match_list = nullptr;
@@ -336,8 +345,10 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                         // launch only the pieces a changed hole can reach (the kernels re-check the flags themselves)
                         uint32_t nm = 0, np_ = 0;
                         const uint32_t per = kMatchTile / jb.match_sub;
+                        uint32_t *sl = h_lists + max_list + npt, nsk = 0;
                         for (uint32_t t = 0; t < nmt; t++) {
                             if (!h_dirty[t]) continue;
+                            sl[nsk++] = t;
                             for (uint32_t k = 0; k < per; k++) if ((uint64_t)(t * per + k) * jb.match_sub < N) h_lists[nm++] = t * per + k;
                         }
                         uint32_t *pl = h_lists + max_list;
@@ -355,15 +366,23 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                         if (!np_) pl[0] = 0;
                         CK(cudaMemcpyAsync(d_lists, h_lists, (size_t)(nm ? nm : 1) * 4, cudaMemcpyHostToDevice, st));
                         CK(cudaMemcpyAsync(d_lists + max_list, pl, (size_t)(np_ ? np_ : 1) * 4, cudaMemcpyHostToDevice, st));
+                        if (nsk) {
+                            CK(cudaMemcpyAsync(d_lists + max_list + npt, sl, (size_t)nsk * 4, cudaMemcpyHostToDevice, st));
+                            jb.skip_list = d_lists + max_list + npt;
+                            pbegin();
+                            k_skip<<<nsk, 1024, kSkipSmemBytes, st>>>(jb);
+                            pend(1, 1);
+                            launches++;
+                        }
                         jb.match_list = d_lists;
                         jb.nxt_list = d_lists + max_list;
                         nsub = nm ? nm : 1;
                         n_ptiles = np_ ? np_ : 1;
                     }
-                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32) * 4 * 3 + 8192 + 16;
+                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32 + 1) * 4 * 4 + 8192;
                     jb.use_bucket_map = iters > 1;
                     pbegin();
-                    k_match<<<nsub, 1024, msmem, st>>>(jb);
+                    k_match<<<nsub, mthreads, msmem, st>>>(jb);
                     pend(1, 1);
                     if (profile && iters == 1) phase_ms[11] = phase_ms[1]; // the full first pass
                     pbegin();

@@ -64,6 +64,15 @@ struct SAcc { // shared-memory window of k_match
     }
 };
 
+struct SAccR { // shared-memory window of k_match; links are already bridged over holes
+    const uint8_t *sdata;
+    const uint16_t *sL;
+    uint32_t ws;
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const { return sdata[y - ws]; }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { return sL[y - ws]; }
+    __device__ __forceinline__ bool inserted(uint32_t) const { return true; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // k_links: L[x] = distance to the previous position with the same hash (hash_calc.rs:40-59): the
 // reference's head/prev chains as if every position were inserted (holes are bridged by k_skip's skip
@@ -132,6 +141,59 @@ __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_skip: Lr[] = the chain links with the holes bridged, for one dirty 32 KiB tile.  At a hole (a position the
+// parser never inserted) the link becomes the distance to the nearest INSERTED position further down the chain
+// (pointer jumping over the tile and the 32 KiB window before it, in shared memory); a link INTO a hole is
+// extended by that hole's distance.  Unordered in-place updates are fine: every value ever stored is a valid
+// partial jump along the same chain.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSkipSpan = 2 * kWSize;
+__global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *sL = reinterpret_cast<uint16_t *>(smem);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kSkipSpan * 2);
+    const uint32_t tile = jb.skip_list ? jb.skip_list[blockIdx.x] : blockIdx.x;
+    const uint32_t ts = tile * kMatchTile;
+    if (ts >= jb.N) return;
+    const uint32_t te = min(ts + kMatchTile, jb.N);
+    const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
+    const uint32_t span = te - ws, tid = threadIdx.x;
+    {
+        const uint4 *ls = reinterpret_cast<const uint4 *>(jb.L + ws);
+        uint4 *ld = reinterpret_cast<uint4 *>(sL);
+        for (uint32_t i = tid; i < (span + 7) / 8; i += 1024) ld[i] = ls[i];
+        for (uint32_t i = tid; i < (span + 31) / 32; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
+    }
+    __syncthreads();
+    for (uint32_t round = 0; round < 24; round++) {
+        int ch = 0;
+        for (uint32_t i = tid; i < span; i += 1024) {
+            if (!((sh[i >> 5] >> (i & 31)) & 1u)) continue;
+            const uint32_t d = sL[i];
+            if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
+            const uint32_t t = i - d;
+            if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
+            const uint32_t d2 = sL[t];
+            sL[i] = (uint16_t)((d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2);
+            ch = 1;
+        }
+        if (!__syncthreads_or(ch)) break;
+    }
+    for (uint32_t i = ts - ws + tid; i < span; i += 1024) {
+        uint32_t d = sL[i];
+        if (!((sh[i >> 5] >> (i & 31)) & 1u) && d != 0 && d <= i) {
+            const uint32_t t = i - d;
+            if ((sh[t >> 5] >> (t & 31)) & 1u) {
+                const uint32_t d2 = sL[t];
+                d = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
+            }
+        }
+        jb.Lr[ws + i] = (uint16_t)d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_match: M[x] for every x of a 32 KiB tile.  The tile plus the 32 KiB before it (data, chain links,
 // hole bits) are staged in shared memory; 1024 threads walk their chains independently.
 // ------------------------------------------------------------------------------------------------
@@ -160,8 +222,19 @@ __device__ __forceinline__ uint32_t sld_u32u(uint32_t a) // unaligned
     return __funnelshift_r(sld_u32(al), sld_u32(al + 4), (a & 3u) * 8u);
 }
 
+struct DiffMaps { // changed-hole bitmaps of the staged window with exclusive prefix popcounts
+    const uint32_t *del, *pdel; // holes that became inserted positions
+    const uint32_t *add, *padd; // inserted positions that became holes
+    __device__ __forceinline__ static bool any(const uint32_t *b, const uint32_t *p, uint32_t lo, uint32_t hi)
+    {
+        const uint32_t c_hi = p[hi >> 5] + __popc(b[hi >> 5] & ((1u << (hi & 31)) - 1u));
+        const uint32_t c_lo = p[lo >> 5] + __popc(b[lo >> 5] & ((1u << (lo & 31)) - 1u));
+        return c_hi != c_lo;
+    }
+};
+
 __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sbm,
-                                                const uint32_t *sdf, const uint32_t *spf, uint32_t ws, uint32_t te, uint32_t *s_next)
+                                                const DiffMaps dm, uint32_t ws, uint32_t te, uint32_t *s_next)
 {
     const bool filt = jb.use_bucket_map != 0;
     const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(sdata);
@@ -201,12 +274,24 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                         const uint32_t h = hash_u32(xw0);
                         skip = !((sbm[h >> 5] >> (h & 31)) & 1u);
                         if (!skip) {
-                            // ... and only if a changed hole lies within the reach of the previous walk
+                            // ... and only if the change can alter the previous walk (its reach and how it ended are in RD):
+                            //  * a new candidate (hole -> inserted) anywhere in the reach;
+                            //  * a lost candidate (inserted -> hole) if it was the best one, or -- when the walk ended on its
+                            //    budget -- anywhere in the reach (one more candidate gets examined);
+                            //  * the nearest candidate now sits exactly at the window limit (only a first candidate may, medium.rs:76).
                             const uint32_t rd = RDout[xr];
-                            const uint32_t lo = rd == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - rd;
-                            const uint32_t c_hi = spf[xr >> 5] + __popc(sdf[xr >> 5] & ((1u << (xr & 31)) - 1u));
-                            const uint32_t c_lo = spf[lo >> 5] + __popc(sdf[lo >> 5] & ((1u << (lo & 31)) - 1u));
-                            skip = c_hi == c_lo;
+                            const bool on_budget = rd != 0xffffu && (rd & 0x8000u);
+                            const uint32_t lo = rd == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - (rd & 0x7fffu);
+                            bool redo = DiffMaps::any(dm.del, dm.pdel, lo, xr);
+                            if (!redo) {
+                                if (on_budget) redo = DiffMaps::any(dm.add, dm.padd, lo, xr);
+                                else {
+                                    const uint32_t m = Mout[xr];
+                                    if (m) { const uint32_t h = xr - (m & 0xffffu); redo = (dm.add[h >> 5] >> (h & 31)) & 1u; }
+                                }
+                            }
+                            if (!redo) redo = sld_u16(lbase + 2 * xr) == kMaxDist;
+                            skip = !redo;
                         }
                     }
                     if (!skip) {
@@ -243,7 +328,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     if (best >= nice) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cand); state = LS_IDLE; }
                     else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
                 }
-                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cand); state = LS_IDLE; }
+                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)((xr - cand) | 0x8000u); state = LS_IDLE; }
             }
             continue;
         }
@@ -260,7 +345,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
                     // the byte at `best` and the first 3 (best == 2) / 4 bytes must match for a longer match
                     if (fb == xb && (best == 2 ? (dw & 0x00ffffffu) : dw) == 0) { cand = cr; state = LS_PEND; }
-                    else if (--chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cr); state = LS_IDLE; }
+                    else if (--chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)((xr - cr) | 0x8000u); state = LS_IDLE; }
                 }
             }
         }
@@ -270,7 +355,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
 __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_next, s_any_hole;
+    __shared__ uint32_t s_next;
     const uint32_t sub = jb.match_sub;
     const uint32_t ts = (jb.match_list ? jb.match_list[blockIdx.x] : blockIdx.x) * sub;
     if (ts >= jb.N) return;
@@ -282,52 +367,59 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     uint8_t *sdata = smem;
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem + data_bytes);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem + data_bytes + (kWSize + sub) * 2);
-    uint32_t *sbm = sh + (kWSize + sub) / 32; // 2048 words
-    uint32_t *sdf = sbm + 2048;               // changed-hole bits of the staged window
-    uint32_t *spf = sdf + (kWSize + sub) / 32 + 1; // exclusive prefix popcounts of sdf
+    uint32_t *sbm = sh;                        // 2048 words: dirty hash buckets
+    const uint32_t wmax = (kWSize + sub) / 32 + 1;
+    uint32_t *sdel = sbm + 2048, *pdel = sdel + wmax, *sadd = pdel + wmax, *padd = sadd + wmax; // changed-hole bits + prefix counts
     __shared__ uint32_t s_wsum[32];
     const uint32_t N = jb.N;
     const uint32_t te = min(ts + sub, N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     if (jb.use_bucket_map) {
         // nothing to do unless a position of this piece hashes into a bucket with a changed hole
         int hit = 0;
-        for (uint32_t x = ts + tid; x < te; x += 1024) {
+        for (uint32_t x = ts + tid; x < te; x += nthr) {
             const uint8_t *q = jb.in + x; // zero padded behind N
             const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
             if ((jb.bucket_map[h >> 5] >> (h & 31)) & 1u) {
                 const uint32_t rd = jb.SK[x];
-                const uint32_t lo = rd == 0xffffu ? (x > kMaxDist ? x - kMaxDist : 0u) : x - rd;
+                const uint32_t lo = rd == 0xffffu ? (x > kMaxDist ? x - kMaxDist : 0u) : x - (rd & 0x7fffu);
                 for (uint32_t b = lo >> 10; b <= (x >> 10); b++) hit |= jb.hcoarse[b];
             }
         }
         if (!__syncthreads_or(hit)) return;
-        for (uint32_t i = tid; i < 2048; i += 1024) sbm[i] = jb.bucket_map[i];
-        // changed-hole bitmap of [ws, te) and its prefix counts (two words per thread at most)
+        for (uint32_t i = tid; i < 2048; i += nthr) sbm[i] = jb.bucket_map[i];
+        // changed-hole bitmaps of [ws, te) and their exclusive prefix counts: every thread owns a run of consecutive words
         const uint32_t nwd = (te - ws + 31) / 32;
-        const uint32_t w0 = 2 * tid, w1 = 2 * tid + 1;
-        const uint32_t v0 = w0 < nwd ? jb.hdiff[(ws >> 5) + w0] : 0u, v1 = w1 < nwd ? jb.hdiff[(ws >> 5) + w1] : 0u;
-        if (w0 <= nwd) sdf[w0] = v0;
-        if (w1 <= nwd) sdf[w1] = v1;
-        const uint32_t mine = __popc(v0) + __popc(v1);
-        uint32_t incl = mine;
+        const uint32_t per = (nwd + 1 + nthr - 1) / nthr;
+        const uint32_t wb = tid * per;
         const uint32_t lane_ = tid & 31, warp_ = tid >> 5;
+        for (int which = 0; which < 2; which++) {
+            const uint32_t *src = which ? jb.hdiff : jb.hdiff + jb.hdiff_words; // add : del
+            uint32_t *bits = which ? sadd : sdel, *pre = which ? padd : pdel;
+            uint32_t mine = 0;
+            for (uint32_t k = 0; k < per; k++) {
+                const uint32_t w = wb + k;
+                if (w <= nwd) { const uint32_t v = w < nwd ? src[(ws >> 5) + w] : 0u; bits[w] = v; mine += __popc(v); }
+            }
+            uint32_t incl = mine;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane_ >= (uint32_t)d) incl += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane_ >= (uint32_t)d) incl += t;
+            }
+            __syncthreads(); // s_wsum of the previous round has been read
+            if (lane_ == 31) s_wsum[warp_] = incl;
+            __syncthreads();
+            uint32_t run = incl - mine;
+            for (uint32_t k = 0; k < warp_; k++) run += s_wsum[k];
+            for (uint32_t k = 0; k < per; k++) {
+                const uint32_t w = wb + k;
+                if (w <= nwd) { pre[w] = run; run += __popc(bits[w]); }
+            }
         }
-        if (lane_ == 31) s_wsum[warp_] = incl;
-        __syncthreads();
-        uint32_t wbase_cnt = 0;
-        for (uint32_t k = 0; k < warp_; k++) wbase_cnt += s_wsum[k];
-        const uint32_t excl = wbase_cnt + incl - mine;
-        if (w0 <= nwd) spf[w0] = excl;
-        if (w1 <= nwd) spf[w1] = excl + __popc(v0);
     }
-    if (tid == 0) { s_next = ts; s_any_hole = 0; }
-    const uint32_t nw = (te - ws + 31) / 32;
+    if (tid == 0) s_next = ts;
     const long long t_0 = clock64();
     __syncthreads();
     {
@@ -335,69 +427,20 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         const uint32_t n16 = (te + 512 - ws + 15) / 16;
         const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
         uint4 *dst = reinterpret_cast<uint4 *>(sdata);
-        for (uint32_t i = tid; i < n16 && i < data_bytes / 16; i += 1024) dst[i] = src[i];
-        // hole bits, then the chain links with the skip pointers substituted at hole positions
-        uint32_t any = 0;
-        for (uint32_t i = tid; i < nw; i += 1024) { const uint32_t w = jb.holes[(ws >> 5) + i]; sh[i] = w; any |= w; }
-        if (any) s_any_hole = 1;
+        for (uint32_t i = tid; i < n16 && i < data_bytes / 16; i += nthr) dst[i] = src[i];
+        // chain links with the holes already bridged (k_skip): a walk never lands on a hole
         const uint32_t nl = (te - ws + 7) / 8; // 8 links per uint4
-        const uint4 *ls = reinterpret_cast<const uint4 *>(jb.L + ws);
+        const uint4 *ls = reinterpret_cast<const uint4 *>(jb.Lr + ws);
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
-        for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
+        for (uint32_t i = tid; i < nl; i += nthr) ld[i] = ls[i];
     }
     __syncthreads();
     const long long t_1 = clock64();
     uint32_t dbg_rounds = 0;
-    const bool has_holes = s_any_hole != 0;
-    if (has_holes) {
-        // Skip pointers: at a hole (a position the parser never inserted) the staged link is replaced by the
-        // distance to the nearest INSERTED position further down the chain, by pointer jumping over the staged
-        // window.  A chain walk then bridges any run of holes in one extra step.
-        __shared__ uint32_t s_changed;
-        for (uint32_t round = 0; round < 24; round++) {
-            __syncthreads(); // everybody has read s_changed of the previous round
-            if (tid == 0) s_changed = 0;
-            __syncthreads();
-            bool ch = false;
-            for (uint32_t w = tid; w < nw; w += 1024) { // one bitmap word (32 positions) at a time: work ~ number of holes
-                uint32_t bits = sh[w];
-                while (bits) {
-                    const uint32_t i = w * 32 + (__ffs(bits) - 1);
-                    bits &= bits - 1;
-                    if (i >= te - ws) break;
-                    const uint32_t d = sL[i];
-                    if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
-                    const uint32_t t = i - d;
-                    if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
-                    const uint32_t d2 = sL[t];
-                    const uint32_t nd = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
-                    sL[i] = (uint16_t)nd;
-                    ch = true;
-                }
-            }
-            if (ch) s_changed = 1;
-            __syncthreads();
-            const bool any = s_changed != 0;
-            dbg_rounds++;
-            if (!any) break;
-        }
-        __syncthreads();
-        // links INTO a hole are extended by the hole's skip distance, so that a walk never lands on a hole
-        for (uint32_t i = tid; i < te - ws; i += 1024) {
-            if ((sh[i >> 5] >> (i & 31)) & 1u) continue; // a hole's own entry is its skip distance already
-            const uint32_t d = sL[i];
-            if (d == 0 || d > i) continue;
-            const uint32_t t = i - d;
-            if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue;
-            const uint32_t d2 = sL[t];
-            sL[i] = (uint16_t)((d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2);
-        }
-        __syncthreads();
-    }
     const long long t_2 = clock64();
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
-        match_tile_fast(jb, sdata, sL, sbm, sdf, spf, ws, te, &s_next);
+        match_tile_fast(jb, sdata, sL, sbm, DiffMaps{sdel, pdel, sadd, padd}, ws, te, &s_next);
         __syncthreads();
         if (tid == 0) {
             const long long t_3 = clock64();
@@ -409,9 +452,9 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         }
         return;
     }
-    // levels 3/4 (early exit): generic walk; a hole's staged link already bridges to an inserted position
-    SAcc a{sdata, sL, sh, ws};
-    for (uint32_t x = ts + tid; x < te; x += 1024) {
+    // levels 3/4 (early exit): generic walk over the bridged links
+    SAccR a{sdata, sL, ws};
+    for (uint32_t x = ts + tid; x < te; x += nthr) {
         uint32_t v = 0;
         if (jb.use_bucket_map && x + 4 <= N) {
             const uint32_t h = hash_u32(a.byte(x) | (a.byte(x + 1) << 8) | (a.byte(x + 2) << 16) | (a.byte(x + 3) << 24));
@@ -703,7 +746,8 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t a = jb.holes[w], b = jb.holes_new[w];
-    jb.hdiff[w] = a ^ b;
+    jb.hdiff[w] = b & ~a;                  // became holes
+    jb.hdiff[jb.hdiff_words + w] = a & ~b; // became inserted positions
     if (a != b) {
         jb.hcoarse[w >> 5] = 1;
         const uint32_t t = (w * 32) / kMatchTile;

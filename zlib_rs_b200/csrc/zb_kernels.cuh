@@ -47,7 +47,8 @@ struct JobBufs {
     uint32_t tail_start;
     uint16_t *L;          // N + kPad
     uint16_t *SK;         // N + kPad: reach of the chain walk of M[x]: x - (lowest position examined), 0xffff = to the end of the window
-    uint32_t *hdiff;      // bitmap: holes that changed in the last iteration
+    uint32_t *hdiff;      // two bitmaps of hdiff_words words: positions that became holes / stopped being holes in the last iteration
+    uint32_t hdiff_words;
     uint8_t *hcoarse;     // one flag per 1024 positions: some hole changed there
     uint32_t *holes;      // bitmap, (N >> 5) + 2 words
     uint32_t *holes_new;
@@ -81,6 +82,8 @@ struct JobBufs {
     uint32_t *long_cnt;
     SlowParams sp;            // level 7..9 parameters
     uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9)
+    uint16_t *Lr;             // N + kPad: links with the holes bridged (k_skip); equals L while there are no holes
+    const uint32_t *skip_list;  // k_skip: match tile per CTA
     const uint32_t *match_list; // k_match: sub-tile index per CTA (nullptr: all sub-tiles)
     const uint32_t *nxt_list;   // k_nxt: path tile per 16 CTAs (nullptr: all tiles)
     uint4 *chain_state;       // k_path_chain: (entry, symbol base, done, tail entry) at every tile boundary
