@@ -261,6 +261,34 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": N, "launch_ms": full_ms,
                 "phases_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "iterations": int(res.iterations)}
 
+    # the other BASELINE.json configs, measured once each on rank 0 at N=1 (device resident, CUDA events; reported, not the headline)
+    other = None
+    if rank == 0 and world == 1:
+        try:
+            from corpus import silesia_gz
+            gz = silesia_gz()
+            other = {}
+            best = min(eng.inflate(gz, N)[2].gpu_ms for _ in range(3))
+            rc, got, r3 = eng.inflate(gz, N)
+            other["inflate_silesia_small_tar_gz"] = {"ms": best, "out_GBps": N / best / 1e6, "bit_exact": bool(rc == 0 and got == tar),
+                                                     "gpu_launches": int(r3.gpu_launches), "note": "config 3; host buffers, copies inside the timed region"}
+            o9, r9 = eng.deflate(ins[0].data_ptr(), n=N, level=9, src_on_device=True, dst=out_t.data_ptr(), dst_cap=cap, dst_on_device=True)
+            o9, r9 = eng.deflate(ins[1].data_ptr(), n=N, level=9, src_on_device=True, dst=out_t.data_ptr(), dst_cap=cap, dst_on_device=True)
+            out9 = bytes(out_t[: int(r9.out_bytes)].cpu().numpy().tobytes())
+            other["deflate_level9_silesia_small_tar"] = {"ms": r9.gpu_ms, "GiBps": N / (r9.gpu_ms * 1e-3) / GIB, "out_bytes": int(r9.out_bytes),
+                                                         "equals_reference_file": out9 == gz, "exact_parity": int(r9.exact_parity)}
+            nck = 8 << 30
+            pck = eng.alloc(nck)
+            try:
+                eng.fill_random(pck, nck, 42)
+                a_ms = min(eng.adler32(pck, nck, on_device=True)[1] for _ in range(3))
+                c_ms = min(eng.crc32(pck, nck, on_device=True)[1] for _ in range(3))
+                other["checksums_8GiB"] = {"adler32_GBps": nck / a_ms / 1e6, "crc32_GBps": nck / c_ms / 1e6, "note": "config 5; splitmix64 buffer generated on the device"}
+            finally:
+                eng.free(pck)
+        except Exception as ex:  # the headline must not depend on these
+            other = {"error": repr(ex)}
+
     if rank == 0:
         value = world * N / (ms_per_step * 1e-3) / GIB
         e2e = world * N / (e2e_ms * 1e-3) / GIB
@@ -281,6 +309,8 @@ def main():
         }
         if cpu_b:
             line["cpu_baseline"] = cpu_b
+        if other:
+            line["other_configs"] = other
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -510,8 +510,9 @@ __device__ __forceinline__ uint32_t cand_lookup(const uint32_t *htab, const InfC
 struct DecShared {
     ICode lencode[kEnoughLens], distcode[kEnoughDists];
     uint16_t lens[320], work[288];
-    uint32_t q[32];
-    uint32_t qn, done, err;
+    uint32_t q[4][32];   // symbol batches handed from the decoding warp to the replaying warp
+    uint32_t qn[4], qfin[4];
+    uint32_t err;
     uint64_t end_bit;
 };
 
@@ -688,59 +689,80 @@ __global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const I
     par->trailer_len = isz;
 }
 
-// 4. all chained blocks in parallel -> 16-bit symbols.  One warp per block: lane 0 decodes 32 symbols at a time into a
-// queue, then the warp replays them on a 32 Ki-symbol ring in shared memory (a run of literals in one step, a match in
-// ceil(len/32) steps) and streams the ring out to global memory in coalesced pieces.
+// 4. all chained blocks in parallel -> 16-bit symbols.  Two warps per block: lane 0 of warp 0 decodes 32 symbols at a
+// time into one of four queue buffers; warp 1 replays them on a 32 Ki-symbol ring in shared memory (a run of literals
+// in one step, a match in ceil(len/32) steps) and streams the ring out to global memory in coalesced pieces.  The
+// warps hand buffers over with named barriers (full / empty per buffer), so decoding and replaying overlap.
 struct DecodeShared {
     DecShared d;
     uint16_t win[kWSize];
 };
 
-__global__ void __launch_bounds__(32) k_inf_decode(const uint8_t *src, uint64_t n, InfPar *par, const InfBlock *blocks, uint16_t *tmp)
+__device__ __forceinline__ void nb_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void nb_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t n, InfPar *par, const InfBlock *blocks, uint16_t *tmp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeShared &S = *reinterpret_cast<DecodeShared *>(smem_raw);
     const uint32_t k = blockIdx.x;
     if (k >= par->nblocks) return;
     const InfBlock b = blocks[k];
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *dst = tmp + b.out_off;
     if (b.type == 0) {
-        for (uint32_t i = lane; i < b.out_len; i += 32) dst[i] = src[b.src_byte + i];
+        for (uint32_t i = threadIdx.x; i < b.out_len; i += 64) dst[i] = src[b.src_byte + i];
         return;
     }
-    BitRd br;
-    uint32_t lm = 0, dm = 0;
-    if (lane == 0) {
-        uint32_t lenbits, distbits, bf;
-        const int rc = dec_setup(S.d, src, n, b.start_bit, br, lenbits, distbits, &bf);
-        S.d.err = rc != 0;
-        S.d.done = rc != 0;
-        lm = (1u << lenbits) - 1;
-        dm = (1u << distbits) - 1;
+    constexpr uint32_t kFull = 1, kEmpty = 5; // named barriers 1..4 / 5..8
+    if (warp == 0) {
+        // ---- decoding warp
+        BitRd br;
+        uint32_t lm = 0, dm = 0, done = 0;
+        if (lane == 0) {
+            uint32_t lenbits = 0, distbits = 0, bf;
+            const int rc = dec_setup(S.d, src, n, b.start_bit, br, lenbits, distbits, &bf);
+            S.d.err = rc != 0;
+            done = rc != 0;
+            lm = (1u << lenbits) - 1;
+            dm = (1u << distbits) - 1;
+        }
+        for (uint32_t it = 0;; it++) {
+            const uint32_t q = it & 3;
+            if (it >= 4) nb_sync(kEmpty + q);
+            if (lane == 0) {
+                uint32_t cnt = 0;
+                while (!done && cnt < 32) {
+                    uint32_t v, d;
+                    const int t = dec_symbol(S.d, br, lm, dm, v, d);
+                    if (t == 0) S.d.q[q][cnt++] = v;
+                    else if (t == 1) S.d.q[q][cnt++] = (v << 16) | d;
+                    else { done = 1; if (t < 0) S.d.err = 1; }
+                }
+                S.d.qn[q] = cnt;
+                S.d.qfin[q] = done;
+            }
+            __syncwarp();
+            nb_arrive(kFull + q);
+            if (__shfl_sync(0xffffffffu, done, 0)) break;
+        }
+        return;
     }
-    __syncwarp();
+    // ---- replaying warp
     uint32_t o = 0, flushed = 0;
     bool bad = false;
     const uint64_t reach = b.out_off; // bytes of output in front of this block
-    while (true) {
-        if (lane == 0 && !S.d.done) {
-            uint32_t cnt = 0;
-            while (cnt < 32) {
-                uint32_t v, d;
-                const int t = dec_symbol(S.d, br, lm, dm, v, d);
-                if (t == 0) S.d.q[cnt++] = v;
-                else if (t == 1) S.d.q[cnt++] = (v << 16) | d;
-                else { S.d.done = 1; if (t < 0) S.d.err = 1; break; }
-            }
-            S.d.qn = cnt;
-        } else if (lane == 0) S.d.qn = 0;
+    for (uint32_t it = 0;; it++) {
+        const uint32_t q = it & 3;
+        nb_sync(kFull + q);
+        const uint32_t cnt = S.d.qn[q];
+        const bool fin = S.d.qfin[q] != 0;
+        const uint32_t e = lane < cnt ? S.d.q[q][lane] : 0;
         __syncwarp();
-        const uint32_t cnt = S.d.qn;
-        const uint32_t e = lane < cnt ? S.d.q[lane] : 0;
+        nb_arrive(kEmpty + q); // the batch is in registers
         const uint32_t len = e >> 16;
         const bool islit = lane < cnt && len == 0;
-        uint32_t l = lane < cnt ? (len ? len : 1u) : 0u;
+        const uint32_t l = lane < cnt ? (len ? len : 1u) : 0u;
         uint32_t incl = l;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -772,12 +794,11 @@ __global__ void __launch_bounds__(32) k_inf_decode(const uint8_t *src, uint64_t 
             __syncwarp();
         }
         o += __shfl_sync(0xffffffffu, incl, 31);
-        const bool fin = S.d.done != 0;
         if (o - flushed >= kWSize / 2 || fin) {
-            for (uint32_t idx = flushed + lane; idx < o; idx += 32) dst[idx] = S.win[idx & (kWSize - 1)];
+            for (uint32_t idx = flushed + lane; idx < o && idx < b.out_len; idx += 32) dst[idx] = S.win[idx & (kWSize - 1)];
             flushed = o;
         }
-        if (o > kMaxBlockOut) { bad = true; break; }
+        if (o > b.out_len) bad = true; // cannot happen (k_inf_scan measured this block); never leave the hand-over loop early
         __syncwarp();
         if (fin) break;
     }
@@ -912,7 +933,7 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 if ((rc = reserve(4 /*S_M*/, (hpar.total_out + 64) * 2, &p)) != ZB_OK) return rc;
                 dtmp = static_cast<uint16_t *>(p);
                 CKI(cudaFuncSetAttribute(k_inf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
-                k_inf_decode<<<hpar.nblocks, 32, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp);
+                k_inf_decode<<<hpar.nblocks, 64, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp);
                 const uint64_t quads = (hpar.total_out + 1023) / 1024;
                 k_inf_resolve<<<(unsigned)(quads < 148 * 16 ? (quads ? quads : 1) : 148 * 16), 256, 0, st>>>(dpar, dblk, dtmp, d_dst);
                 launches += 2;
