@@ -44,6 +44,10 @@ __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
 __global__ void k_links_roll(JobBufs);
+__global__ void k_links2_std(JobBufs);
+__global__ void k_links2_roll(JobBufs);
+__global__ void k_links_fix_std(JobBufs);
+__global__ void k_links_fix_roll(JobBufs);
 __global__ void k_slow(JobBufs);
 __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
@@ -51,6 +55,7 @@ __global__ void k_tail_slow(JobBufs);
 constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
+constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64;
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kRollSmemBytes = 32768 * 4 + (kLinkTile + 32768 + 64);
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
@@ -74,6 +79,8 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmemBytes));
     CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
     CK(cudaFuncSetAttribute(k_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkipSmemBytes));
+    CK(cudaFuncSetAttribute(k_links2_std, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
+    CK(cudaFuncSetAttribute(k_links2_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
     CK(cudaFuncSetAttribute(k_links_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmemBytes));
     CK(cudaFuncSetAttribute(k_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlowSmemBytes));
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
@@ -146,7 +153,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -216,6 +223,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
     RES(S_BMAP, 8192, bucket_map, uint32_t *)
     RES(S_LR, npad * 2, Lr, uint16_t *)
+    RES(S_LLAST, (size_t)nmt * 65536 * 2, link_last, uint16_t *)
     RES(S_CSTATE, (size_t)(npt + 1) * 16, chain_state, uint4 *)
     uint32_t *d_lists;
     const uint32_t max_list = N / 512 + 2;
@@ -300,9 +308,19 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
             pbegin();
-            if (jb.slow_mode && jb.sp.slow) k_links_roll<<<nmt, 1024, kRollSmemBytes, st>>>(jb);
-            else k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
-            launches++;
+            if (getenv("ZB_LINKS_V1")) {
+                if (jb.slow_mode && jb.sp.slow) k_links_roll<<<nmt, 1024, kRollSmemBytes, st>>>(jb);
+                else k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
+                launches++;
+            } else if (jb.slow_mode && jb.sp.slow) {
+                k_links2_roll<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
+                k_links_fix_roll<<<N / 256 + 1, 256, 0, st>>>(jb);
+                launches += 2;
+            } else {
+                k_links2_std<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
+                k_links_fix_std<<<N / 256 + 1, 256, 0, st>>>(jb);
+                launches += 2;
+            }
             if (!jb.slow_mode) CK(cudaMemcpyAsync(jb.Lr, jb.L, npad * 2, cudaMemcpyDeviceToDevice, st));
             pend(0, 1);
             if (jb.slow_mode) {

@@ -12,7 +12,7 @@ extern thread_local char g_err[256];
 size_t deflate_bound(size_t n);
 
 struct Engine {
-    static constexpr int kSlots = 36;
+    static constexpr int kSlots = 40;
     struct Buf { void *p = nullptr; size_t cap = 0; };
     int device = -1;
     cudaStream_t st = nullptr;

@@ -91,6 +91,98 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte
     return __funnelshift_r(words[w], words[w + 1], (byte_idx & 3u) * 8u);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_links2 / k_links_fix: the same L[] as k_links, without the warm-up replay and without every warp hashing every
+// position.  A CTA handles one 32 KiB tile on its own:
+//   A. all threads hash the tile's positions once into a shared key array;
+//   B. warp w owns the keys with key % 32 == w and replays their insertions in position order against the shared head
+//      table (32 positions per step, __match_any_sync orders equal keys inside a step);
+//   C. the head table (last occurrence of every key in the tile) goes to global memory; a position that is the first of
+//      its key in the tile is flagged and k_links_fix links it to the last occurrence in the PREVIOUS tile (a link
+//      never reaches further: tile >= max distance).
+// kRoll: the rolling 3-byte hash of level 9 (15-bit keys, links up to kLinkCapSlow) instead of the 4-byte hash.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kFirstFlag = 0xffffu; // L value of a first occurrence until k_links_fix has seen it
+
+template <bool kRoll>
+__device__ __forceinline__ void links2_body(const JobBufs &jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
+    uint16_t *head = reinterpret_cast<uint16_t *>(smem);                 // kKeys entries: 1 + position in the tile
+    uint16_t *keys = reinterpret_cast<uint16_t *>(smem + kKeys * 2);     // kLinkTile entries
+    uint8_t *sd = smem + kKeys * 2 + kLinkTile * 2;                      // kLinkTile + 16 bytes of data
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : kMaxDist;
+    const uint32_t ts = blockIdx.x * kLinkTile;
+    const uint32_t te = min(ts + kLinkTile, N);
+    const uint32_t tv = N >= need ? min(te, N - need + 1) : ts; // positions with enough bytes to hash
+    for (uint32_t i = tid; i < kKeys / 2; i += 1024) reinterpret_cast<uint32_t *>(head)[i] = 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ts); // zero padded behind N
+        uint4 *dst = reinterpret_cast<uint4 *>(sd);
+        for (uint32_t i = tid; i < (te - ts + 16 + 15) / 16; i += 1024) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < te - ts; i += 1024) {
+        uint32_t k;
+        if (kRoll) k = hash_roll3(sd[i], sd[i + 1], sd[i + 2]);
+        else k = hash_u32(lds_u32(words, i));
+        keys[i] = (uint16_t)k;
+    }
+    __syncthreads();
+    const uint32_t nv = tv > ts ? tv - ts : 0;
+    for (uint32_t base = 0; base < nv; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < nv ? keys[i] : 0u;
+        const bool mine = i < nv && (key & 31u) == warp;
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (m == 0) continue;
+        if (mine) {
+            const uint32_t peers = __match_any_sync(m, key);
+            const uint32_t lower = peers & ((1u << lane) - 1u);
+            uint32_t pred = lower ? base + (31 - __clz(lower)) + 1 : head[key]; // 1 + position, 0 = none in this tile
+            uint32_t d = pred ? i + 1 - pred : kFirstFlag;
+            if (pred && d > cap) d = 0;
+            jb.L[ts + i] = (uint16_t)d;
+            if ((peers >> lane) == 1u) head[key] = (uint16_t)(i + 1);
+        }
+        __syncwarp();
+    }
+    for (uint32_t x = tv + tid; x < te; x += 1024) jb.L[x] = 0; // positions without enough input are never hashed
+    __syncthreads();
+    uint4 *out = reinterpret_cast<uint4 *>(jb.link_last + (size_t)blockIdx.x * kKeys);
+    const uint4 *hv = reinterpret_cast<const uint4 *>(head);
+    for (uint32_t i = tid; i < kKeys * 2 / 16; i += 1024) out[i] = hv[i];
+}
+
+template <bool kRoll>
+__device__ __forceinline__ void links_fix_body(const JobBufs &jb)
+{
+    constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
+    const uint32_t x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= jb.N || jb.L[x] != kFirstFlag) return;
+    const uint32_t tile = x / kLinkTile, cap = kRoll ? kLinkCapSlow : kMaxDist;
+    uint32_t d = 0;
+    if (tile > 0) {
+        const uint8_t *q = jb.in + x;
+        const uint32_t key = kRoll ? hash_roll3(q[0], q[1], q[2])
+                                   : hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+        const uint32_t last = jb.link_last[(size_t)(tile - 1) * kKeys + key]; // 1 + position in the previous tile
+        if (last) {
+            d = x - ((tile - 1) * kLinkTile + last - 1);
+            if (d > cap) d = 0;
+        }
+    }
+    jb.L[x] = (uint16_t)d;
+}
+
+__global__ void __launch_bounds__(1024) k_links2_std(JobBufs jb) { links2_body<false>(jb); }
+__global__ void __launch_bounds__(1024) k_links2_roll(JobBufs jb) { links2_body<true>(jb); }
+__global__ void __launch_bounds__(256) k_links_fix_std(JobBufs jb) { links_fix_body<false>(jb); }
+__global__ void __launch_bounds__(256) k_links_fix_roll(JobBufs jb) { links_fix_body<true>(jb); }
+
 __global__ void __launch_bounds__(1024) k_links(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
