@@ -1,5 +1,5 @@
 """GPU parity tests (run on the B200 box): every call goes through the C ABI of libz_b200.so and is
-compared with the CPU oracle on the same inputs -- bit-exact for the level 3..6 one-shot path."""
+compared with the CPU oracle on the same inputs -- bit-exact for the level 3..9 one-shot path."""
 import hashlib
 import json
 import os

@@ -89,3 +89,21 @@ def test_slow_levels_parse_matches_reference_parser(level):
         o = _syms("hm_oracle_trace", data, level)
         s = _syms("hm_parse_slow", data, level)
         assert len(o) == len(s) and (o == s).all(), name
+
+
+def test_inflate_scout_finds_exactly_the_dynamic_blocks():
+    """parse_dynamic_header (zb_inflate_core.h) run on EVERY bit position of a stream flags the true dynamic block starts and
+    nothing else: the block-parallel inflate chains blocks through these candidates."""
+    import zlib
+    for data, level in ((silesia_member(3)[:300000], 6), (silesia_member(3)[:300000], 1), (synthetic_mix(400000, 17), 9)):
+        comp = zlib.compress(data, level)
+        cap = 4096
+        starts = (ctypes.c_uint64 * cap)()
+        nd, outlen = ctypes.c_uint32(0), ctypes.c_uint64(0)
+        rc = H().hm_inflate_walk(comp, len(comp), ctypes.c_uint64(16), starts, cap, ctypes.byref(nd), ctypes.byref(outlen))
+        assert rc == 0 and outlen.value == len(data) and nd.value >= 1
+        cands = (ctypes.c_uint64 * 65536)()
+        nc = ctypes.c_uint32(0)
+        assert H().hm_inflate_scout(comp, len(comp), cands, 65536, ctypes.byref(nc)) == 0
+        assert set(starts[: nd.value]) <= set(cands[: nc.value])
+        assert nc.value - nd.value <= 2  # false candidates are possible in principle, they never reach the chain

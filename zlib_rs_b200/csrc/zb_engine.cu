@@ -25,7 +25,6 @@ static void set_err(const char *what, cudaError_t e)
     } while (0)
 
 // kernels (zb_kernels.cu)
-__global__ void k_links(JobBufs);
 __global__ void k_match(JobBufs);
 __global__ void k_skip(JobBufs);
 __global__ void k_nxt(JobBufs);
@@ -43,7 +42,6 @@ __global__ void k_encode(JobBufs);
 __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
-__global__ void k_links_roll(JobBufs);
 __global__ void k_links2_std(JobBufs);
 __global__ void k_links2_roll(JobBufs);
 __global__ void k_links_fix_std(JobBufs);
@@ -52,12 +50,10 @@ __global__ void k_slow(JobBufs);
 __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
 
-constexpr uint32_t kLinksSmemBytes = 65536 * 2 + (kLinkTile + kLinkWarm + 64);
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64;
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
-constexpr uint32_t kRollSmemBytes = 32768 * 4 + (kLinkTile + 32768 + 64);
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
 
@@ -76,12 +72,10 @@ int Engine::init(int dev)
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(upload_tables());
-    CK(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmemBytes));
     CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
     CK(cudaFuncSetAttribute(k_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkipSmemBytes));
     CK(cudaFuncSetAttribute(k_links2_std, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
     CK(cudaFuncSetAttribute(k_links2_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
-    CK(cudaFuncSetAttribute(k_links_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmemBytes));
     CK(cudaFuncSetAttribute(k_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlowSmemBytes));
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
@@ -308,11 +302,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
             pbegin();
-            if (getenv("ZB_LINKS_V1")) {
-                if (jb.slow_mode && jb.sp.slow) k_links_roll<<<nmt, 1024, kRollSmemBytes, st>>>(jb);
-                else k_links<<<nmt, 1024, kLinksSmemBytes, st>>>(jb);
-                launches++;
-            } else if (jb.slow_mode && jb.sp.slow) {
+            if (jb.slow_mode && jb.sp.slow) {
                 k_links2_roll<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
                 k_links_fix_roll<<<N / 256 + 1, 256, 0, st>>>(jb);
                 launches += 2;

@@ -1,7 +1,8 @@
 // zb_kernels.cu -- CUDA kernels of the B200 deflate engine (compiled for sm_100a only).
 //
 // Pipeline for one level-3..6 job (DESIGN.md has the full picture):
-//   k_links      L[x]   : previous position with the same 4-byte hash (the reference's head/prev chains)
+//   k_links2/fix L[x]   : previous position with the same 4-byte hash (the reference's head/prev chains)
+//   k_skip       Lr[x]  : the same links with the never-inserted positions (holes) bridged
 //   k_match      M[x]   : longest_match for EVERY position, 64 KiB window + chains staged in shared memory
 //   k_nxt        nxt[p] : canonical macro step of the reference parser from every position
 //   k_path_*            : which positions the serial parser really visits (tile-local pointer jumping,
@@ -73,16 +74,6 @@ struct SAccR { // shared-memory window of k_match; links are already bridged ove
     __device__ __forceinline__ bool inserted(uint32_t) const { return true; }
 };
 
-// ------------------------------------------------------------------------------------------------
-// k_links: L[x] = distance to the previous position with the same hash (hash_calc.rs:40-59): the
-// reference's head/prev chains as if every position were inserted (holes are bridged by k_skip's skip
-// pointers when the chains are staged in k_match).  One CTA per 32 KiB tile
-// replays the insertions of the tile and of the 32512 positions before it, in order, against a
-// shared-memory head table.  The 32 warps split the hash space (warp w owns keys with key%32 == w), so
-// their head entries are disjoint and every warp can run through the positions at its own pace, 32
-// positions per step; __match_any_sync orders equal keys inside a step.
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t kLinksSmem = 65536 * 2 + (kLinkTile + kLinkWarm + 64) + ((kLinkTile + kLinkWarm) / 32 + 8) * 4;
 
 __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte_idx)
 {
@@ -92,8 +83,9 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_links2 / k_links_fix: the same L[] as k_links, without the warm-up replay and without every warp hashing every
-// position.  A CTA handles one 32 KiB tile on its own:
+// k_links2 / k_links_fix: L[x] = distance to the previous position with the same hash (hash_calc.rs:40-59), i.e. the
+// reference's head/prev chains as if every position were inserted (k_skip bridges the holes later).  No warm-up replay of the
+// window before a tile and no redundant hashing: a CTA handles one 32 KiB tile on its own:
 //   A. all threads hash the tile's positions once into a shared key array;
 //   B. warp w owns the keys with key % 32 == w and replays their insertions in position order against the shared head
 //      table (32 positions per step, __match_any_sync orders equal keys inside a step);
@@ -182,55 +174,6 @@ __global__ void __launch_bounds__(1024) k_links2_std(JobBufs jb) { links2_body<f
 __global__ void __launch_bounds__(1024) k_links2_roll(JobBufs jb) { links2_body<true>(jb); }
 __global__ void __launch_bounds__(256) k_links_fix_std(JobBufs jb) { links_fix_body<false>(jb); }
 __global__ void __launch_bounds__(256) k_links_fix_roll(JobBufs jb) { links_fix_body<true>(jb); }
-
-__global__ void __launch_bounds__(1024) k_links(JobBufs jb)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *head = reinterpret_cast<uint16_t *>(smem);
-    uint8_t *sd = smem + 65536 * 2;
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t N = jb.N;
-    const uint32_t ts = blockIdx.x * kLinkTile;
-    const uint32_t te = min(ts + kLinkTile, N);
-    const uint32_t ws = ts > kLinkWarm ? ts - kLinkWarm : 0; // multiple of 32 (and of 16)
-    for (uint32_t i = tid; i < 32768; i += 1024) reinterpret_cast<uint32_t *>(head)[i] = 0;
-    {
-        const uint32_t n16 = (te + 16 - ws + 15) / 16; // the input buffer is zero padded
-        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
-        uint4 *dst = reinterpret_cast<uint4 *>(sd);
-        for (uint32_t i = tid; i < n16; i += 1024) dst[i] = src[i];
-    }
-    __syncthreads();
-    for (uint32_t base = ws; base < te; base += 32) {
-        const uint32_t x = base + lane;
-        const bool valid = x < te && x + 4 <= N;
-        uint32_t key = 0;
-        if (valid) key = hash_u32(lds_u32(words, x - ws));
-        const bool mine = valid && (key & 31u) == warp;
-        const uint32_t m = __ballot_sync(0xffffffffu, mine);
-        if (m == 0) continue;
-        uint32_t pred_rel = 0, peers_ins = 0;
-        if (mine) {
-            peers_ins = __match_any_sync(m, key);
-            const uint32_t lower = peers_ins & ((1u << lane) - 1u);
-            if (lower) pred_rel = (base + (31 - __clz(lower))) - ws + 1;
-            else pred_rel = head[key];
-        }
-        __syncwarp();
-        if (mine) {
-            const uint32_t rel = x - ws + 1;
-            if (x >= ts) {
-                const uint32_t d = pred_rel ? rel - pred_rel : 0;
-                jb.L[x] = (uint16_t)((d && d <= kMaxDist) ? d : 0);
-            }
-            if ((peers_ins >> lane) == 1u) head[key] = (uint16_t)rel;
-        }
-        __syncwarp();
-    }
-    // positions without four bytes of input are never hashed
-    for (uint32_t x = max(ts, N >= 3 ? N - 3 : 0) + tid; x < te; x += 1024) jb.L[x] = 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_skip: Lr[] = the chain links with the holes bridged, for one dirty 32 KiB tile.  At a hole (a position the

@@ -9,8 +9,7 @@
 
 namespace zb {
 
-constexpr uint32_t kLinkTile = 32768;   // positions per k_links CTA
-constexpr uint32_t kLinkWarm = 32512;   // warm-up positions before the tile (>= kMaxDist)
+constexpr uint32_t kLinkTile = 32768;   // positions per k_links2 CTA (>= the largest link)
 constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the match phase
 constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA (126 KiB of shared memory)
 constexpr uint32_t kPathTile = 16384;   // positions per path tile

@@ -1,6 +1,6 @@
 // zb_slow.cu -- kernels of the level 7..9 path (deflate_slow, lazy matching; sm_100a).
 //
-//   k_links_roll  L[x]   : previous position with the same rolling 3-byte hash (level 9; levels 7/8 use k_links)
+//   k_links2_roll L[x]   : previous position with the same rolling 3-byte hash (level 9; levels 7/8 use k_links2_std; zb_kernels.cu)
 //   k_slow        nxt[p] : macro step of the lazy parser from every position taken as a fresh loop-top
 //                 M[p]   : its symbols (literal count, match length, distance)
 //   k_path_*             : shared with the level-6 path
@@ -10,55 +10,6 @@
 #include "zb_slow.h"
 
 namespace zb {
-
-constexpr uint32_t kRollWarm = 32768;
-
-__global__ void __launch_bounds__(1024) k_links_roll(JobBufs jb)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t *head = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *sd = smem + 32768 * 4;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t N = jb.N;
-    const uint32_t ts = blockIdx.x * kLinkTile;
-    const uint32_t te = min(ts + kLinkTile, N);
-    const uint32_t ws = ts > kRollWarm ? ts - kRollWarm : 0;
-    for (uint32_t i = tid; i < 32768; i += 1024) head[i] = 0;
-    {
-        const uint32_t n16 = (te + 16 - ws + 15) / 16; // the input buffer is zero padded
-        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
-        uint4 *dst = reinterpret_cast<uint4 *>(sd);
-        for (uint32_t i = tid; i < n16; i += 1024) dst[i] = src[i];
-    }
-    __syncthreads();
-    for (uint32_t base = ws; base < te; base += 32) {
-        const uint32_t x = base + lane;
-        const bool valid = x < te && x + 3 <= N;
-        uint32_t key = 0;
-        if (valid) key = hash_roll3(sd[x - ws], sd[x - ws + 1], sd[x - ws + 2]);
-        const bool mine = valid && (key & 31u) == warp;
-        const uint32_t m = __ballot_sync(0xffffffffu, mine);
-        if (m == 0) continue;
-        uint32_t pred_rel = 0, peers_ins = 0;
-        if (mine) {
-            peers_ins = __match_any_sync(m, key);
-            const uint32_t lower = peers_ins & ((1u << lane) - 1u);
-            if (lower) pred_rel = (base + (31 - __clz(lower))) - ws + 1;
-            else pred_rel = head[key];
-        }
-        __syncwarp();
-        if (mine) {
-            const uint32_t rel = x - ws + 1;
-            if (x >= ts) {
-                const uint32_t d = pred_rel ? rel - pred_rel : 0;
-                jb.L[x] = (uint16_t)((d && d <= kLinkCapSlow) ? d : 0);
-            }
-            if ((peers_ins >> lane) == 1u) head[key] = rel;
-        }
-        __syncwarp();
-    }
-    for (uint32_t x = max(ts, N >= 2 ? N - 2 : 0) + tid; x < te; x += 1024) jb.L[x] = 0;
-}
 
 // shared-memory window of k_slow: data and links of [ws, ws + span)
 struct SlowSAcc {
