@@ -78,29 +78,32 @@ struct TreeScratch {
     CtData ltree[kHeapSize], dtree[2 * kDCodes + 1], bltree[2 * kBlCodes + 1];
     uint32_t heap[kHeapSize];
     uint8_t depth[kHeapSize];
+    uint64_t hk[kHeapSize]; // the active heap with its sort key: ((freq << 8 | depth) << 16) | node -- one load per comparison
 };
 
 struct TreeState { uint64_t opt_len, static_len; };
 
 ZB_HD uint32_t freq_depth(const CtData *tree, const uint8_t *depth, uint32_t i) { return ((uint32_t)tree[i].fc << 8) | depth[i]; }
 
-ZB_HDN inline void pqdownheap(TreeScratch &s, const CtData *tree, int heap_len, int k)
+// deflate.rs:3045-3085: sift down; ties on (freq, depth) prefer the right child, the node number never decides
+ZB_HDN inline void pqdownheap(TreeScratch &s, int heap_len, int k)
 {
-    uint32_t v = s.heap[k], v_val = freq_depth(tree, s.depth, v);
+    const uint64_t v = s.hk[k], v_val = v >> 16;
     int j = k << 1;
     while (j <= heap_len) {
-        uint32_t j_val = freq_depth(tree, s.depth, s.heap[j]);
+        uint64_t e = s.hk[j];
         if (j < heap_len) {
-            uint32_t j1 = freq_depth(tree, s.depth, s.heap[j + 1]);
-            if (j1 <= j_val) { j++; j_val = j1; }
+            const uint64_t e1 = s.hk[j + 1];
+            if ((e1 >> 16) <= (e >> 16)) { j++; e = e1; }
         }
-        if (v_val <= j_val) break;
-        s.heap[k] = s.heap[j];
+        if (v_val <= (e >> 16)) break;
+        s.hk[k] = e;
         k = j;
         j <<= 1;
     }
-    s.heap[k] = v;
+    s.hk[k] = v;
 }
+ZB_HD uint64_t heap_entry(const CtData *tree, const uint8_t *depth, uint32_t node) { return ((uint64_t)freq_depth(tree, depth, node) << 16) | node; }
 
 // kind: 0 = literal/length tree, 1 = distance tree, 2 = bit-length tree.  Returns max_code.
 ZB_HDN inline int build_tree(const HuffTables &t, TreeScratch &s, TreeState &st, CtData *tree, int kind)
@@ -121,22 +124,24 @@ ZB_HDN inline int build_tree(const HuffTables &t, TreeScratch &s, TreeState &st,
         if (kind == 0) st.static_len -= t.sl_len[node];
         else if (kind == 1) st.static_len -= 5;
     }
-    for (n = heap_len / 2; n >= 1; n--) pqdownheap(s, tree, heap_len, n);
+    for (n = 1; n <= heap_len; n++) s.hk[n] = heap_entry(tree, s.depth, s.heap[n]);
+    for (n = heap_len / 2; n >= 1; n--) pqdownheap(s, heap_len, n);
     node = elems;
     do {
-        n = (int)s.heap[1];
-        s.heap[1] = s.heap[heap_len--];
-        pqdownheap(s, tree, heap_len, 1);
-        int m = (int)s.heap[1];
+        n = (int)(s.hk[1] & 0xffffu);
+        s.hk[1] = s.hk[heap_len--];
+        pqdownheap(s, heap_len, 1);
+        int m = (int)(s.hk[1] & 0xffffu);
         s.heap[--heap_max] = (uint32_t)n;
         s.heap[--heap_max] = (uint32_t)m;
         tree[node].fc = (uint16_t)(tree[n].fc + tree[m].fc);
         s.depth[node] = (uint8_t)((s.depth[n] >= s.depth[m] ? s.depth[n] : s.depth[m]) + 1);
         tree[n].dl = tree[m].dl = (uint16_t)node;
-        s.heap[1] = (uint32_t)node++;
-        pqdownheap(s, tree, heap_len, 1);
+        s.hk[1] = heap_entry(tree, s.depth, (uint32_t)node);
+        node++;
+        pqdownheap(s, heap_len, 1);
     } while (heap_len >= 2);
-    s.heap[--heap_max] = s.heap[1];
+    s.heap[--heap_max] = (uint32_t)(s.hk[1] & 0xffffu);
 
     // gen_bitlen
     uint16_t bl_count[kMaxBits + 1];
