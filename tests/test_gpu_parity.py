@@ -162,6 +162,29 @@ def test_silesia_tar_level9_equals_reference_file(eng):
     assert out == silesia_gz()
 
 
+def test_rle_strategy_bit_exact(eng):
+    """Z_RLE (deflate/algorithm/rle.rs): runs of the previous byte only; same bytes as the oracle at every level."""
+    rng = np.random.default_rng(3)
+    runs = b"".join(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 700)) for _ in range(3000))
+    cases = [b"", b"a", b"aa", b"aaa", b"aaaa", bytes(5), bytes(300000), runs, runs[:65536], runs[:65537] + b"zz", synthetic_mix(200000, 8),
+             silesia_member(7)[:300000], b"ab" * 1000 + bytes(70000) + b"x" * 258 + b"y" * 259 + b"z" * 260]
+    for level in (1, 6, 9):
+        for d in cases:
+            out, res = eng.deflate(d, level=level, strategy=3)
+            assert res.exact_parity == 1
+            assert out == O.compress(d, level, 15, 8, 3)[1], (level, len(d))
+
+
+def test_slow_levels_full_block_of_literals(eng):
+    """16383 symbols ending with the pending literal: deflate_slow's last tally ignores the full buffer (slow.rs:150-153)."""
+    rng = np.random.default_rng(2)
+    for n in (16383, 16384, 32766, 32767):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for level in (7, 9):
+            out, res = eng.deflate(d, level=level)
+            assert out == O.compress(d, level)[1], (n, level)
+
+
 def test_other_levels_and_strategies_valid_streams(eng):
     d = silesia_member(3)[:200000]
     for level in (0, 1, 2, 7, 8, 9):
@@ -172,8 +195,7 @@ def test_other_levels_and_strategies_valid_streams(eng):
     for strategy in (1, 2, 3, 4):
         out, res = eng.deflate(d, level=6, strategy=strategy)
         assert zlib.decompress(out) == d
-        if strategy in (1, 2, 4):  # FILTERED / HUFFMAN_ONLY / FIXED follow the reference exactly
-            assert out == O.compress(d, 6, 15, 8, strategy)[1], strategy
+        assert out == O.compress(d, 6, 15, 8, strategy)[1], strategy  # FILTERED / HUFFMAN_ONLY / RLE / FIXED follow the reference exactly
     for wb in (-15, 31):
         out, res = eng.deflate(d, level=6, window_bits=wb)
         assert out == O.compress(d, 6, wb)[1]

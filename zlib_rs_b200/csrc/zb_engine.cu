@@ -47,6 +47,7 @@ __global__ void k_links2_roll(JobBufs);
 __global__ void k_links_fix_std(JobBufs);
 __global__ void k_links_fix_roll(JobBufs);
 __global__ void k_slow(JobBufs);
+__global__ void k_rle(JobBufs);
 __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
 
@@ -250,16 +251,13 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.not_last = (flags & ZB_FLAG_NOT_LAST) ? 1 : 0;
     if (jb.not_last && (level == 0 || wrap != 0)) { snprintf(g_err, sizeof g_err, "NOT_LAST needs raw deflate and level > 0"); return ZB_E_PARAM; }
     jb.xfl = level == 9 ? 2 : (strategy >= 2 || level < 2) ? 4 : 0;
-    // levels 3..6 follow the reference parser exactly; the other levels run the closest exact kernel set
+    // levels 3..9 and Z_RLE follow the reference parser exactly; levels 1 and 2 run the level-3 kernel set
     int eng_level = level;
     bool exact = wb == 15;
     if (level != 0 && !jb.huffman_only) {
-        if (level < 3) { eng_level = 3; exact = false; }
-        if (strategy == 3) exact = false; // Z_RLE parser not implemented: medium parser instead
-        if (level > 6) {
-            if (strategy == 3) eng_level = 6;
-            else { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
-        }
+        if (level < 3) { eng_level = 3; exact = strategy == 3; } // deflate_quick / deflate_fast: level-3 kernel set instead
+        if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level
+        else if (level > 6) { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
     }
     if (jb.slow_mode) jb.tail_start = N; // the lazy path needs no serial tail: every step knows the end of the input
     jb.lp = level_params(eng_level);
@@ -302,7 +300,9 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             CK(cudaMemsetAsync(jb.M + N, 0, (size_t)kPad * 4, st));
             CK(cudaMemsetAsync(jb.L + N, 0, (size_t)kPad * 2, st));
             pbegin();
-            if (jb.slow_mode && jb.sp.slow) {
+            if (jb.slow_mode == 2) {
+                // no hash chains
+            } else if (jb.slow_mode && jb.sp.slow) {
                 k_links2_roll<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
                 k_links_fix_roll<<<N / 256 + 1, 256, 0, st>>>(jb);
                 launches += 2;
@@ -317,7 +317,8 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 if (N > 0) {
                     iters = 1;
                     pbegin();
-                    k_slow<<<(N + kSlowSub - 1) / kSlowSub, 1024, kSlowSmemBytes, st>>>(jb);
+                    if (jb.slow_mode == 2) k_rle<<<(N + 255) / 256, 256, 0, st>>>(jb);
+                    else k_slow<<<(N + kSlowSub - 1) / kSlowSub, 1024, kSlowSmemBytes, st>>>(jb);
                     pend(1, 1);
                     if (profile) phase_ms[11] = phase_ms[1];
                     pbegin();

@@ -871,6 +871,8 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
             if (jb.huffman_only) {
                 const uint32_t q = jb.syms[li].pos;
                 Bf = q < 2 * kWSize ? 0 : kWSize * (1 + (q - 2 * kWSize) / kWSize);
+            } else if (jb.slow_mode == 2) {
+                Bf = base_at(jb.syms[li].pos, jb.N);     // Z_RLE tallies a symbol at its own loop-top
             } else if (jb.slow_mode) {
                 Bf = base_at(jb.syms[li].pos + 1, jb.N); // the symbol is tallied at the loop-top behind its first byte (slow.rs:84-136)
             } else Bf = li < n_mid ? wbase(jb.syms[li].pos) : jb.sym_base[li - n_mid];

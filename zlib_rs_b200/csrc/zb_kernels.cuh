@@ -80,7 +80,7 @@ struct JobBufs {
     uint32_t *long_list;      // per path sub-tile: positions of path nodes whose macro step emits a long match
     uint32_t *long_cnt;
     SlowParams sp;            // level 7..9 parameters
-    uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9)
+    uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9); 2: Z_RLE (steps from k_rle, same path/emit kernels)
     uint16_t *link_last;      // per 32 KiB tile: last occurrence (1 + position in the tile) of every hash key (k_links2 -> k_links_fix)
     uint16_t *Lr;             // N + kPad: links with the holes bridged (k_skip); equals L while there are no holes
     const uint32_t *skip_list;  // k_skip: match tile per CTA

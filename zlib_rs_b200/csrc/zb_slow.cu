@@ -270,6 +270,28 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
     }
 }
 
+// Z_RLE (deflate/algorithm/rle.rs): a match is a run of the previous byte (distance 1); the step at p depends on the data only.
+__global__ void __launch_bounds__(256) k_rle(JobBufs jb)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, N = jb.N;
+    if (p >= N) return;
+    const uint8_t *d = jb.in;
+    const uint32_t B = base_at(p, N), la = lookahead_at(p, B, N);
+    uint32_t len = 0;
+    if (la >= 3 && p > 0 && d[p - 1] == d[p] && d[p] == d[p + 1]) {
+        const uint32_t c = d[p - 1];
+        uint32_t n = 0;
+        while (n < 256 && p + 2 + n < N + kPad - 8 && d[p + 2 + n] == c) n++; // bytes behind the input: the clamp below decides
+        len = n + 2;
+        if (len > la) len = la;
+        if (len > kMaxMatch) len = kMaxMatch;
+        if (len < 3) len = 0;
+    }
+    const uint32_t next = p + (len ? len : 1u);
+    jb.nxt[p] = ((next - p) & 0xffffu) | (1u << 16) | (next >= N ? kNxtTail : 0u);
+    jb.M[p] = len ? pack_step(SlowStep{next, 0, len, 1}) : pack_step(SlowStep{next, 1, 0, 0});
+}
+
 __device__ __forceinline__ uint32_t emit_step(const JobBufs &jb, uint32_t p, Sym *out)
 {
     const uint32_t v = jb.M[p];
@@ -297,7 +319,14 @@ __global__ void k_tail_slow(JobBufs jb)
     if (jb.N > 0) n += emit_step(jb, jb.info->tail_entry, jb.syms + n);
     jb.info->n_syms = n;
     jb.info->final_base = base_at(jb.N, jb.N);
-    jb.info->n_blocks = n / kBlockSyms + 1;
+    uint32_t nb = n / kBlockSyms + 1;
+    // deflate_slow tallies a pending last literal after its loop and ignores that the symbol buffer may just have filled up
+    // (slow.rs:150-153): the full block then IS the last block instead of being followed by an empty one
+    if (jb.slow_mode == 1 && n > 0 && n % kBlockSyms == 0) {
+        const Sym last = jb.syms[n - 1];
+        if (last.dist == 0 && last.pos + 1 == jb.N) nb--;
+    }
+    jb.info->n_blocks = nb;
 }
 
 } // namespace zb
