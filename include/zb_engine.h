@@ -60,6 +60,10 @@ ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_
 #define ZB_FLAG_NOT_LAST 1u /* raw segment that is not the end of the stream: BFINAL stays 0 and the Z_SYNC_FLUSH marker
                                (empty stored block 00 00 ff ff, zlib-rs/src/deflate.rs:2733-2738) is appended, so segments
                                concatenate into one stream (pigz-style sharding) */
+#define ZB_FLAG_LOW_PARALLEL 2u /* levels 1 and 2: use the parallel level-3 kernel set instead of the exact warp-serial
+                                   deflate_quick / deflate_fast (valid stream, smaller, not byte-identical; exact_parity = 0) */
+#define ZB_FLAG_MEMLEVEL(m) ((uint32_t)(m) << 8) /* deflateInit2's memLevel 1..9 (0 = default 8): lit_bufsize = 1 << (memLevel + 6)
+                                                    sets the symbols per block (zlib-rs/src/deflate.rs:321, deflate/sym_buf.rs:23) */
 ZB_API int zb_deflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                   int level, int strategy, int window_bits, uint32_t flags, zb_deflate_result *res);
 ZB_API size_t zb_deflate_bound(size_t src_len);

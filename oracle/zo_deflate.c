@@ -1225,6 +1225,7 @@ static int deflate_quick(zo_stream *strm, int flush)
                     if (match_len >= WANT_MIN_MATCH) {
                         if (match_len > s->lookahead) match_len = s->lookahead;
                         if (match_len > STD_MAX_MATCH) match_len = STD_MAX_MATCH;
+                        if (s->trace) s->trace(s->trace_ctx, s->abs_base + s->strstart, (unsigned)dist, (unsigned)match_len);
                         emit_dist_static(s, (unsigned)(match_len - STD_MIN_MATCH), (unsigned)dist);
                         s->lookahead -= match_len;
                         s->strstart += match_len;
@@ -1236,6 +1237,7 @@ static int deflate_quick(zo_stream *strm, int flush)
         } else {
             lc = s->window[s->strstart];
         }
+        if (s->trace) s->trace(s->trace_ctx, s->abs_base + s->strstart, 0, lc);
         bw_send_code(s, lc, static_ltree);
         s->strstart++;
         s->lookahead--;

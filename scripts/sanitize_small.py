@@ -1,4 +1,4 @@
-"""compute-sanitizer target: small deflate (levels 6, 9), inflate (parallel + serial) and checksum calls."""
+"""compute-sanitizer target: small deflate (levels 1, 2, 4, 6, 9, memLevel 1/9), inflate (parallel + serial) and checksum calls."""
 import sys, os, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -7,9 +7,12 @@ from corpus import synthetic_mix, silesia_member
 e = Z.Engine(0)
 cases = [synthetic_mix(150000, 4), bytes(200000) + synthetic_mix(70000, 5), silesia_member(1)[:200000], silesia_member(9)[:140000], b"abc" * 30000]
 for d in cases:
-    for level in (6, 9, 4):
+    for level in (6, 9, 4, 1, 2):
         out, r = e.deflate(d, level=level)
         assert zlib.decompress(out) == d, (len(d), level)
+    for mem in (1, 9):
+        out, r = e.deflate(d, level=6, mem_level=mem)
+        assert zlib.decompress(out) == d, (len(d), mem)
     print("deflate ok", len(d), flush=True)
 big = silesia_member(7)[:700000]
 comp = zlib.compress(big, 6)

@@ -161,6 +161,81 @@ static void put_bits(std::vector<uint8_t> &out, uint64_t bitpos, uint64_t val, u
     }
 }
 
+// syms -> blocks -> trees -> bit stream.  blockB(b): window base when block b is flushed.  quick: one static block cut into pieces.
+template <class BF>
+static int encode_stream(const uint8_t *data, uint32_t N, int level, const std::vector<Sym> &syms, BF &&blockB, bool quick, bool fixed, uint32_t block_syms,
+                         uint8_t *dst, uint32_t cap, uint32_t *out_len, int *data_type_out)
+{
+    // ---- blocks ----
+    HuffTables T;
+    init_tables(T);
+    uint32_t nsyms = (uint32_t)syms.size();
+    uint32_t nblocks = nsyms / block_syms + 1;
+    std::vector<BlockDesc> blocks(nblocks);
+    TreeScratch scratch;
+    uint32_t in_pos = 0;
+    int data_type = 2;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        BlockDesc &bd = blocks[b];
+        bd.sym_begin = b * block_syms;
+        bd.sym_count = (b + 1 < nblocks) ? block_syms : nsyms - bd.sym_begin;
+        bd.last = b + 1 == nblocks;
+        bd.in_start = in_pos;
+        uint32_t end = bd.last ? N : (syms[bd.sym_begin + bd.sym_count - 1].pos +
+                                      (syms[bd.sym_begin + bd.sym_count - 1].dist ? syms[bd.sym_begin + bd.sym_count - 1].lc + 3u : 1u));
+        bd.in_len = end - in_pos;
+        in_pos = end;
+        uint32_t Bflush = blockB(b, bd);
+        uint32_t lfreq[kLCodes] = {0}, dfreq[kDCodes] = {0};
+        for (uint32_t i = 0; i < bd.sym_count; i++) {
+            const Sym &s = syms[bd.sym_begin + i];
+            if (s.dist == 0) lfreq[s.lc]++;
+            else { lfreq[257 + T.length_code[s.lc]]++; dfreq[d_code(T, s.dist - 1u)]++; }
+        }
+        if (quick) build_quick_piece(T, bd, lfreq, dfreq, b == 0, b + 1 == nblocks, true);
+        else build_block(T, scratch, bd, lfreq, dfreq, bd.in_start >= Bflush, fixed);
+        if (data_type == 2 && bd.sym_count) data_type = (int)bd.data_type;
+    }
+    // ---- scan + pack ----
+    std::vector<uint8_t> out(2, 0);
+    uint32_t lf = (level < 2 || fixed) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3; // deflate.rs:1591-1601
+    uint32_t h = ((8 + (7 << 4)) << 8) | (lf << 6);
+    h += 31 - (h % 31);
+    out[0] = (uint8_t)(h >> 8); out[1] = (uint8_t)h;
+    uint64_t bit = 16;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        BlockDesc &bd = blocks[b];
+        bd.bit_base = bit;
+        if (bd.type == 0) {
+            put_bits(out, bit, bd.hdr[0], 3);
+            uint64_t p = (bit + 3 + 7) & ~7ull;
+            uint16_t sl = (uint16_t)bd.in_len;
+            put_bits(out, p, sl, 16); put_bits(out, p + 16, (uint16_t)~sl, 16);
+            for (uint32_t i = 0; i < sl; i++) put_bits(out, p + 32 + 8ull * i, data[bd.in_start + i], 8);
+        } else {
+            for (uint32_t i = 0; i < bd.hdr_bits; i++) put_bits(out, bit + i, (bd.hdr[i >> 3] >> (i & 7)) & 1, 1);
+            uint64_t q = bit + bd.hdr_bits;
+            for (uint32_t i = 0; i < bd.sym_count; i++) {
+                const Sym &s = syms[bd.sym_begin + i];
+                uint64_t v; uint32_t n = sym_bits(T, bd, s.dist, s.lc, v);
+                put_bits(out, q, v, n); q += n;
+            }
+            if (!bd.no_eob) { put_bits(out, q, bd.lcode[kEndBlock], bd.llen[kEndBlock]); q += bd.llen[kEndBlock]; }
+            if (q != bit + bd.hdr_bits + bd.body_bits) return -7;
+        }
+        bit = block_end_bit(bd, bit);
+    }
+    uint64_t bytes = (bit + 7) >> 3;
+    out.resize(bytes, 0);
+    uint32_t ad = zo_adler32(1, data, N);
+    out.push_back((uint8_t)(ad >> 24)); out.push_back((uint8_t)(ad >> 16)); out.push_back((uint8_t)(ad >> 8)); out.push_back((uint8_t)ad);
+    if (out.size() > cap) return -5;
+    memcpy(dst, out.data(), out.size());
+    *out_len = (uint32_t)out.size();
+    *data_type_out = data_type;
+    return 0;
+}
+
 extern "C" int hm_deflate(const uint8_t *data, uint32_t N, int level, uint8_t *dst, uint32_t cap, uint32_t *out_len,
                           uint32_t *iters_out, int *data_type_out)
 {
@@ -207,74 +282,11 @@ extern "C" int hm_deflate(const uint8_t *data, uint32_t N, int level, uint8_t *d
     std::vector<uint32_t> ins(64 + (N - tail_entry) / 32 + 2, 0);
     uint32_t finalB = serial_medium(a, N, tail_entry, ins.data(), (uint32_t)ins.size(), lp,
                                     [&](Sym s, uint32_t B) { syms.push_back(s); symB.push_back(B); });
-    // ---- blocks ----
-    HuffTables T;
-    init_tables(T);
-    uint32_t nsyms = (uint32_t)syms.size();
-    uint32_t nblocks = nsyms / kBlockSyms + 1;
-    std::vector<BlockDesc> blocks(nblocks);
-    TreeScratch scratch;
-    uint32_t in_pos = 0;
-    int data_type = 2;
-    for (uint32_t b = 0; b < nblocks; b++) {
-        BlockDesc &bd = blocks[b];
-        bd.sym_begin = b * kBlockSyms;
-        bd.sym_count = (b + 1 < nblocks) ? kBlockSyms : nsyms - bd.sym_begin;
-        bd.last = b + 1 == nblocks;
-        bd.in_start = in_pos;
-        uint32_t end = bd.last ? N : (syms[bd.sym_begin + bd.sym_count - 1].pos +
-                                      (syms[bd.sym_begin + bd.sym_count - 1].dist ? syms[bd.sym_begin + bd.sym_count - 1].lc + 3u : 1u));
-        bd.in_len = end - in_pos;
-        in_pos = end;
-        uint32_t Bflush = bd.last ? finalB : symB[bd.sym_begin + bd.sym_count - 1];
-        uint32_t lfreq[kLCodes] = {0}, dfreq[kDCodes] = {0};
-        for (uint32_t i = 0; i < bd.sym_count; i++) {
-            const Sym &s = syms[bd.sym_begin + i];
-            if (s.dist == 0) lfreq[s.lc]++;
-            else { lfreq[257 + T.length_code[s.lc]]++; dfreq[d_code(T, s.dist - 1u)]++; }
-        }
-        build_block(T, scratch, bd, lfreq, dfreq, bd.in_start >= Bflush, false);
-        if (data_type == 2 && bd.sym_count) data_type = (int)bd.data_type;
-    }
-    // ---- scan + pack ----
-    std::vector<uint8_t> out(2, 0);
-    uint32_t lf = level < 2 ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
-    uint32_t h = ((8 + (7 << 4)) << 8) | (lf << 6);
-    h += 31 - (h % 31);
-    out[0] = (uint8_t)(h >> 8); out[1] = (uint8_t)h;
-    uint64_t bit = 16;
-    for (uint32_t b = 0; b < nblocks; b++) {
-        BlockDesc &bd = blocks[b];
-        bd.bit_base = bit;
-        if (bd.type == 0) {
-            put_bits(out, bit, bd.hdr[0], 3);
-            uint64_t p = (bit + 3 + 7) & ~7ull;
-            uint16_t sl = (uint16_t)bd.in_len;
-            put_bits(out, p, sl, 16); put_bits(out, p + 16, (uint16_t)~sl, 16);
-            for (uint32_t i = 0; i < sl; i++) put_bits(out, p + 32 + 8ull * i, data[bd.in_start + i], 8);
-        } else {
-            for (uint32_t i = 0; i < bd.hdr_bits; i++) put_bits(out, bit + i, (bd.hdr[i >> 3] >> (i & 7)) & 1, 1);
-            uint64_t q = bit + bd.hdr_bits;
-            for (uint32_t i = 0; i < bd.sym_count; i++) {
-                const Sym &s = syms[bd.sym_begin + i];
-                uint64_t v; uint32_t n = sym_bits(T, bd, s.dist, s.lc, v);
-                put_bits(out, q, v, n); q += n;
-            }
-            put_bits(out, q, bd.lcode[kEndBlock], bd.llen[kEndBlock]); q += bd.llen[kEndBlock];
-            if (q != bit + bd.hdr_bits + bd.body_bits) return -7;
-        }
-        bit = block_end_bit(bd, bit);
-    }
-    uint64_t bytes = (bit + 7) >> 3;
-    out.resize(bytes, 0);
-    uint32_t ad = zo_adler32(1, data, N);
-    out.push_back((uint8_t)(ad >> 24)); out.push_back((uint8_t)(ad >> 16)); out.push_back((uint8_t)(ad >> 8)); out.push_back((uint8_t)ad);
-    if (out.size() > cap) return -5;
-    memcpy(dst, out.data(), out.size());
-    *out_len = (uint32_t)out.size();
+    uint32_t it_dummy = iters;
+    (void)it_dummy;
     *iters_out = iters;
-    *data_type_out = data_type;
-    return 0;
+    return encode_stream(data, N, level, syms, [&](uint32_t, const BlockDesc &bd) { return bd.last ? finalB : symB[bd.sym_begin + bd.sym_count - 1]; },
+                         false, false, kBlockSyms, dst, cap, out_len, data_type_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -406,4 +418,48 @@ extern "C" int hm_parse_slow(const uint8_t *data, uint32_t N, int level, SymOut 
     }
     *nsyms = n;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Levels 1 and 2 (zb_serial.h): the warp-serial restatement of deflate_quick / deflate_fast with scalar Ops.
+// ------------------------------------------------------------------------------------------
+#include "../../zlib_rs_b200/csrc/zb_serial.h"
+
+struct LowAcc {
+    const uint8_t *data; uint32_t N;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 65536) return 0; y -= 32768; }
+        return data[y];
+    }
+    uint32_t word(uint32_t y) const { return byte(y) | (byte(y + 1) << 8) | (byte(y + 2) << 16) | (byte(y + 3) << 24); }
+};
+
+static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
+{
+    std::vector<uint16_t> head(65536, 0), prev(32768, 0);
+    LowAcc a{data, N};
+    SerialLow<LowAcc, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms));
+    if (level == 1) return m.run_quick([&](Sym s) { syms.push_back(s); });
+    return m.run_fast([&](Sym s) { syms.push_back(s); }, [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; });
+}
+
+extern "C" int hm_parse_low(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    std::vector<Sym> syms;
+    std::vector<uint32_t> blockB;
+    run_low(data, N, level, kBlockSyms, syms, blockB);
+    for (size_t i = 0; i < syms.size() && i < cap; i++) out[i] = SymOut{syms[i].pos, syms[i].dist, syms[i].lc};
+    *nsyms = (uint32_t)syms.size();
+    return 0;
+}
+
+extern "C" int hm_deflate_low(const uint8_t *data, uint32_t N, int level, int fixed, int mem_level, uint8_t *dst, uint32_t cap,
+                              uint32_t *out_len, int *data_type_out)
+{
+    const uint32_t block_syms = (1u << (mem_level + 6)) - 1;
+    std::vector<Sym> syms;
+    std::vector<uint32_t> blockB;
+    const uint32_t finalB = run_low(data, N, level, block_syms, syms, blockB);
+    return encode_stream(data, N, level, syms, [&](uint32_t b, const BlockDesc &bd) { return (bd.last || b >= blockB.size()) ? finalB : blockB[b]; }, level == 1,
+                         fixed != 0, level == 1 ? kBlockSyms : block_syms, dst, cap, out_len, data_type_out);
 }

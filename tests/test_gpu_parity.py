@@ -1,5 +1,5 @@
 """GPU parity tests (run on the B200 box): every call goes through the C ABI of libz_b200.so and is
-compared with the CPU oracle on the same inputs -- bit-exact for the level 3..9 one-shot path."""
+compared with the CPU oracle on the same inputs -- bit-exact for the one-shot path at every level."""
 import hashlib
 import json
 import os
@@ -185,13 +185,86 @@ def test_slow_levels_full_block_of_literals(eng):
             assert out == O.compress(d, level)[1], (n, level)
 
 
+ALL_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["flush"] == 4]
+
+
+@pytest.mark.parametrize("v", ALL_KATS, ids=[v["name"] for v in ALL_KATS])
+def test_reference_golden_vectors_all_one_shot(v, eng):
+    """Every one-shot deflate vector of the reference's tests (any level / strategy / memLevel / wrapper).  Window sizes below
+    32 KiB are exact when the input never leaves the smaller window's match range (the engine says so in exact_parity)."""
+    d = bytes.fromhex(v["input_hex"])
+    out, res = eng.deflate(d, level=v["level"], strategy=v["strategy"], window_bits=v["window_bits"], mem_level=v["mem_level"])
+    wb = v["window_bits"] - 16 if v["window_bits"] > 15 else abs(v["window_bits"])
+    fits = len(d) + 262 <= (1 << max(wb, 9))
+    assert res.exact_parity == (1 if fits else 0)
+    if fits:
+        assert out == bytes.fromhex(v["expected_hex"])
+    else:  # hash_calc_difference, longest_match_difference: 512-byte windows that slide
+        assert zlib.decompress(out, v["window_bits"] if v["window_bits"] > 15 else 15) == d
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_low_levels_bit_exact(level, eng):
+    """deflate_quick / deflate_fast (zb_serial.h: the reference's serial parser on one warp): bytes equal the oracle's."""
+    rng = np.random.default_rng(level)
+    cases = [synthetic_mix(n, seed=n + level) for n in SMALL]
+    cases += [bytes(300000), b"a" * 100000, b"abc" * 50000, rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+              rng.integers(0, 256, 16383, dtype=np.uint8).tobytes(), rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+              (b"x" * 65274 + synthetic_mix(1000, 1)) * 3, bytes(65274) + b"\x01" + bytes(70000)]
+    cases += [silesia_member(k)[:300000] for k in (1, 2, 5, 7, 9)]
+    for d in cases:
+        out, res = eng.deflate(d, level=level)
+        assert res.exact_parity == 1
+        assert out == O.compress(d, level)[1], (level, len(d))
+    d = silesia_member(6)[:400000]
+    for strategy in (1, 4):  # Z_FILTERED changes nothing at these levels, Z_FIXED forces static blocks
+        out, res = eng.deflate(d, level=level, strategy=strategy)
+        assert out == O.compress(d, level, 15, 8, strategy)[1], strategy
+    for wbits in (-15, 31):
+        assert eng.deflate(d, level=level, window_bits=wbits)[0] == O.compress(d, level, wbits)[1]
+    assert Z.compress2(d, level) == O.compress(d, level)[1]  # the zlib C ABI takes the same path
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_low_levels_silesia_tar(level, eng):
+    d = silesia_tar()
+    out, res = eng.deflate(d, level=level)
+    assert res.exact_parity == 1 and out == O.compress(d, level)[1]
+    assert zlib.decompress(out) == d
+    # the parallel alternative: level-3 kernel set, valid stream, not the reference's bytes
+    out2, res2 = eng.deflate(d, level=level, flags=Z.ZB_FLAG_LOW_PARALLEL)
+    assert res2.exact_parity == 0 and zlib.decompress(out2) == d
+
+
+def test_mem_level_sets_the_block_size(eng):
+    """deflateInit2's memLevel: lit_bufsize = 1 << (memLevel + 6) symbols per block (deflate.rs:321, sym_buf.rs:23)."""
+    d = silesia_member(5)[:300000]
+    for mem in (1, 4, 7, 9):
+        for level, strategy in ((1, 0), (2, 0), (4, 0), (6, 0), (6, 1), (6, 2), (6, 3), (6, 4), (7, 0), (9, 0)):
+            out, res = eng.deflate(d, level=level, strategy=strategy, mem_level=mem)
+            assert res.exact_parity == 1
+            assert out == O.compress(d, level, 15, mem, strategy)[1], (mem, level, strategy)
+    z = Z.Deflate(6, mem_level=9)
+    assert z.deflate(d, Z.Z_FINISH) == O.compress(d, 6, 15, 9, 0)[1]
+
+
+def test_small_windows_that_fit_are_exact(eng):
+    for wb in (9, 10, 12, 14):
+        n = (1 << wb) - 262
+        d = silesia_member(9)[7000:7000 + n]
+        for level in (0, 1, 2, 6, 9):
+            out, res = eng.deflate(d, level=level, window_bits=wb)
+            assert res.exact_parity == 1 and out == O.compress(d, level, wb)[1], (wb, level)
+        out, res = eng.deflate(d + b"x", level=6, window_bits=wb)  # one byte more: 32 KiB engine, CINFO 7, still a valid stream
+        assert res.exact_parity == 0 and zlib.decompress(out) == d + b"x"
+
+
 def test_other_levels_and_strategies_valid_streams(eng):
     d = silesia_member(3)[:200000]
     for level in (0, 1, 2, 7, 8, 9):
         out, res = eng.deflate(d, level=level)
         assert zlib.decompress(out) == d
-        if level == 0:
-            assert out == O.compress(d, 0)[1]
+        assert out == O.compress(d, level)[1]
     for strategy in (1, 2, 3, 4):
         out, res = eng.deflate(d, level=6, strategy=strategy)
         assert zlib.decompress(out) == d

@@ -107,3 +107,28 @@ def test_inflate_scout_finds_exactly_the_dynamic_blocks():
         assert H().hm_inflate_scout(comp, len(comp), cands, 65536, ctypes.byref(nc)) == 0
         assert set(starts[: nd.value]) <= set(cands[: nc.value])
         assert nc.value - nd.value <= 2  # false candidates are possible in principle, they never reach the chain
+
+
+def _deflate_low(data, level, fixed=0, mem_level=8):
+    cap = len(data) + len(data) // 8 + 1024
+    buf = ctypes.create_string_buffer(cap)
+    n, dt = ctypes.c_uint32(0), ctypes.c_int(0)
+    rc = H().hm_deflate_low(data, len(data), level, fixed, mem_level, buf, cap, ctypes.byref(n), ctypes.byref(dt))
+    assert rc == 0, rc
+    return buf.raw[: n.value]
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_low_levels_serial_restatement(level):
+    """zb_serial.h (what k_serial_low runs on one warp) with scalar Ops: every symbol deflate_quick / deflate_fast emits,
+    and the final bytes (quick: one static block encoded in pieces; fast: a block per full sym_buf)."""
+    for name, data in CASES + [("dickens", silesia_member(3)[:400000]), ("mix1M", synthetic_mix(1 << 20, 21)),
+                               ("sao", silesia_member(8)[:300000]), ("slide", (b"x" * 65274 + synthetic_mix(1000, 1)) * 3)]:
+        o = _syms("hm_oracle_trace", data, level)
+        s = _syms("hm_parse_low", data, level)
+        assert len(o) == len(s) and (o == s).all(), name
+        assert _deflate_low(data, level) == O.compress(data, level)[1], name
+    d = silesia_member(5)[:300000]
+    for mem in (1, 4, 9):
+        assert _deflate_low(d, level, 0, mem) == O.compress(d, level, 15, mem, 0)[1]
+    assert _deflate_low(d, level, 1) == O.compress(d, level, 15, 8, 4)[1]  # Z_FIXED

@@ -23,6 +23,7 @@ Z_NO_FLUSH, Z_PARTIAL_FLUSH, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH, Z_BLOCK = 0, 
 Z_DEFAULT_STRATEGY, Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED = 0, 1, 2, 3, 4
 ZLIB_VERSION = b"1.3.0-zlib-rs-0.6.7-b200"
 ZB_FLAG_NOT_LAST = 1
+ZB_FLAG_LOW_PARALLEL = 2
 
 
 class ZStream(ctypes.Structure):
@@ -316,9 +317,11 @@ class Engine:
         return dst.raw[:n]
 
     def deflate(self, src, n=None, level=6, strategy=0, window_bits=15, flags=0, src_on_device=False, dst=None, dst_cap=0,
-                dst_on_device=False):
-        """Returns (bytes or None, DeflateResult). Host `src` may be bytes; device `src` is a pointer + n."""
+                dst_on_device=False, mem_level=8):
+        """Returns (bytes or None, DeflateResult). Host `src` may be bytes; device `src` is a pointer + n.
+        mem_level: deflateInit2's memLevel (symbols per block); flags: ZB_FLAG_*."""
         res = DeflateResult()
+        flags |= (mem_level & 15) << 8
         keep = None
         if not src_on_device:
             data, keep = _buf(src)

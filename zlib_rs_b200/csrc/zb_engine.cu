@@ -50,6 +50,7 @@ __global__ void k_slow(JobBufs);
 __global__ void k_rle(JobBufs);
 __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
+__global__ void k_serial_low(JobBufs);
 
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
@@ -57,6 +58,7 @@ constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
+constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2; // head + prev tables of one stream
 
 int Engine::init(int dev)
 {
@@ -81,6 +83,7 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
+    CK(cudaFuncSetAttribute(k_serial_low, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerialSmemBytes));
     CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_check, 16));
@@ -148,7 +151,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -161,6 +164,9 @@ size_t deflate_bound(size_t n)
 int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int level, int strategy,
                     int window_bits, uint32_t flags, zb_deflate_result *res)
 {
+    int mem_level = (int)((flags >> 8) & 15u);
+    if (mem_level == 0) mem_level = 8;
+    if (mem_level > 9) return ZB_E_PARAM;
     if (!res || (!src && n) || !dst) return ZB_E_PARAM;
     memset(res, 0, sizeof *res);
     if (n > 0xF0000000ull) { snprintf(g_err, sizeof g_err, "input too large for one job (%zu)", n); return ZB_E_PARAM; }
@@ -182,7 +188,13 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const size_t npad = (size_t)N + kPad;
     const uint32_t nwords = (N >> 5) + 2;
     const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
-    const uint32_t max_blocks = N / kBlockSyms + 2;
+    // levels 1 and 2 (deflate_quick / deflate_fast) run the reference's serial parser on one warp (zb_serial.h) unless the caller
+    // asks for the parallel level-3 kernel set (valid stream, better ratio, not byte-identical)
+    const bool low_parallel = (flags & ZB_FLAG_LOW_PARALLEL) != 0;
+    const bool serial_low = (level == 1 || level == 2) && strategy != 2 && strategy != 3 && !low_parallel;
+    // deflate_quick writes one static block: its pieces are an encoding detail, not sym_buf flushes
+    const uint32_t block_syms = (serial_low && level == 1) ? kBlockSyms : (1u << (mem_level + 6)) - 1u;
+    const uint32_t max_blocks = N / block_syms + 2;
     const size_t out_cap = (deflate_bound(n) + 15) & ~(size_t)15;
     if ((rc = stage((size_t)nmt + 64 + ((size_t)N / 512 + 2 + npt + nmt + 8) * 4 + 64)) != ZB_OK) return rc;
     uint8_t *h_dirty = static_cast<uint8_t *>(h_stage);
@@ -197,6 +209,8 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.N = N;
     jb.nmt = nmt;
     jb.tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    jb.block_syms = block_syms;
+    jb.serial_mode = serial_low ? (uint32_t)level : 0u;
     RES(S_L, npad * 2, L, uint16_t *)
     RES(S_SK, npad * 2, SK, uint16_t *)
     RES(S_HOLES, (size_t)nwords * 4, holes, uint32_t *)
@@ -228,7 +242,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.hdiff_words = nwords;
     RES(S_HCOARSE, (size_t)(N >> 10) + 16, hcoarse, uint8_t *)
     RES(S_BLOCKS, (size_t)max_blocks * sizeof(BlockDesc), blocks, BlockDesc *)
-    RES(S_SCRATCH, (size_t)max_blocks * sizeof(TreeScratch), scratch, TreeScratch *)
+    RES(S_BBASE, (size_t)max_blocks * 4, block_base, uint32_t *)
     uint32_t *d_freq;
     if ((rc = reserve(S_FREQ, (size_t)max_blocks * 320 * 4, &p)) != ZB_OK) return rc;
     d_freq = static_cast<uint32_t *>(p);
@@ -253,9 +267,14 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     jb.xfl = level == 9 ? 2 : (strategy >= 2 || level < 2) ? 4 : 0;
     // levels 3..9 and Z_RLE follow the reference parser exactly; levels 1 and 2 run the level-3 kernel set
     int eng_level = level;
-    bool exact = wb == 15;
+    // Only the 32 KiB window is implemented.  A smaller window changes nothing but the header's CINFO as long as the input never
+    // slides it and every distance fits: N <= w_size - MIN_LOOKAHEAD (deflate.rs:1423, 1787); windowBits 8 is 9 (deflate.rs:308-312).
+    const int wb_eff = wb == 8 ? 9 : wb;
+    const bool small_ok = wb_eff < 15 && (uint64_t)N + kMinLookahead <= (1ull << wb_eff);
+    bool exact = wb_eff == 15 || small_ok;
+    jb.cinfo = small_ok ? (uint32_t)(wb_eff - 8) : 7u;
     if (level != 0 && !jb.huffman_only) {
-        if (level < 3) { eng_level = 3; exact = strategy == 3; } // deflate_quick / deflate_fast: level-3 kernel set instead
+        if (level < 3 && !serial_low) { eng_level = 3; exact = strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
         if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level
         else if (level > 6) { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
     }
@@ -292,6 +311,12 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         if (jb.huffman_only) {
             k_literal_syms<<<N / 256 + 1, 256, 0, st>>>(jb);
             launches++;
+        } else if (jb.serial_mode) {
+            iters = 1;
+            pbegin();
+            k_serial_low<<<1, 32, jb.serial_mode == 2 ? kSerialSmemBytes : 65536u * 2u, st>>>(jb);
+            launches++;
+            pend(1, 1);
         } else {
             CK(cudaMemsetAsync(jb.holes, 0, (size_t)nwords * 4, st));
             CK(cudaMemsetAsync(jb.holes_new, 0, (size_t)nwords * 4, st));

@@ -271,7 +271,7 @@ struct BlockDesc {
     uint32_t hdr_bits;             // 3-bit block header + (dynamic) tree description
     uint32_t data_type;            // detect_data_type of this block's literals
     uint32_t have_window;          // block_start >= 0 in window coordinates at flush time
-    uint32_t pad0;
+    uint32_t no_eob;               // deflate_quick pieces: the end-of-block code belongs to the last piece only
     uint64_t body_bits;            // symbol bits + end-of-block code
     uint64_t bit_base;             // position of the block header in the output bit stream (set by the scan)
     uint16_t lcode[kLCodes];
@@ -302,6 +302,7 @@ ZB_HDN inline void build_block(const HuffTables &t, TreeScratch &s, BlockDesc &b
     int max_blindex = 0, lmax = 0, dmax = 0;
     TreeState st{0, 0};
     b.data_type = 2;
+    b.no_eob = 0;
     if (b.sym_count == 0) {
         opt_lenb = static_lenb = 0;
         st.static_len = 7;
@@ -351,6 +352,25 @@ ZB_HDN inline void build_block(const HuffTables &t, TreeScratch &s, BlockDesc &b
         for (int n = 0; n < kLCodes; n++) { b.lcode[n] = n <= lmax ? s.ltree[n].fc : 0; b.llen[n] = n <= lmax ? (uint8_t)s.ltree[n].dl : 0; }
         for (int n = 0; n < kDCodes; n++) { b.dcode[n] = n <= dmax ? s.dtree[n].fc : 0; b.dlen[n] = n <= dmax ? (uint8_t)s.dtree[n].dl : 0; }
     }
+}
+
+// deflate_quick (deflate/algorithm/quick.rs:12-169) writes ONE static block per deflate() call straight into the bit stream; the
+// engine encodes it in pieces of one sym_buf each: the 3-bit block header belongs to the first piece, the end-of-block code to the
+// last one.  data_type stays Z_UNKNOWN (zng_tr_flush_block never runs at level 1).
+ZB_HDN inline void build_quick_piece(const HuffTables &t, BlockDesc &b, const uint32_t *lfreq, const uint32_t *dfreq, bool first, bool last, bool final_block)
+{
+    uint64_t bits = 0;
+    for (int n = 0; n < 256; n++) bits += (uint64_t)lfreq[n] * t.sl_len[n];
+    for (int c = 0; c < 29; c++) bits += (uint64_t)lfreq[257 + c] * (t.sl_len[257 + c] + extra_lbits(c));
+    for (int c = 0; c < kDCodes; c++) bits += (uint64_t)dfreq[c] * (5 + extra_dbits(c));
+    b.type = 1;
+    b.data_type = 2;
+    b.no_eob = last ? 0 : 1;
+    b.hdr_bits = first ? 3 : 0;
+    b.hdr[0] = (uint8_t)(2 | (final_block ? 1 : 0)); // emit_tree(StaticTrees, last) of the one real block
+    b.body_bits = bits + (last ? t.sl_len[kEndBlock] : 0);
+    for (int n = 0; n < kLCodes; n++) { b.lcode[n] = t.sl_code[n]; b.llen[n] = t.sl_len[n]; }
+    for (int n = 0; n < kDCodes; n++) { b.dcode[n] = t.sd_code[n]; b.dlen[n] = 5; }
 }
 
 // Bits of one symbol under a block's codes (BitWriter::emit_lit / emit_dist, deflate.rs:1114-1148).

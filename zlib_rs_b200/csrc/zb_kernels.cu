@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(32) k_tail(JobBufs jb)
     });
     jb.info->n_syms = n_mid + k;
     jb.info->final_base = fb;
-    jb.info->n_blocks = (n_mid + k) / kBlockSyms + 1;
+    jb.info->n_blocks = (n_mid + k) / jb.block_syms + 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -841,8 +841,8 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
     for (uint32_t i = threadIdx.x; i < kLCodes; i += blockDim.x) lf[i] = 0;
     if (threadIdx.x < kDCodes) df[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t begin = b * kBlockSyms;
-    const uint32_t count = (b + 1 < nblocks) ? kBlockSyms : nsyms - begin;
+    const uint32_t begin = b * jb.block_syms;
+    const uint32_t count = (b + 1 < nblocks) ? jb.block_syms : nsyms - begin;
     for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
         const Sym s = jb.syms[begin + i];
         if (s.dist == 0) atomicAdd(&lf[s.lc], 1u);
@@ -868,7 +868,9 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
         if (last) Bf = jb.info->final_base;
         else {
             const uint32_t li = begin + count - 1, n_mid = jb.info->n_mid_syms;
-            if (jb.huffman_only) {
+            if (jb.serial_mode) {
+                Bf = jb.serial_mode == 2 ? jb.block_base[b] : 0; // recorded at the flush (deflate_quick has no stored decision)
+            } else if (jb.huffman_only) {
                 const uint32_t q = jb.syms[li].pos;
                 Bf = q < 2 * kWSize ? 0 : kWSize * (1 + (q - 2 * kWSize) / kWSize);
             } else if (jb.slow_mode == 2) {
@@ -893,7 +895,10 @@ __global__ void __launch_bounds__(32) k_build_blocks(JobBufs jb, const uint32_t 
     for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
         reinterpret_cast<uint32_t *>(&bd)[i] = reinterpret_cast<const uint32_t *>(&jb.blocks[b])[i];
     __syncwarp();
-    if (threadIdx.x == 0) build_block(c_tab, s, bd, fr, fr + kLCodes, bd.have_window != 0, jb.strategy_fixed != 0);
+    if (threadIdx.x == 0) {
+        if (jb.serial_mode == 1) build_quick_piece(c_tab, bd, fr, fr + kLCodes, b == 0, b + 1 == jb.info->n_blocks, jb.not_last == 0);
+        else build_block(c_tab, s, bd, fr, fr + kLCodes, bd.have_window != 0, jb.strategy_fixed != 0);
+    }
     __syncwarp();
     for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
         reinterpret_cast<uint32_t *>(&jb.blocks[b])[i] = reinterpret_cast<const uint32_t *>(&bd)[i];
@@ -922,7 +927,7 @@ __global__ void k_scan_blocks(JobBufs jb)
         // zlib header (deflate.rs:1572-1601)
         // level_flags (deflate.rs:1591-1601): strategy >= HuffmanOnly or level < 2 -> 0
         const uint32_t lf = (jb.huffman_only || jb.strategy_fixed || jb.level < 2) ? 0 : jb.level < 6 ? 1 : jb.level == 6 ? 2 : 3;
-        uint32_t h = ((8u + (7u << 4)) << 8) | (lf << 6);
+        uint32_t h = ((8u + (jb.cinfo << 4)) << 8) | (lf << 6);
         h += 31 - (h % 31);
         jb.out[0] = (uint8_t)(h >> 8);
         jb.out[1] = (uint8_t)h;
@@ -982,67 +987,73 @@ __global__ void __launch_bounds__(1024) k_encode(JobBufs jb)
         if (n < 32) v &= (1u << n) - 1u;
         or_bits(out32, bd.bit_base + wi * 32ull, v, n);
     }
-    // symbols: kSymsPerThread consecutive symbols per thread (the end-of-block code is symbol #sym_count)
-    const uint32_t first = tid * kSymsPerThread;
-    const uint32_t total = bd.sym_count + 1;
-    uint64_t vals[kSymsPerThread];
-    uint8_t lens[kSymsPerThread];
-    uint32_t mybits = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < kSymsPerThread; j++) {
-        const uint32_t i = first + j;
-        uint64_t v = 0;
-        uint32_t n = 0;
-        if (i < bd.sym_count) {
-            const Sym s = jb.syms[bd.sym_begin + i];
-            if (s.dist == 0) { v = s_lcode[s.lc]; n = s_llen[s.lc]; }
-            else {
-                uint32_t code = st.length_code[s.lc];
-                v = s_lcode[code + 257];
-                n = s_llen[code + 257];
-                uint32_t extra = extra_lbits(code);
-                if (extra) { v |= (uint64_t)(s.lc - st.base_length[code]) << n; n += extra; }
-                const uint32_t d = s.dist - 1u;
-                code = st.dist_code[d < 256 ? d : 256 + (d >> 7)];
-                uint64_t dv = s_dcode[code];
-                uint32_t dn = s_dlen[code];
-                extra = extra_dbits(code);
-                if (extra) { dv |= (uint64_t)(d - st.base_dist[code]) << dn; dn += extra; }
-                v |= dv << n;
-                n += dn;
-            }
-        } else if (i + 1 == total) { v = s_lcode[kEndBlock]; n = s_llen[kEndBlock]; }
-        vals[j] = v;
-        lens[j] = (uint8_t)n;
-        mybits += n;
-    }
-    // exclusive scan of mybits over the block
-    uint64_t incl = mybits;
+    // symbols: kSymsPerThread consecutive symbols per thread and round (the end-of-block code is symbol #sym_count); a block of
+    // memLevel 9 (32767 symbols) takes two rounds
+    const uint32_t total = bd.sym_count + (bd.no_eob ? 0u : 1u);
     const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint64_t round_bits = 0; // bits of the previous rounds
+    for (uint32_t rb = 0; rb == 0 || rb < total; rb += blockDim.x * kSymsPerThread) {
+        const uint32_t first = rb + tid * kSymsPerThread;
+        uint64_t vals[kSymsPerThread];
+        uint8_t lens[kSymsPerThread];
+        uint32_t mybits = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint64_t ws = warp_sum[lane];
+        for (uint32_t j = 0; j < kSymsPerThread; j++) {
+            const uint32_t i = first + j;
+            uint64_t v = 0;
+            uint32_t n = 0;
+            if (i < bd.sym_count) {
+                const Sym s = jb.syms[bd.sym_begin + i];
+                if (s.dist == 0) { v = s_lcode[s.lc]; n = s_llen[s.lc]; }
+                else {
+                    uint32_t code = st.length_code[s.lc];
+                    v = s_lcode[code + 257];
+                    n = s_llen[code + 257];
+                    uint32_t extra = extra_lbits(code);
+                    if (extra) { v |= (uint64_t)(s.lc - st.base_length[code]) << n; n += extra; }
+                    const uint32_t d = s.dist - 1u;
+                    code = st.dist_code[d < 256 ? d : 256 + (d >> 7)];
+                    uint64_t dv = s_dcode[code];
+                    uint32_t dn = s_dlen[code];
+                    extra = extra_dbits(code);
+                    if (extra) { dv |= (uint64_t)(d - st.base_dist[code]) << dn; dn += extra; }
+                    v |= dv << n;
+                    n += dn;
+                }
+            } else if (i + 1 == total && !bd.no_eob) { v = s_lcode[kEndBlock]; n = s_llen[kEndBlock]; }
+            vals[j] = v;
+            lens[j] = (uint8_t)n;
+            mybits += n;
+        }
+        // exclusive scan of mybits over the CTA
+        uint64_t incl = mybits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t t = __shfl_up_sync(0xffffffffu, ws, o);
-            if ((int)lane >= o) ws += t;
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
         }
-        warp_sum[lane] = ws;
-    }
-    __syncthreads();
-    uint64_t pos = bd.bit_base + bd.hdr_bits + (incl - mybits) + (warp ? warp_sum[warp - 1] : 0);
-    if (tid == blockDim.x - 1 && warp_sum[31] != bd.body_bits) atomicOr(&jb.info->error, 16u);
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t ws = warp_sum[lane];
 #pragma unroll
-    for (uint32_t j = 0; j < kSymsPerThread; j++) {
-        or_bits(out32, pos, vals[j], lens[j]);
-        pos += lens[j];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if ((int)lane >= o) ws += t;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        uint64_t pos = bd.bit_base + bd.hdr_bits + round_bits + (incl - mybits) + (warp ? warp_sum[warp - 1] : 0);
+#pragma unroll
+        for (uint32_t j = 0; j < kSymsPerThread; j++) {
+            or_bits(out32, pos, vals[j], lens[j]);
+            pos += lens[j];
+        }
+        round_bits += warp_sum[31];
+        __syncthreads(); // warp_sum is rewritten by the next round
     }
+    if (tid == blockDim.x - 1 && round_bits != bd.body_bits) atomicOr(&jb.info->error, 16u);
 }
 
 __global__ void k_finish(JobBufs jb, const uint32_t *check)
@@ -1071,7 +1082,7 @@ __global__ void __launch_bounds__(256) k_literal_syms(JobBufs jb)
     if (p == 0) {
         jb.info->n_mid_syms = jb.N;
         jb.info->n_syms = jb.N;
-        jb.info->n_blocks = jb.N / kBlockSyms + 1;
+        jb.info->n_blocks = jb.N / jb.block_syms + 1;
         // deflate_huff refills only when lookahead == 0: the base moves when strstart reaches 64 KiB + k*32 KiB
         jb.info->final_base = jb.N < 2 * kWSize ? 0 : kWSize * (1 + (jb.N - 2 * kWSize) / kWSize);
     }
@@ -1098,7 +1109,12 @@ __global__ void __launch_bounds__(256) k_stored(JobBufs jb)
             jb.info->total_bits = 8ull * (jb.hdr_len + (uint64_t)N + 5ull * nb);
             jb.info->out_bytes = jb.hdr_len + (uint64_t)N + 5ull * nb + (jb.wrap == 1 ? 4 : jb.wrap == 2 ? 8 : 0);
             jb.info->data_type = 2;
-            if (jb.wrap == 1) { jb.out[0] = 0x78; jb.out[1] = 0x01; }
+            if (jb.wrap == 1) {
+                uint32_t h = (8u + (jb.cinfo << 4)) << 8; // level_flags 0 (deflate.rs:1572-1601)
+                h += 31 - (h % 31);
+                jb.out[0] = (uint8_t)(h >> 8);
+                jb.out[1] = (uint8_t)h;
+            }
             else if (jb.wrap == 2) {
                 const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, 4, 3};
                 for (int i = 0; i < 10; i++) jb.out[i] = g[i];

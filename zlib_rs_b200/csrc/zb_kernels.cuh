@@ -90,6 +90,10 @@ struct JobBufs {
     uint32_t *bucket_map;     // 65536 bits: hash buckets in which a hole changed in the last iteration
     uint32_t use_bucket_map;  // k_match recomputes only positions of those buckets (later iterations)
     uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
+    uint32_t block_syms;      // symbols per deflate block: lit_bufsize - 1 = (1 << (memLevel + 6)) - 1 (deflate.rs:321, sym_buf.rs:23)
+    uint32_t serial_mode;     // 1: deflate_quick (level 1), 2: deflate_fast (level 2) -- k_serial_low, zb_serial.h
+    uint32_t *block_base;     // serial levels: window base in force when block b was flushed
+    uint32_t cinfo;           // zlib header CINFO = windowBits - 8 (7 unless the whole input fits a smaller window's match range)
 };
 
 cudaError_t upload_tables();

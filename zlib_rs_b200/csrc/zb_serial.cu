@@ -1,0 +1,88 @@
+// zb_serial.cu -- levels 1 and 2 on the GPU: one warp runs the reference's serial parser (zb_serial.h) with the
+// head/prev tables of the stream in shared memory (128 KiB + 64 KiB).  All 32 lanes execute the loop in lockstep
+// on identical state (loads broadcast, identical stores coalesce); the lanes split only the wide operations:
+// compare256 (32 bytes per step, ballot for the first mismatch) and slide_hash (SIMD saturating subtract).
+#include "zb_kernels.cuh"
+#include "zb_serial.h"
+
+namespace zb {
+
+struct DevLowAcc {
+    const uint8_t *in; // zero padded behind N (kPad)
+    uint32_t N;
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const
+    {
+        // bytes behind the input are what the reference's window buffer still holds there (cf. GAcc)
+        while (y >= N) {
+            if (y < 2 * kWSize) return 0;
+            y -= kWSize;
+        }
+        return in[y];
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t y) const
+    {
+        if (y + 4 <= N) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(in + y);
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            return __funnelshift_r(q[0], q[1], (uint32_t)(a & 3u) * 8u);
+        }
+        return byte(y) | (byte(y + 1) << 8) | (byte(y + 2) << 16) | (byte(y + 3) << 24);
+    }
+};
+
+struct WarpOps {
+    static __device__ __forceinline__ void slide(uint16_t *t, uint32_t n)
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(t);
+        const uint32_t lane = threadIdx.x & 31;
+        __syncwarp();
+        for (uint32_t i = lane; i < n / 2; i += 32) w[i] = __vsubus2(w[i], 0x80008000u); // per-halfword saturating - 32768
+        __syncwarp();
+    }
+    template <class D>
+    static __device__ __forceinline__ uint32_t compare256(const D &d, uint32_t a, uint32_t b)
+    {
+        const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
+        for (uint32_t k = 0; k < 256; k += 32) {
+            const uint32_t m = __ballot_sync(0xffffffffu, d.byte(a + k + lane) != d.byte(b + k + lane));
+            if (m) return k + (uint32_t)__ffs(m) - 1u;
+        }
+        return 256;
+    }
+};
+
+// One CTA of one warp per stream.  Writes the symbols, the per-block window bases and the job totals.
+__global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *head = reinterpret_cast<uint16_t *>(smem);
+    uint16_t *prev = jb.serial_mode == 2 ? reinterpret_cast<uint16_t *>(smem + 65536 * 2) : nullptr;
+    const uint32_t lane = threadIdx.x;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        const uint32_t n16 = (jb.serial_mode == 2 ? (65536u + kWSize) * 2u : 65536u * 2u) / 16u;
+        for (uint32_t i = lane; i < n16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    DevLowAcc a{jb.in, jb.N};
+    SerialLow<DevLowAcc, WarpOps> m(a, head, prev, jb.N, serial_low_params((int)jb.serial_mode, jb.block_syms));
+    Sym *syms = jb.syms;
+    uint32_t n = 0, fb;
+    if (jb.serial_mode == 1) {
+        fb = m.run_quick([&](const Sym &s) { if (lane == 0) syms[n] = s; n++; });
+    } else {
+        uint32_t *bb = jb.block_base;
+        fb = m.run_fast([&](const Sym &s) { if (lane == 0) syms[n] = s; n++; },
+                        [&](uint32_t b, uint32_t B) { if (lane == 0) bb[b] = B; });
+    }
+    if (lane == 0) {
+        jb.info->n_mid_syms = 0;
+        jb.info->n_syms = n;
+        jb.info->final_base = fb;
+        // deflate_quick's single block is encoded in pieces of kBlockSyms symbols; deflate_fast flushes a block per full sym_buf
+        jb.info->n_blocks = n / jb.block_syms + 1;
+    }
+}
+
+} // namespace zb

@@ -319,10 +319,10 @@ __global__ void k_tail_slow(JobBufs jb)
     if (jb.N > 0) n += emit_step(jb, jb.info->tail_entry, jb.syms + n);
     jb.info->n_syms = n;
     jb.info->final_base = base_at(jb.N, jb.N);
-    uint32_t nb = n / kBlockSyms + 1;
+    uint32_t nb = n / jb.block_syms + 1;
     // deflate_slow tallies a pending last literal after its loop and ignores that the symbol buffer may just have filled up
     // (slow.rs:150-153): the full block then IS the last block instead of being followed by an empty one
-    if (jb.slow_mode == 1 && n > 0 && n % kBlockSyms == 0) {
+    if (jb.slow_mode == 1 && n > 0 && n % jb.block_syms == 0) {
         const Sym last = jb.syms[n - 1];
         if (last.dist == 0 && last.pos + 1 == jb.N) nb--;
     }

@@ -230,10 +230,10 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     const size_t cap = zb_deflate_bound(n) + 64;
     int rc;
     if (final && !d->any_segment) {
-        // the one-shot path: byte-identical to compress2 for levels 3..6
+        // the one-shot path: byte-identical to the reference's deflate(Z_FINISH) at every level, strategy and memLevel (32 KiB window)
         d->out.resize(base + cap);
-        rc = zb_deflate(e, d->in.data(), n, 0, d->out.data() + base, cap, 0, d->level, d->strategy,
-                        d->wrap == 0 ? -15 : d->wrap == 2 ? 31 : 15, &r);
+        rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + base, cap, 0, d->level, d->strategy,
+                           d->wrap == 0 ? -15 : d->wrap == 2 ? 31 : 15, ZB_FLAG_MEMLEVEL(d->mem_level), &r);
         if (rc != ZB_OK) { d->out.resize(base); strm->msg = zb_last_error(); return map_rc(rc); }
         d->out.resize(base + r.out_bytes);
         strm->adler = r.check;
@@ -258,7 +258,8 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     const size_t b2 = d->out.size();
     d->out.resize(b2 + cap);
     const int lvl = d->level == 0 ? 1 : d->level; // stored segments need level > 0 framing
-    rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + b2, cap, 0, lvl, d->strategy, -15, final ? 0 : ZB_FLAG_NOT_LAST, &r);
+    rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + b2, cap, 0, lvl, d->strategy, -15,
+                       (final ? 0 : ZB_FLAG_NOT_LAST) | ZB_FLAG_MEMLEVEL(d->mem_level), &r);
     if (rc != ZB_OK) { d->out.resize(b2); strm->msg = zb_last_error(); return map_rc(rc); }
     d->out.resize(b2 + r.out_bytes);
     // running check value over all consumed input (segment checks chained with the combine algebra)
