@@ -277,6 +277,19 @@ def main():
             out9 = bytes(out_t[: int(r9.out_bytes)].cpu().numpy().tobytes())
             other["deflate_level9_silesia_small_tar"] = {"ms": r9.gpu_ms, "GiBps": N / (r9.gpu_ms * 1e-3) / GIB, "out_bytes": int(r9.out_bytes),
                                                          "equals_reference_file": out9 == gz, "exact_parity": int(r9.exact_parity)}
+            for lv in (1, 2):  # deflate_quick / deflate_fast: the reference's serial parser on one warp (exact, latency-bound)
+                olv, rlv = eng.deflate(ins[lv].data_ptr(), n=N, level=lv, src_on_device=True, dst=out_t.data_ptr(), dst_cap=cap, dst_on_device=True)
+                other["deflate_level%d_silesia_small_tar" % lv] = {"ms": rlv.gpu_ms, "GiBps": N / (rlv.gpu_ms * 1e-3) / GIB, "out_bytes": int(rlv.out_bytes),
+                                                                   "exact_parity": int(rlv.exact_parity), "note": "one warp per stream (zb_serial.h)"}
+            try:
+                from corpus import calgary_mix
+                cm = calgary_mix()
+                ocm, rcm = eng.deflate(cm, level=9)
+                ocm, rcm = eng.deflate(cm, level=9)
+                other["deflate_level9_calgary_mix_64MiB"] = {"ms": rcm.gpu_ms, "GiBps": len(cm) / (rcm.gpu_ms * 1e-3) / GIB, "out_bytes": int(rcm.out_bytes),
+                                                            "exact_parity": int(rcm.exact_parity), "note": "config 4 as one stream; host buffers, copies inside the timed region"}
+            except Exception as ex:
+                other["calgary_mix_error"] = repr(ex)
             # several independent streams in flight on one GPU (one Engine = one CUDA stream + its own buffers per host thread):
             # the single-stream pipeline leaves most SMs idle in its latency-bound phases
             try:

@@ -68,3 +68,41 @@ def synthetic_mix(n, seed=1):
         parts.append(w)
         total += len(w)
     return b"".join(parts)[:n]
+
+
+CALGARY_MIX_BYTES = 64 << 20
+CALGARY_MIX_SHA256 = "bfe943ead7312a5efa1338c4b72734ecd5a29c7a65b648837205315bc3063096"
+
+
+def calgary_mix(n=CALGARY_MIX_BYTES):
+    """BASELINE config 4's "64 MiB synthetic Calgary-mix" (SURVEY.md 8d item 4).  The Calgary corpus is not available offline, so the
+    buffer is defined from the committed corpus: 64 KiB slices drawn round-robin from the 12 Silesia members at xorshift64*-chosen
+    offsets (seed 0x9E3779B97F4A7C15), every 16th slice replaced by seeded random bytes and every 32nd by zeros."""
+    key = ("calgary", n)
+    if key in _cache:
+        return _cache[key]
+    SL = 65536
+    x = 0x9E3779B97F4A7C15
+    mask = (1 << 64) - 1
+    members = [silesia_member(k) for k in range(12)]
+    parts = []
+    i = 0
+    while i * SL < n:
+        x ^= x >> 12
+        x ^= (x << 25) & mask
+        x ^= x >> 27
+        r = (x * 0x2545F4914F6CDD1D) & mask
+        if i % 32 == 31:
+            parts.append(bytes(SL))
+        elif i % 16 == 15:
+            parts.append(xorshift_bytes(SL, seed=r))
+        else:
+            m = members[i % 12]
+            off = r % (len(m) - SL)
+            parts.append(m[off: off + SL])
+        i += 1
+    out = b"".join(parts)[:n]
+    if n == CALGARY_MIX_BYTES:
+        assert hashlib.sha256(out).hexdigest() == CALGARY_MIX_SHA256
+    _cache[key] = out
+    return out

@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as O
 import zlib_rs_b200 as Z
-from corpus import silesia_gz, silesia_member, silesia_tar, synthetic_mix
+from corpus import calgary_mix, silesia_gz, silesia_member, silesia_tar, synthetic_mix
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -272,6 +272,25 @@ def test_other_levels_and_strategies_valid_streams(eng):
     for wb in (-15, 31):
         out, res = eng.deflate(d, level=6, window_bits=wb)
         assert out == O.compress(d, 6, wb)[1]
+
+
+def test_config4_calgary_mix_level9_whole_and_chunk_sharded(eng):
+    """BASELINE config 4: deflate level 9 of the 64 MiB Calgary-mix buffer -- as one stream (bytes equal the oracle's) and
+    chunk-sharded the way 8 ranks split it (zlib_rs_b200/shard.py: raw segments closed by the sync marker, adler32 combined)."""
+    from zlib_rs_b200 import shard
+    d = calgary_mix()
+    out, res = eng.deflate(d, level=9)
+    assert res.exact_parity == 1 and out == O.compress(d, 9)[1]
+    segs, ads, lens = [], [], []
+    for r, (lo, hi) in enumerate(shard.plan_shards(len(d), 8)):
+        last = r == 7
+        seg, sres = eng.deflate(d[lo:hi], level=9, window_bits=-15, flags=0 if last else Z.ZB_FLAG_NOT_LAST)
+        assert last or seg.endswith(b"\x00\x00\xff\xff")
+        segs.append(seg); ads.append(Z.adler32(d[lo:hi])); lens.append(hi - lo)
+    stream = shard.stitch_zlib(segs, ads, lens, level=9)
+    assert zlib.decompress(stream) == d
+    rc, got, ires = eng.inflate(stream, len(d))  # the GPU inflater reads the stitched stream too
+    assert rc == 0 and got == d
 
 
 def test_streaming_deflate_zpipe_shape():

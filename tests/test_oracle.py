@@ -233,3 +233,13 @@ def test_inflate_chunked_all_sizes():
             continue
         rc, out, _, adler = O.inflate_stream(comp, 15, in_chunk=ic, out_chunk=oc)
         assert rc == 1 and out == data and adler == zlib.adler32(data)
+
+
+def test_calgary_mix_generator_is_pinned():
+    """BASELINE config 4's buffer (tests/corpus.py::calgary_mix): generator pinned by SHA-256; oracle level-9 round trip."""
+    import zlib
+    from corpus import CALGARY_MIX_BYTES, calgary_mix
+    d = calgary_mix()
+    assert len(d) == CALGARY_MIX_BYTES  # the hash is asserted inside the generator
+    rc, out = O.compress(d[: 8 << 20], 9)
+    assert rc == 0 and zlib.decompress(out) == d[: 8 << 20]

@@ -58,6 +58,7 @@ constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
+constexpr uint32_t kTailSmemBytes = 36864 * 3 + 36864 / 8 + 64; // k_tail: data, links, hole bits of the last 36 KiB
 constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2; // head + prev tables of one stream
 
 int Engine::init(int dev)
@@ -83,6 +84,7 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
+    CK(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
     CK(cudaFuncSetAttribute(k_serial_low, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerialSmemBytes));
     CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_info, sizeof(JobInfo)));
@@ -463,7 +465,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 pend(4, 1);
             }
             pbegin();
-            k_tail<<<1, 32, 0, st>>>(jb);
+            k_tail<<<1, 1024, kTailSmemBytes, st>>>(jb);
             launches++;
             pend(5, 1);
             }
@@ -476,7 +478,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         pbegin();
         k_block_hist<<<nblocks, 256, 0, st>>>(jb, d_freq);
         k_build_blocks<<<nblocks, 32, 0, st>>>(jb, d_freq);
-        k_scan_blocks<<<1, 32, 0, st>>>(jb);
+        k_scan_blocks<<<1, 256, 0, st>>>(jb);
         pend(6, 3);
         pbegin();
         k_encode<<<nblocks, 1024, 0, st>>>(jb);

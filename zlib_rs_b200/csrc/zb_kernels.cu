@@ -807,11 +807,44 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
 // ------------------------------------------------------------------------------------------------
 // k_tail: exact serial simulation from the tail entry to the end of the stream (one thread).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_tail(JobBufs jb)
+constexpr uint32_t kTailSpan = 36864; // bytes before the end of the input staged for the serial tail (window + tail zone)
+struct TAcc { // k_tail: the end of the stream from shared memory, anything older from global memory
+    const uint8_t *sdata;
+    const uint16_t *sL;
+    const uint32_t *sh;
+    uint32_t lo; // absolute position of the first staged byte (multiple of 32)
+    GAcc g;
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const
+    {
+        while (y >= g.N) {
+            if (y < 2 * kWSize) return 0;
+            y -= kWSize;
+        }
+        return y >= lo ? sdata[y - lo] : g.data[y];
+    }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { return y + 4 <= g.N ? (y >= lo ? sL[y - lo] : g.L[y]) : 0; }
+    __device__ __forceinline__ bool inserted(uint32_t y) const
+    {
+        if (y < lo) return g.inserted(y);
+        const uint32_t i = y - lo;
+        return !((sh[i >> 5] >> (i & 31)) & 1u);
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_tail(JobBufs jb)
 {
+    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t ins[1024];
+    uint8_t *sdata = smem;
+    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kTailSpan);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kTailSpan * 3);
+    const uint32_t N = jb.N;
+    const uint32_t lo = N > kTailSpan ? (N - kTailSpan + 31u) & ~31u : 0u;
+    for (uint32_t i = threadIdx.x; i < N - lo; i += blockDim.x) { sdata[i] = jb.in[lo + i]; sL[i] = jb.L[lo + i]; }
+    for (uint32_t i = threadIdx.x; i < (N - lo + 31) / 32; i += blockDim.x) sh[i] = jb.holes[(lo >> 5) + i];
+    __syncthreads();
     if (threadIdx.x != 0) return;
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    TAcc a{sdata, sL, sh, lo, GAcc{jb.in, jb.N, jb.L, jb.holes, jb.M}};
     const uint32_t p0 = jb.info->tail_entry;
     const uint32_t n_mid = jb.info->n_mid_syms;
     uint32_t k = 0;
@@ -904,15 +937,38 @@ __global__ void __launch_bounds__(32) k_build_blocks(JobBufs jb, const uint32_t 
         reinterpret_cast<uint32_t *>(&jb.blocks[b])[i] = reinterpret_cast<const uint32_t *>(&bd)[i];
 }
 
-__global__ void k_scan_blocks(JobBufs jb)
+// Bit position of every block: a serial scan (stored blocks align to a byte), fed from shared memory so that the one scanning
+// thread never waits for global memory.
+constexpr uint32_t kScanChunk = 1024;
+__global__ void __launch_bounds__(256) k_scan_blocks(JobBufs jb)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ uint64_t s_bits[kScanChunk]; // header + body bits, or for stored blocks 1 << 63 | stored length
+    __shared__ uint64_t s_base[kScanChunk];
+    __shared__ uint64_t s_bit;
     const uint32_t nb = jb.info->n_blocks;
-    uint64_t bit = 8ull * jb.hdr_len;
-    for (uint32_t b = 0; b < nb; b++) {
-        jb.blocks[b].bit_base = bit;
-        bit = block_end_bit(jb.blocks[b], bit);
+    if (threadIdx.x == 0) s_bit = 8ull * jb.hdr_len;
+    for (uint32_t c0 = 0; c0 < nb; c0 += kScanChunk) {
+        const uint32_t nc = min(kScanChunk, nb - c0);
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+            const BlockDesc &bd = jb.blocks[c0 + i];
+            s_bits[i] = bd.type == 0 ? (1ull << 63) | (uint16_t)bd.in_len : (uint64_t)bd.hdr_bits + bd.body_bits;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t bit = s_bit;
+            for (uint32_t i = 0; i < nc; i++) {
+                s_base[i] = bit;
+                const uint64_t v = s_bits[i];
+                bit = (v >> 63) ? ((bit + 3 + 7) & ~7ull) + 32 + 8ull * (v & 0xffffu) : bit + v; // block_end_bit()
+            }
+            s_bit = bit;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) jb.blocks[c0 + i].bit_base = s_base[i];
+        __syncthreads();
     }
+    if (threadIdx.x != 0) return;
+    uint64_t bit = s_bit;
     if (jb.not_last) { // Z_SYNC_FLUSH framing: empty stored block, byte aligned (deflate.rs:2733-2738)
         const uint64_t p = (bit + 3 + 7) & ~7ull;
         jb.info->marker_byte = p >> 3;
