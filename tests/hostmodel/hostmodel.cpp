@@ -439,7 +439,12 @@ static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t blo
     std::vector<uint16_t> head(65536, 0), prev(32768, 0);
     LowAcc a{data, N};
     SerialLow<LowAcc, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms));
-    if (level == 1) return m.run_quick([&](Sym s) { syms.push_back(s); });
+    if (level == 1) {
+        uint32_t n = 0;
+        const uint32_t fb = m.run_quick<HostWarp>([&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; }, n);
+        syms.resize(n);
+        return fb;
+    }
     return m.run_fast([&](Sym s) { syms.push_back(s); }, [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; });
 }
 

@@ -58,7 +58,6 @@ constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
-constexpr uint32_t kTailSmemBytes = 36864 * 3 + 36864 / 8 + 64; // k_tail: data, links, hole bits of the last 36 KiB
 constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2; // head + prev tables of one stream
 
 int Engine::init(int dev)
@@ -84,7 +83,6 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
-    CK(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
     CK(cudaFuncSetAttribute(k_serial_low, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerialSmemBytes));
     CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_info, sizeof(JobInfo)));
@@ -158,9 +156,10 @@ static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
 {
-    // stored blocks are the worst case for every path of the engine (deflate.rs:3193-3307 gives the
-    // reference's tighter figure for its own block splitting; ours never exceeds stored + framing)
-    return n + (n / 16383 + 2) * 8 + (n >> 10) + 64;
+    // The conservative bound of the reference (deflate.rs:3193-3205: n + (n+7)/8 + (n+63)/64 + 5 + wrapper): deflate_quick has no
+    // stored fallback and codes a literal in up to 9 bits (deflate_quick_overhead, :3169-3176); every other path of the engine
+    // stays below stored + framing, which this covers for every memLevel.
+    return n + ((n + 7) >> 3) + ((n + 63) >> 6) + 5 + 18 + 64;
 }
 
 int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int level, int strategy,
@@ -465,7 +464,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 pend(4, 1);
             }
             pbegin();
-            k_tail<<<1, 1024, kTailSmemBytes, st>>>(jb);
+            k_tail<<<1, 32, 0, st>>>(jb);
             launches++;
             pend(5, 1);
             }

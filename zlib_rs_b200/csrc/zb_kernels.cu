@@ -807,44 +807,13 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
 // ------------------------------------------------------------------------------------------------
 // k_tail: exact serial simulation from the tail entry to the end of the stream (one thread).
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kTailSpan = 36864; // bytes before the end of the input staged for the serial tail (window + tail zone)
-struct TAcc { // k_tail: the end of the stream from shared memory, anything older from global memory
-    const uint8_t *sdata;
-    const uint16_t *sL;
-    const uint32_t *sh;
-    uint32_t lo; // absolute position of the first staged byte (multiple of 32)
-    GAcc g;
-    __device__ __forceinline__ uint32_t byte(uint32_t y) const
-    {
-        while (y >= g.N) {
-            if (y < 2 * kWSize) return 0;
-            y -= kWSize;
-        }
-        return y >= lo ? sdata[y - lo] : g.data[y];
-    }
-    __device__ __forceinline__ uint32_t link(uint32_t y) const { return y + 4 <= g.N ? (y >= lo ? sL[y - lo] : g.L[y]) : 0; }
-    __device__ __forceinline__ bool inserted(uint32_t y) const
-    {
-        if (y < lo) return g.inserted(y);
-        const uint32_t i = y - lo;
-        return !((sh[i >> 5] >> (i & 31)) & 1u);
-    }
-};
-
-__global__ void __launch_bounds__(1024) k_tail(JobBufs jb)
+// One thread: the loop is a chain of dependent instructions, so it runs at the issue latency of a single thread whatever memory
+// it reads (staging the window in shared memory was measured slower: more address arithmetic on the same chain).
+__global__ void __launch_bounds__(32) k_tail(JobBufs jb)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t ins[1024];
-    uint8_t *sdata = smem;
-    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kTailSpan);
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kTailSpan * 3);
-    const uint32_t N = jb.N;
-    const uint32_t lo = N > kTailSpan ? (N - kTailSpan + 31u) & ~31u : 0u;
-    for (uint32_t i = threadIdx.x; i < N - lo; i += blockDim.x) { sdata[i] = jb.in[lo + i]; sL[i] = jb.L[lo + i]; }
-    for (uint32_t i = threadIdx.x; i < (N - lo + 31) / 32; i += blockDim.x) sh[i] = jb.holes[(lo >> 5) + i];
-    __syncthreads();
     if (threadIdx.x != 0) return;
-    TAcc a{sdata, sL, sh, lo, GAcc{jb.in, jb.N, jb.L, jb.holes, jb.M}};
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     const uint32_t p0 = jb.info->tail_entry;
     const uint32_t n_mid = jb.info->n_mid_syms;
     uint32_t k = 0;

@@ -52,6 +52,21 @@ struct WarpOps {
     }
 };
 
+struct DevWarp { // the lane-parallel policy of zb_serial.h on a real warp
+    static constexpr uint32_t kSlots = 1;
+    static __device__ __forceinline__ uint32_t first() { return threadIdx.x & 31u; }
+    static __device__ __forceinline__ uint32_t end() { return (threadIdx.x & 31u) + 1u; }
+    static __device__ __forceinline__ uint32_t slot(uint32_t) { return 0; }
+    static __device__ __forceinline__ bool leader() { return (threadIdx.x & 31u) == 0; }
+    static __device__ __forceinline__ uint32_t ballot(const LaneVar<DevWarp, uint32_t> &p) { return __ballot_sync(0xffffffffu, p.v[0] != 0); }
+    static __device__ __forceinline__ void match_any(const LaneVar<DevWarp, uint32_t> &key, LaneVar<DevWarp, uint32_t> &out)
+    {
+        out.v[0] = __match_any_sync(0xffffffffu, key.v[0]);
+    }
+    static __device__ __forceinline__ uint32_t bcast(const LaneVar<DevWarp, uint32_t> &x, uint32_t src) { return __shfl_sync(0xffffffffu, x.v[0], src); }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
 // One CTA of one warp per stream.  Writes the symbols, the per-block window bases and the job totals.
 __global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
 {
@@ -70,7 +85,7 @@ __global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
     Sym *syms = jb.syms;
     uint32_t n = 0, fb;
     if (jb.serial_mode == 1) {
-        fb = m.run_quick([&](const Sym &s) { if (lane == 0) syms[n] = s; n++; });
+        fb = m.run_quick<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, n);
     } else {
         uint32_t *bb = jb.block_base;
         fb = m.run_fast([&](const Sym &s) { if (lane == 0) syms[n] = s; n++; },

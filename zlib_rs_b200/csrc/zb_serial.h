@@ -44,6 +44,66 @@ struct ScalarOps {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Lane-parallel code that is shared by the device (32 real lanes, one slot per variable) and the host model (a loop
+// over 32 lanes, 32 slots per variable).  W supplies: kSlots, first()/end() of the lane loop, slot(l), leader(),
+// ballot, match_any, bcast, sync.  Uniform values (the same in every lane) are plain variables.
+// ---------------------------------------------------------------------------------------------
+#define ZB_FOR_LANES(W_, l) for (uint32_t l = W_::first(), zb_e_ = W_::end(); l < zb_e_; l++)
+template <class W, class T>
+struct LaneVar {
+    T v[W::kSlots];
+    ZB_HD T &operator[](uint32_t l) { return v[W::slot(l)]; }
+    ZB_HD const T &operator[](uint32_t l) const { return v[W::slot(l)]; }
+};
+struct HostWarp { // scalar emulation
+    static constexpr uint32_t kSlots = 32;
+    static ZB_HD uint32_t first() { return 0; }
+    static ZB_HD uint32_t end() { return 32; }
+    static ZB_HD uint32_t slot(uint32_t l) { return l; }
+    static ZB_HD bool leader() { return true; }
+    static ZB_HD uint32_t ballot(const LaneVar<HostWarp, uint32_t> &p)
+    {
+        uint32_t m = 0;
+        for (uint32_t l = 0; l < 32; l++) m |= (p.v[l] ? 1u : 0u) << l;
+        return m;
+    }
+    static ZB_HD void match_any(const LaneVar<HostWarp, uint32_t> &key, LaneVar<HostWarp, uint32_t> &out)
+    {
+        for (uint32_t l = 0; l < 32; l++) {
+            uint32_t m = 0;
+            for (uint32_t k = 0; k < 32; k++) m |= (key.v[k] == key.v[l] ? 1u : 0u) << k;
+            out.v[l] = m;
+        }
+    }
+    static ZB_HD uint32_t bcast(const LaneVar<HostWarp, uint32_t> &x, uint32_t src) { return x.v[src]; }
+    static ZB_HD void sync() {}
+};
+ZB_HD uint32_t bit_range(uint32_t a, uint32_t b) // bits a .. b-1, 0 <= a <= b <= 32
+{
+    const uint32_t hi = b >= 32 ? 0xffffffffu : (1u << b) - 1u;
+    const uint32_t lo = a >= 32 ? 0xffffffffu : (1u << a) - 1u;
+    return hi & ~lo;
+}
+ZB_HD uint32_t top_bit(uint32_t m) // index of the highest set bit, m != 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)m);
+#endif
+    uint32_t i = 31;
+    while (!((m >> i) & 1u)) i--;
+    return i;
+}
+ZB_HD uint32_t low_bit(uint32_t m) // index of the lowest set bit, m != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)m) - 1u;
+#endif
+    uint32_t i = 0;
+    while (!((m >> i) & 1u)) i++;
+    return i;
+}
+
 // D: byte(y) (stale-window semantics behind the input, see GAcc), word(y) = little-endian 32 bits at y.
 // OPS: slide / compare256.  EMIT(Sym).  FLUSH(block_index, B): a full sym_buf was flushed (deflate_fast only).
 template <class D, class OPS>
@@ -153,10 +213,65 @@ struct SerialLow {
         return n;
     }
 
-    // deflate_quick (quick.rs:12-169), one call with Z_FINISH and ample output: one static block.
-    template <class E>
-    ZB_HD uint32_t run_quick(E &&emit)
+    // 32 loop-tops of deflate_quick at once.  Every lane takes one position and assumes that all positions before it in the step
+    // are loop-tops (literals); the first lane whose table candidate matches ends the run of literals with its match, and the
+    // lanes behind the match resume as loop-tops of a further round.  "The table" for a lane is the stored head plus the lanes of
+    // this step that are loop-tops so far (same-hash lanes found with match_any), so the stored table is written once, at the
+    // end.  Requires that no position of the step can trigger fill_window (lookahead >= MIN_LOOKAHEAD + 32).
+    template <class W, class EA>
+    ZB_HD bool quick_wide_step(EA &&emit_at, uint32_t &nsym)
     {
+        if (F - p < kMinLookahead + 32u) return false;
+        const uint32_t sw0 = p - B;
+        LaneVar<W, uint32_t> val, hsh, peers, cand, eq;
+        ZB_FOR_LANES(W, l) { val[l] = d.word(p + l); hsh[l] = hash_u32(val[l]); }
+        W::match_any(hsh, peers);
+        uint32_t inserted = 0; // lanes of this step that are loop-tops (hence in the table)
+        uint32_t s = 0;        // first lane that is not parsed yet
+        while (s < 32) {
+            ZB_FOR_LANES(W, l) {
+                uint32_t e = 0, hh = 0;
+                if (l >= s) {
+                    const uint32_t lower = peers[l] & (inserted | bit_range(s, l));
+                    hh = lower ? sw0 + top_bit(lower) : head[hsh[l]];
+                    const uint32_t sw = sw0 + l;
+                    // quick.rs:113-119: distance in range and the first four bytes equal => a match of at least 4
+                    if (hh < sw && sw - hh <= kMaxDist && d.word(B + hh) == val[l]) e = 1;
+                }
+                cand[l] = hh;
+                eq[l] = e;
+            }
+            const uint32_t m = W::ballot(eq);
+            const uint32_t f = m ? low_bit(m) : 32u;
+            ZB_FOR_LANES(W, l) { if (l >= s && l < f) emit_at(nsym + (l - s), Sym{0, (uint16_t)(val[l] & 0xffu), p + l}); }
+            nsym += f - s;
+            inserted |= bit_range(s, f < 32 ? f + 1 : 32);
+            if (f == 32) { s = 32; break; }
+            const uint32_t hh = W::bcast(cand, f);
+            uint32_t len = OPS::compare256(d, p + f + 2, B + hh + 2) + 2;
+            if (len > kMaxMatch) len = kMaxMatch; // lookahead > 258 here
+            ZB_FOR_LANES(W, l) { if (l == f) emit_at(nsym, Sym{(uint16_t)(sw0 + f - hh), (uint16_t)(len - 3), p + f}); }
+            nsym++;
+            s = f + len;
+        }
+        // the last loop-top of every hash value is what the table keeps (prev is never read at level 1)
+        ZB_FOR_LANES(W, l) {
+            if ((inserted >> l) & 1u) {
+                const uint32_t mine = peers[l] & inserted;
+                if ((mine >> l) == 1u) head[hsh[l]] = (uint16_t)(sw0 + l);
+            }
+        }
+        W::sync();
+        p += s;
+        return true;
+    }
+
+    // deflate_quick (quick.rs:12-169), one call with Z_FINISH and ample output: one static block.  emit_at(index, Sym).
+    // Returns the final window base; nsym receives the number of symbols.
+    template <class W, class EA>
+    ZB_HD uint32_t run_quick(EA &&emit_at, uint32_t &nsym)
+    {
+        nsym = 0;
         for (;;) {
             uint32_t lookahead = F - p;
             if (lookahead < kMinLookahead) {
@@ -164,6 +279,7 @@ struct SerialLow {
                 lookahead = F - p;
                 if (lookahead == 0) break;
             }
+            if (quick_wide_step<W>(emit_at, nsym)) continue;
             uint32_t lc;
             if (lookahead >= 4) {
                 const uint32_t sw = p - B;
@@ -176,7 +292,8 @@ struct SerialLow {
                         if (len >= 4) {
                             if (len > lookahead) len = lookahead;
                             if (len > kMaxMatch) len = kMaxMatch;
-                            emit(Sym{(uint16_t)(sw - hh), (uint16_t)(len - 3), p});
+                            if (W::leader()) emit_at(nsym, Sym{(uint16_t)(sw - hh), (uint16_t)(len - 3), p});
+                            nsym++;
                             p += len;
                             continue;
                         }
@@ -186,7 +303,8 @@ struct SerialLow {
             } else {
                 lc = d.byte(p);
             }
-            emit(Sym{0, (uint16_t)lc, p});
+            if (W::leader()) emit_at(nsym, Sym{0, (uint16_t)lc, p});
+            nsym++;
             p++;
         }
         return B;
