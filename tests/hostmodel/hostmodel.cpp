@@ -445,7 +445,11 @@ static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t blo
         syms.resize(n);
         return fb;
     }
-    return m.run_fast([&](Sym s) { syms.push_back(s); }, [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; });
+    uint32_t n = 0;
+    const uint32_t fb = m.run_fast<HostWarp>([&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; },
+                                             [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; }, n);
+    syms.resize(n);
+    return fb;
 }
 
 extern "C" int hm_parse_low(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)

@@ -88,8 +88,7 @@ __global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
         fb = m.run_quick<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, n);
     } else {
         uint32_t *bb = jb.block_base;
-        fb = m.run_fast([&](const Sym &s) { if (lane == 0) syms[n] = s; n++; },
-                        [&](uint32_t b, uint32_t B) { if (lane == 0) bb[b] = B; });
+        fb = m.run_fast<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, [&](uint32_t b, uint32_t B) { bb[b] = B; }, n);
     }
     if (lane == 0) {
         jb.info->n_mid_syms = 0;

@@ -206,8 +206,11 @@ struct SerialLow {
         return best;
     }
 
-    static ZB_HD uint32_t ctz_bytes(uint32_t x)
+    static ZB_HD uint32_t ctz_bytes(uint32_t x) // index of the lowest non-zero byte, x != 0
     {
+#if defined(__CUDA_ARCH__)
+        return ((uint32_t)__ffs((int)x) - 1u) >> 3;
+#endif
         uint32_t n = 0;
         while (!(x & 0xffu)) { x >>= 8; n++; }
         return n;
@@ -310,11 +313,116 @@ struct SerialLow {
         return B;
     }
 
-    // deflate_fast (fast.rs:12-118), one call with Z_FINISH and ample output.  Returns the final window base.
-    template <class E, class FL>
-    ZB_HD uint32_t run_fast(E &&emit, FL &&flush)
+    // 32 positions of deflate_fast at once, same idea as quick_wide_step.  Differences: a lane walks up to max_chain candidates
+    // (same-hash lanes of this step that are in the table, newest first, then the stored head/prev chain) with the 8-byte
+    // pre-check of longest_match (:198-224; nice_match = 8 ends the walk at the first candidate that passes it); a match of
+    // length 4 puts its interior into the table, a longer one only its last position (fast.rs:62-77); prev links are written with
+    // the head at commit time.  Positions behind lane 31 that a match inserts are inserted by the scalar code after the commit.
+    template <class W, class EA, class FL>
+    ZB_HD bool fast_wide_step(EA &&emit_at, FL &&flush, uint32_t &nsym, uint32_t &fill, uint32_t &nblk)
     {
-        uint32_t nsym = 0, nblk = 0;
+        if (F - p < kMinLookahead + 32u || sp.block_syms < 64u) return false;
+        const uint32_t sw0 = p - B;
+        LaneVar<W, uint32_t> val, hsh, peers, mstart, mlen, ism;
+        ZB_FOR_LANES(W, l) { val[l] = d.word(p + l); hsh[l] = hash_u32(val[l]); }
+        W::match_any(hsh, peers);
+        uint32_t inserted = 0; // lanes of this step that are in the table (all below s)
+        uint32_t s = 0;        // first lane that is not parsed yet
+        uint32_t post_lo = 0, post_hi = 0; // window indices [post_lo, post_hi) behind the step that a match inserts
+        while (s < 32) {
+            ZB_FOR_LANES(W, l) {
+                uint32_t is_match = 0, best = 2, start = 0;
+                if (l >= s) {
+                    const uint32_t sw = sw0 + l;
+                    const uint32_t limit = sw > kMaxDist ? sw - kMaxDist : 0;
+                    uint32_t pm = peers[l] & (inserted | bit_range(s, l));
+                    bool in_table = false;
+                    uint32_t cur, chain = sp.chain;
+                    if (pm) { const uint32_t j = top_bit(pm); pm &= ~(1u << j); cur = sw0 + j; }
+                    else { cur = head[hsh[l]]; in_table = true; }
+                    // fast.rs:45: dist in range, hash_head != 0
+                    if (cur < sw && sw - cur <= kMaxDist && cur != 0) {
+                        for (;;) {
+                            const uint32_t c = B + cur;
+                            const uint32_t x0 = val[l] ^ d.word(c);
+                            uint32_t c8;
+                            if (x0) c8 = ctz_bytes(x0);
+                            else { const uint32_t x1 = d.word(p + l + 4) ^ d.word(c + 4); c8 = x1 ? 4 + ctz_bytes(x1) : 8; }
+                            if (c8 == 8) { start = cur; best = 8; break; } // full length is computed for the winning lane only
+                            if (c8 > best) { start = cur; best = c8; }
+                            if (--chain == 0) break;
+                            if (pm) { const uint32_t j = top_bit(pm); pm &= ~(1u << j); cur = sw0 + j; }
+                            else if (!in_table) { cur = head[hsh[l]]; in_table = true; }
+                            else cur = prev[cur & (kWSize - 1)];
+                            if (cur <= limit) break;
+                        }
+                        is_match = best >= 4 ? 1u : 0u;
+                    }
+                }
+                ism[l] = is_match;
+                mstart[l] = start;
+                mlen[l] = best;
+            }
+            const uint32_t m = W::ballot(ism);
+            const uint32_t f = m ? low_bit(m) : 32u;
+            ZB_FOR_LANES(W, l) { if (l >= s && l < f) emit_at(nsym + (l - s), Sym{0, (uint16_t)(val[l] & 0xffu), p + l}); }
+            uint32_t added = f - s;
+            inserted |= bit_range(s, f < 32 ? f + 1 : 32);
+            if (f == 32) { s = 32; }
+            else {
+                const uint32_t st = W::bcast(mstart, f);
+                uint32_t len = W::bcast(mlen, f);
+                if (len == 8) {
+                    len = OPS::compare256(d, p + f + 2, B + st + 2) + 2;
+                    if (len > kMaxMatch) len = kMaxMatch; // lookahead > 258 here
+                }
+                ZB_FOR_LANES(W, l) { if (l == f) emit_at(nsym + added, Sym{(uint16_t)(sw0 + f - st), (uint16_t)(len - 3), p + f}); }
+                added++;
+                // table: a match of max_insert_length (4) inserts its interior, a longer one only its last position
+                const uint32_t i0 = len <= sp.lazy ? f + 1 : f + len - 1, i1 = f + len; // lanes [i0, i1)
+                if (i0 < 32) inserted |= bit_range(i0, i1 < 32 ? i1 : 32);
+                if (i1 > 32) { post_lo = sw0 + (i0 > 32 ? i0 : 32); post_hi = sw0 + i1; }
+                s = f + len;
+            }
+            nsym += added;
+            fill += added;
+            if (fill >= sp.block_syms) { // a full sym_buf inside the step: the base cannot change before the next fill_window
+                if (W::leader()) flush(nblk, B);
+                nblk++;
+                fill -= sp.block_syms;
+            }
+        }
+        // commit: every inserted lane links to the entry that was the head when it was inserted; the newest lane of a hash is the head
+        LaneVar<W, uint32_t> pred;
+        ZB_FOR_LANES(W, l) {
+            uint32_t pv = 0;
+            if ((inserted >> l) & 1u) {
+                const uint32_t lower = peers[l] & inserted & bit_range(0, l);
+                pv = lower ? sw0 + top_bit(lower) : head[hsh[l]];
+            }
+            pred[l] = pv;
+        }
+        W::sync();
+        ZB_FOR_LANES(W, l) {
+            if ((inserted >> l) & 1u) {
+                prev[(sw0 + l) & (kWSize - 1)] = (uint16_t)pred[l];
+                const uint32_t mine = peers[l] & inserted;
+                if ((mine >> l) == 1u) head[hsh[l]] = (uint16_t)(sw0 + l);
+            }
+        }
+        W::sync();
+        for (uint32_t str = post_lo; str < post_hi; str++) insert_at(str);
+        p += s;
+        return true;
+    }
+
+    // deflate_fast (fast.rs:12-118), one call with Z_FINISH and ample output.  emit_at(index, Sym); flush(block, base) at every full
+    // sym_buf.  Returns the final window base; nsym receives the number of symbols.
+    template <class W, class EA, class FL>
+    ZB_HD uint32_t run_fast(EA &&emit_at, FL &&flush, uint32_t &nsym)
+    {
+        uint32_t fill = 0, nblk = 0;
+        nsym = 0;
         for (;;) {
             uint32_t lookahead = F - p;
             if (lookahead < kMinLookahead) {
@@ -322,6 +430,7 @@ struct SerialLow {
                 lookahead = F - p;
                 if (lookahead == 0) break;
             }
+            if (fast_wide_step<W>(emit_at, flush, nsym, fill, nblk)) continue;
             bool matched = false;
             uint32_t lc = 0;
             if (lookahead >= 4) {
@@ -332,7 +441,7 @@ struct SerialLow {
                     uint32_t start = 0;
                     uint32_t len = longest_match(hh, start);
                     if (len >= 4) {
-                        emit(Sym{(uint16_t)(sw - start), (uint16_t)(len - 3), p});
+                        if (W::leader()) emit_at(nsym, Sym{(uint16_t)(sw - start), (uint16_t)(len - 3), p});
                         lookahead -= len;
                         if (len <= sp.lazy && lookahead >= 4) {
                             // insert_string(strstart + 1, len - 1) (hash_calc.rs:61-82)
@@ -353,12 +462,14 @@ struct SerialLow {
                 lc = d.byte(p);
             }
             if (!matched) {
-                emit(Sym{0, (uint16_t)lc, p});
+                if (W::leader()) emit_at(nsym, Sym{0, (uint16_t)lc, p});
                 p++;
             }
-            if (++nsym == sp.block_syms) { // tally_* reported a full sym_buf: flush_block!(stream, false)
-                flush(nblk++, B);
-                nsym = 0;
+            nsym++;
+            if (++fill == sp.block_syms) { // tally_* reported a full sym_buf: flush_block!(stream, false)
+                if (W::leader()) flush(nblk, B);
+                nblk++;
+                fill = 0;
             }
         }
         return B;
