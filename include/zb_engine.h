@@ -42,7 +42,7 @@ typedef struct zb_deflate_result {
     uint32_t n_symbols;    /* literal/match symbols */
     uint32_t n_blocks;     /* deflate blocks */
     uint32_t gpu_launches; /* kernels launched for this call */
-    int32_t exact_parity;  /* 1: bytes equal zlib-rs' compress2 at this level/strategy; 0: valid stream only */
+    int32_t exact_parity;  /* 1: bytes equal zlib-rs' deflate(Z_FINISH) at this level/strategy/memLevel; 0: valid stream only */
     float gpu_ms;          /* device time of the call (CUDA events), copies included when buffers are on the host */
 } zb_deflate_result;
 
@@ -52,8 +52,9 @@ ZB_API void zb_engine_destroy(zb_engine *e);
 ZB_API const char *zb_last_error(void);
 ZB_API int zb_device_count(void);
 
-/* window_bits follows deflateInit2: 9..15 zlib, -9..-15 raw, 25..31 gzip.  Only a 32 KiB window is implemented;
- * other sizes are accepted and compressed with the 32 KiB engine (valid stream, CINFO=7). */
+/* window_bits follows deflateInit2: 9..15 zlib, -9..-15 raw, 25..31 gzip.  Only the 32 KiB window is implemented: a smaller
+ * window gives the reference's bytes when the input never leaves its match range (src_len <= 2^bits - 262, only CINFO differs);
+ * otherwise the 32 KiB engine is used (valid stream, CINFO=7, exact_parity = 0). */
 ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                int level, int strategy, int window_bits, zb_deflate_result *res);
 /* flags for zb_deflate_ex */

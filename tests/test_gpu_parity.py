@@ -34,6 +34,23 @@ def test_checksums_vs_oracle_and_stock(eng):
     assert Z.crc32(bytes([1, 2, 3])) == 1438416925  # libz-rs-sys/src/lib.rs:146
 
 
+def test_checksums_unaligned_device_ranges(eng):
+    """Device-resident ranges at every 16-byte phase and ragged lengths (the crc kernel splits at 16-byte boundaries)."""
+    n = (5 << 20) + 123
+    d = synthetic_mix(n, seed=77)
+    p = eng.alloc(n + 64)
+    try:
+        eng.to_device(p, d)
+        for off in (0, 1, 3, 8, 15, 16, 17):
+            for ln in (0, 1, 15, 16, 17, 255, 4097, 262144, 262145, 1 << 20, n - off):
+                part = d[off:off + ln]
+                assert eng.crc32(p + off, ln, on_device=True)[0] == zlib.crc32(part), (off, ln)
+                assert eng.adler32(p + off, ln, on_device=True)[0] == zlib.adler32(part), (off, ln)
+        assert eng.crc32(p + 5, 3 << 20, start=0x12345678, on_device=True)[0] == zlib.crc32(d[5:5 + (3 << 20)], 0x12345678)
+    finally:
+        eng.free(p)
+
+
 def test_checksum_of_checksums_large(eng):
     """Size-independent property at a large size: chunk checksums combine to the whole (device resident)."""
     n = 256 << 20

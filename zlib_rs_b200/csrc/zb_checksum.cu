@@ -132,77 +132,114 @@ __device__ __forceinline__ uint32_t x2nmodp(uint64_t n, uint32_t k)
     return p;
 }
 
-constexpr uint32_t kCrcSeg = 2048; // bytes per thread
-constexpr uint32_t kCrcThreads = 128;
-constexpr uint32_t kCrcChunk = kCrcSeg * kCrcThreads; // 256 KiB per CTA
+// k_crc_partial: byte-sliced table CRC is bound by shared-memory lookups (one per input byte).  Two things decide its speed:
+//  * bank conflicts -- a 256-entry table hit by 32 lanes at random indices serialises ~3.5-fold.  Here every lane owns a private copy
+//    of the four slice tables in its own bank (entry (k, idx) of lane t lives at word (k*256 + idx)*32 + t: 128 KiB per CTA), so
+//    every lookup of a warp is one conflict-free wavefront;
+//  * issue slots -- per 32-bit word: 4 lookups, 4 address computations (shift + and + add), two 3-input xors.
+// One persistent CTA of 1024 threads per SM builds the tables once and loops over chunks; thread t computes the raw CRC of a
+// contiguous segment with 128-bit loads.  Chunks and segments are aligned to E = the last 16-byte boundary of the buffer (the
+// first ones are the short ones), so segment k of a chunk always has exactly (T-1-k) full segments behind it, every segment
+// start is 16-byte aligned, and every shift in the combine tree is by a full piece length.  The < 16 bytes behind E are
+// appended by k_crc_final.
+constexpr uint32_t kCrcThreads = 1024;
+constexpr uint32_t kCrcTabBytes = 4 * 256 * 32 * 4 + 32768; // + slack to align the tables to 32 KiB in the shared window
 
-// Raw CRC of each chunk.  Chunks and segments are aligned to the END of the buffer (the first ones are the short
-// ones), so segment k of a chunk always has exactly (kCrcThreads-1-k) full segments behind it.
-__global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__restrict__ buf, uint64_t len, uint32_t nchunks,
-                                                              uint32_t *__restrict__ part)
+template <uint32_t KOFF, uint32_t SHIFT>
+__device__ __forceinline__ uint32_t crc_lds(uint32_t tb, uint32_t x)
 {
-    __shared__ uint32_t tab[8][256];
-    __shared__ uint32_t segcrc[kCrcThreads];
-    __shared__ uint32_t shiftop[8];
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < 256; i += kCrcThreads) {
-        uint32_t c = i;
-        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
-        tab[0][i] = c;
-    }
-    if (tid < 7) shiftop[tid] = x2nmodp((uint64_t)kCrcSeg << tid, 3); // x^(8*seg*2^level)
-    __syncthreads();
-    for (uint32_t i = tid; i < 256; i += kCrcThreads) {
-        uint32_t c = tab[0][i];
-        for (int t = 1; t < 8; t++) { c = tab[0][c & 0xff] ^ (c >> 8); tab[t][i] = c; }
-    }
-    __syncthreads();
-    // chunk j covers [len - (nchunks-j)*C, len - (nchunks-j-1)*C) clipped at 0
-    const uint64_t cend = len - (uint64_t)(nchunks - 1 - blockIdx.x) * kCrcChunk;
-    const uint64_t cbeg = cend > kCrcChunk ? cend - kCrcChunk : 0;
-    // segment tid covers [cend - (T-tid)*S, cend - (T-tid-1)*S) clipped at cbeg
-    const uint64_t send = cend - (uint64_t)(kCrcThreads - 1 - tid) * kCrcSeg;
-    uint32_t crc = 0;
-    if (send > cbeg && cend >= (uint64_t)(kCrcThreads - 1 - tid) * kCrcSeg) {
-        const uint64_t sbeg = (send - cbeg > kCrcSeg) ? send - kCrcSeg : cbeg;
-        const uint8_t *p = buf + sbeg;
-        const uint32_t slen = (uint32_t)(send - sbeg);
-        uint32_t i = 0;
-        while (i < slen && (((uintptr_t)(p + i)) & 15)) { crc = tab[0][(crc ^ p[i]) & 0xff] ^ (crc >> 8); i++; }
-        for (; i + 16 <= slen; i += 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + i));
-            uint32_t lo = v.x ^ crc, hi = v.y;
-            crc = tab[7][lo & 0xff] ^ tab[6][(lo >> 8) & 0xff] ^ tab[5][(lo >> 16) & 0xff] ^ tab[4][lo >> 24] ^
-                  tab[3][hi & 0xff] ^ tab[2][(hi >> 8) & 0xff] ^ tab[1][(hi >> 16) & 0xff] ^ tab[0][hi >> 24];
-            lo = v.z ^ crc; hi = v.w;
-            crc = tab[7][lo & 0xff] ^ tab[6][(lo >> 8) & 0xff] ^ tab[5][(lo >> 16) & 0xff] ^ tab[4][lo >> 24] ^
-                  tab[3][hi & 0xff] ^ tab[2][(hi >> 8) & 0xff] ^ tab[1][(hi >> 16) & 0xff] ^ tab[0][hi >> 24];
-        }
-        for (; i < slen; i++) crc = tab[0][(crc ^ p[i]) & 0xff] ^ (crc >> 8);
-    }
-    segcrc[tid] = crc;
-    __syncthreads();
-    // tree: at level l, segment i absorbs segment i + 2^l, which is 2^l full segments long
-    for (uint32_t l = 0; (1u << l) < kCrcThreads; l++) {
-        const uint32_t s = 1u << l;
-        if ((tid & (2 * s - 1)) == 0) {
-            const uint32_t left = segcrc[tid];
-            segcrc[tid] = (left ? multmodp(shiftop[l], left) : 0) ^ segcrc[tid + s];
-        }
-        __syncthreads();
-    }
-    if (tid == 0) part[blockIdx.x] = segcrc[0];
+    // table word of byte ((x >> SHIFT*8) & 0xff) of slice KOFF/32768.  tb = 32 KiB-aligned table base | lane*4, so the entry offset
+    // (idx * 128, bits 7..14) is OR-ed in: one shift + one LOP3 per lookup; the slice offset rides in the LDS immediate
+    uint32_t v;
+    const uint32_t sh = SHIFT == 0 ? x << 7 : SHIFT == 1 ? x >> 1 : SHIFT == 2 ? x >> 9 : x >> 17;
+    const uint32_t a = (sh & 0x7f80u) | tb;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(KOFF));
+    return v;
+}
+// one 32-bit step of the sliced CRC: x = data word ^ register; returns T3[b0] ^ T2[b1] ^ T1[b2] ^ T0[b3]
+__device__ __forceinline__ uint32_t crc_step(uint32_t tb, uint32_t x)
+{
+    return crc_lds<3u * 32768u, 0>(tb, x) ^ crc_lds<2u * 32768u, 1>(tb, x) ^ crc_lds<32768u, 2>(tb, x) ^ crc_lds<0u, 3>(tb, x);
 }
 
-__global__ void __launch_bounds__(1024) k_crc_final(const uint32_t *part, uint32_t nchunks, uint64_t len, uint32_t start, uint32_t *out)
+__global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__restrict__ buf, uint64_t main_len, uint32_t seg, uint32_t nchunks,
+                                                              uint32_t *__restrict__ part)
+{
+    extern __shared__ __align__(16) uint8_t crc_smem[];
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(crc_smem);
+    const uint32_t tab_base = (smem_base + 32767u) & ~32767u;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(crc_smem + (tab_base - smem_base)); // [4][256][32], 32 KiB aligned
+    __shared__ uint32_t t0[256];
+    __shared__ uint32_t segcrc[kCrcThreads];
+    __shared__ uint32_t shiftop[10];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    if (tid < 256) {
+        uint32_t c = tid;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        t0[tid] = c;
+    }
+    if (tid >= 256 && tid < 266) shiftop[tid - 256] = x2nmodp((uint64_t)seg << (tid - 256), 3); // x^(8*seg*2^level)
+    __syncthreads();
+    for (uint32_t i = tid; i < 256 * 32; i += kCrcThreads) {
+        const uint32_t idx = i >> 5;
+        uint32_t c = t0[idx];
+        tab[i] = c; // T0
+        for (uint32_t t = 1; t < 4; t++) { c = t0[c & 0xff] ^ (c >> 8); tab[t * 8192 + i] = c; }
+    }
+    __syncthreads();
+    const uint32_t tb = tab_base | (lane * 4u);
+    const uint64_t chunk = (uint64_t)seg * kCrcThreads;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        // chunk j covers [E - (nchunks-j)*C, E - (nchunks-j-1)*C) clipped at 0
+        const uint64_t cend = main_len - (uint64_t)(nchunks - 1 - ch) * chunk;
+        const uint64_t cbeg = cend > chunk ? cend - chunk : 0;
+        // segment tid covers [cend - (T-tid)*S, cend - (T-tid-1)*S) clipped at cbeg
+        const uint64_t back = (uint64_t)(kCrcThreads - 1 - tid) * seg;
+        uint32_t crc = 0;
+        if (cend >= back && cend - back > cbeg) {
+            const uint64_t send = cend - back;
+            const uint64_t sbeg = (send - cbeg > seg) ? send - seg : cbeg;
+            const uint8_t *p = buf + sbeg;
+            const uint32_t slen = (uint32_t)(send - sbeg);
+            uint32_t i = 0;
+            // only the first segment of the buffer can start unaligned
+            while (i < slen && (((uintptr_t)(p + i)) & 15)) { crc = t0[(crc ^ p[i]) & 0xff] ^ (crc >> 8); i++; }
+#pragma unroll 2
+            for (; i + 16 <= slen; i += 16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                crc = crc_step(tb, v.x ^ crc);
+                crc = crc_step(tb, v.y ^ crc);
+                crc = crc_step(tb, v.z ^ crc);
+                crc = crc_step(tb, v.w ^ crc);
+            }
+            for (; i < slen; i++) crc = t0[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+        }
+        segcrc[tid] = crc;
+        __syncthreads();
+        // tree: at level l, segment i absorbs segment i + 2^l, which is 2^l full segments long
+        for (uint32_t l = 0; (1u << l) < kCrcThreads; l++) {
+            const uint32_t s2 = 1u << l;
+            if ((tid & (2 * s2 - 1)) == 0) {
+                const uint32_t left = segcrc[tid];
+                segcrc[tid] = (left ? multmodp(shiftop[l], left) : 0) ^ segcrc[tid + s2];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) part[ch] = segcrc[0];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_crc_final(const uint32_t *part, uint32_t nchunks, uint64_t chunk_bytes, const uint8_t *tail, uint32_t tail_len,
+                                                     uint64_t len, uint32_t start, uint32_t *out)
 {
     __shared__ uint32_t sc[1024];
     __shared__ uint32_t ops[12];
     const uint32_t tid = threadIdx.x;
     // thread t reduces `per` consecutive chunk partials (aligned to the end: the leading threads may have fewer)
     const uint32_t per = (nchunks + 1023) / 1024;
-    if (tid == 0) ops[0] = x2nmodp(kCrcChunk, 3);
-    if (tid >= 1 && tid <= 10) ops[tid] = x2nmodp(((uint64_t)kCrcChunk * per) << (tid - 1), 3);
+    if (tid == 0) ops[0] = x2nmodp(chunk_bytes, 3);
+    if (tid >= 1 && tid <= 10) ops[tid] = x2nmodp((chunk_bytes * per) << (tid - 1), 3);
     __syncthreads();
     uint32_t acc = 0;
     {
@@ -223,9 +260,14 @@ __global__ void __launch_bounds__(1024) k_crc_final(const uint32_t *part, uint32
     }
     if (tid == 0) {
         // register after the data starting from r0 = ~start:  raw(M) ^ r0 * x^(8 len); then the final xor
+        uint32_t raw = sc[0];
+        for (uint32_t i = 0; i < tail_len; i++) { // the bytes behind the last 16-byte boundary continue the raw register
+            raw ^= tail[i];
+            for (int k = 0; k < 8; k++) raw = (raw & 1) ? (raw >> 1) ^ kCrcPoly : raw >> 1;
+        }
         const uint32_t r0 = ~start;
         const uint32_t sh = r0 ? multmodp(x2nmodp(len, 3), r0) : 0;
-        *out = ~(sc[0] ^ sh);
+        *out = ~(raw ^ sh);
     }
 }
 
@@ -250,11 +292,36 @@ cudaError_t launch_adler32(const uint8_t *d_buf, uint64_t len, uint32_t start, v
 cudaError_t launch_crc32(const uint8_t *d_buf, uint64_t len, uint32_t start, void *d_scratch, size_t scratch_bytes, uint32_t *d_out,
                          cudaStream_t st)
 {
-    const uint64_t nchunks = (len + kCrcChunk - 1) / kCrcChunk;
+    static int sm_count[64]; // per device; the opt-in for 128 KiB of dynamic shared memory is per device too
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (sm_count[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(k_crc_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcTabBytes);
+        if (e != cudaSuccess) return e;
+        sm_count[dev] = v > 0 ? v : 148;
+    }
+    const int n_sm = sm_count[dev];
+    // main part: up to the last 16-byte boundary; the rest (< 16 bytes) is appended by k_crc_final
+    uint32_t tail_len = (uint32_t)((reinterpret_cast<uintptr_t>(d_buf) + len) & 15u);
+    if (tail_len > len) tail_len = (uint32_t)len;
+    const uint64_t main_len = len - tail_len;
+    // bytes per thread: enough segments to fill every SM once, at most 4 KiB (the combine tree costs ~2500 cycles per chunk)
+    uint64_t seg = (main_len + (uint64_t)n_sm * kCrcThreads - 1) / ((uint64_t)n_sm * kCrcThreads);
+    seg = (seg + 15) & ~15ull;
+    if (seg < 256) seg = 256;
+    if (seg > 4096) seg = 4096;
+    const uint64_t chunk = seg * kCrcThreads;
+    const uint64_t nchunks = (main_len + chunk - 1) / chunk;
     if (nchunks * 4 > scratch_bytes) return cudaErrorInvalidValue;
     uint32_t *part = static_cast<uint32_t *>(d_scratch);
-    if (nchunks) k_crc_partial<<<(uint32_t)nchunks, kCrcThreads, 0, st>>>(d_buf, len, (uint32_t)nchunks, part);
-    k_crc_final<<<1, 1024, 0, st>>>(part, (uint32_t)nchunks, len, start, d_out);
+    if (nchunks) {
+        const uint32_t grid = (uint32_t)(nchunks < (uint64_t)n_sm ? nchunks : (uint64_t)n_sm);
+        k_crc_partial<<<grid, kCrcThreads, kCrcTabBytes, st>>>(d_buf, main_len, (uint32_t)seg, (uint32_t)nchunks, part);
+    }
+    k_crc_final<<<1, 1024, 0, st>>>(part, (uint32_t)nchunks, chunk, d_buf + main_len, tail_len, len, start, d_out);
     return cudaGetLastError();
 }
 
