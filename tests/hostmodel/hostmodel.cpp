@@ -434,22 +434,26 @@ struct LowAcc {
     uint32_t word(uint32_t y) const { return byte(y) | (byte(y + 1) << 8) | (byte(y + 2) << 16) | (byte(y + 3) << 24); }
 };
 
-static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
+template <uint32_t R>
+static uint32_t run_low_ring(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
 {
     std::vector<uint16_t> head(65536, 0), prev(32768, 0);
-    LowAcc a{data, N};
-    SerialLow<LowAcc, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms));
-    if (level == 1) {
-        uint32_t n = 0;
-        const uint32_t fb = m.run_quick<HostWarp>([&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; }, n);
-        syms.resize(n);
-        return fb;
-    }
-    uint32_t n = 0;
-    const uint32_t fb = m.run_fast<HostWarp>([&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; },
-                                             [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; }, n);
+    std::vector<uint8_t> padded(N + 64, 0), ring(R + 16, 0xAA);
+    if (N) memcpy(padded.data(), data, N);
+    RingAcc<R, ScalarCopy> a(ring.data(), padded.data(), N);
+    SerialLow<RingAcc<R, ScalarCopy>, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms));
+    uint32_t n = 0, fb;
+    auto emit_at = [&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; };
+    if (level == 1) fb = m.template run_quick<HostWarp>(emit_at, n);
+    else fb = m.template run_fast<HostWarp>(emit_at, [&](uint32_t b, uint32_t B) { if (blockB.size() <= b) blockB.resize(b + 1); blockB[b] = B; }, n);
     syms.resize(n);
     return fb;
+}
+
+// the ring sizes of k_serial_low: 64 KiB next to the 128 KiB head table at level 1, 35824 B next to head + prev at level 2
+static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
+{
+    return level == 1 ? run_low_ring<65536>(data, N, level, block_syms, syms, blockB) : run_low_ring<35824>(data, N, level, block_syms, syms, blockB);
 }
 
 extern "C" int hm_parse_low(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)

@@ -58,7 +58,8 @@ constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
-constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2; // head + prev tables of one stream
+constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2 + 35824 + 16; // head + prev tables of one stream + the input ring (level 2)
+constexpr uint32_t kSerialSmemQuick = 65536 * 2 + 65536 + 16;         // head + 64 KiB input ring (level 1)
 
 int Engine::init(int dev)
 {
@@ -315,7 +316,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         } else if (jb.serial_mode) {
             iters = 1;
             pbegin();
-            k_serial_low<<<1, 32, jb.serial_mode == 2 ? kSerialSmemBytes : 65536u * 2u, st>>>(jb);
+            k_serial_low<<<1, 32, jb.serial_mode == 2 ? kSerialSmemBytes : kSerialSmemQuick, st>>>(jb);
             launches++;
             pend(1, 1);
         } else {

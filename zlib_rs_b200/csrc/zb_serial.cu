@@ -7,27 +7,10 @@
 
 namespace zb {
 
-struct DevLowAcc {
-    const uint8_t *in; // zero padded behind N (kPad)
-    uint32_t N;
-    __device__ __forceinline__ uint32_t byte(uint32_t y) const
-    {
-        // bytes behind the input are what the reference's window buffer still holds there (cf. GAcc)
-        while (y >= N) {
-            if (y < 2 * kWSize) return 0;
-            y -= kWSize;
-        }
-        return in[y];
-    }
-    __device__ __forceinline__ uint32_t word(uint32_t y) const
-    {
-        if (y + 4 <= N) {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(in + y);
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-            return __funnelshift_r(q[0], q[1], (uint32_t)(a & 3u) * 8u);
-        }
-        return byte(y) | (byte(y + 1) << 8) | (byte(y + 2) << 16) | (byte(y + 3) << 24);
-    }
+struct WarpCopy { // RingAcc's refill on a warp
+    static __device__ __forceinline__ uint32_t first() { return threadIdx.x & 31u; }
+    static __device__ __forceinline__ uint32_t stride() { return 32u; }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
 struct WarpOps {
@@ -68,27 +51,32 @@ struct DevWarp { // the lane-parallel policy of zb_serial.h on a real warp
 };
 
 // One CTA of one warp per stream.  Writes the symbols, the per-block window bases and the job totals.
-__global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
+// Shared memory: head (128 KiB) | prev (64 KiB, level 2) | input ring + 16-byte mirror.
+constexpr uint32_t kRingQuick = 65536, kRingFast = 35824; // level 2: what is left of 227 KiB next to both tables
+
+template <uint32_t R, bool kFast>
+__device__ __forceinline__ void serial_low_body(const JobBufs &jb, uint8_t *smem)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *head = reinterpret_cast<uint16_t *>(smem);
-    uint16_t *prev = jb.serial_mode == 2 ? reinterpret_cast<uint16_t *>(smem + 65536 * 2) : nullptr;
+    uint16_t *prev = kFast ? reinterpret_cast<uint16_t *>(smem + 65536 * 2) : nullptr;
+    uint8_t *ring = smem + 65536 * 2 + (kFast ? kWSize * 2 : 0);
     const uint32_t lane = threadIdx.x;
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem);
-        const uint32_t n16 = (jb.serial_mode == 2 ? (65536u + kWSize) * 2u : 65536u * 2u) / 16u;
+        const uint32_t n16 = (kFast ? (65536u + kWSize) * 2u : 65536u * 2u) / 16u;
         for (uint32_t i = lane; i < n16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
-    DevLowAcc a{jb.in, jb.N};
-    SerialLow<DevLowAcc, WarpOps> m(a, head, prev, jb.N, serial_low_params((int)jb.serial_mode, jb.block_syms));
+    using Acc = RingAcc<R, WarpCopy>;
+    Acc a(ring, jb.in, jb.N);
+    SerialLow<Acc, WarpOps> m(a, head, prev, jb.N, serial_low_params(kFast ? 2 : 1, jb.block_syms));
     Sym *syms = jb.syms;
     uint32_t n = 0, fb;
-    if (jb.serial_mode == 1) {
-        fb = m.run_quick<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, n);
+    if (!kFast) {
+        fb = m.template run_quick<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, n);
     } else {
         uint32_t *bb = jb.block_base;
-        fb = m.run_fast<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, [&](uint32_t b, uint32_t B) { bb[b] = B; }, n);
+        fb = m.template run_fast<DevWarp>([&](uint32_t i, const Sym &s) { syms[i] = s; }, [&](uint32_t b, uint32_t B) { bb[b] = B; }, n);
     }
     if (lane == 0) {
         jb.info->n_mid_syms = 0;
@@ -97,6 +85,13 @@ __global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
         // deflate_quick's single block is encoded in pieces of kBlockSyms symbols; deflate_fast flushes a block per full sym_buf
         jb.info->n_blocks = n / jb.block_syms + 1;
     }
+}
+
+__global__ void __launch_bounds__(32) k_serial_low(JobBufs jb)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    if (jb.serial_mode == 1) serial_low_body<kRingQuick, false>(jb, smem);
+    else serial_low_body<kRingFast, true>(jb, smem);
 }
 
 } // namespace zb

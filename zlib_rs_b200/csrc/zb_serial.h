@@ -104,18 +104,102 @@ ZB_HD uint32_t low_bit(uint32_t m) // index of the lowest set bit, m != 0
     return i;
 }
 
-// D: byte(y) (stale-window semantics behind the input, see GAcc), word(y) = little-endian 32 bits at y.
+// ---------------------------------------------------------------------------------------------
+// RingAcc: the part of the input the parser can touch -- the 32 KiB behind strstart and a few hundred bytes ahead -- kept in a ring
+// of R bytes (shared memory on the device), refilled a few KiB at a time as strstart advances.  A single warp cannot hide the
+// latency of dependent global loads, and with 192 KiB of tables resident the L1 left over is too small for the window.
+// R is a multiple of 16; 16 bytes behind the ring mirror its first bytes so that unaligned word reads never wrap.  Everything outside
+// [lo, hi) -- and the stale-window bytes behind the end of the input -- is read from the input itself.
+// CP: copy16(dst, src, n_units, first_unit) cooperative copy, sync().
+// ---------------------------------------------------------------------------------------------
+#if defined(ZB_RING_STATS)
+static unsigned long long zb_ring_misses = 0;
+#endif
+constexpr uint32_t kRingBack = kWSize + 16;  // bytes kept behind strstart
+constexpr uint32_t kRingAhead = 352;         // bytes guaranteed ahead of strstart after ensure()
+struct ScalarCopy {
+    static ZB_HD uint32_t first() { return 0; }
+    static ZB_HD uint32_t stride() { return 1; }
+    static ZB_HD void sync() {}
+};
+template <uint32_t R, class CP>
+struct RingAcc {
+    uint8_t *ring;     // R + 16 bytes
+    const uint8_t *in; // N bytes, zero padded by at least 16
+    uint32_t N;
+    uint32_t lo = 0, hi = 0; // the ring holds absolute [lo, hi); multiples of 16
+    ZB_HD RingAcc(uint8_t *r, const uint8_t *i, uint32_t n) : ring(r), in(i), N(n) {}
+    ZB_HD uint32_t raw(uint32_t y) const // y < N
+    {
+#if defined(ZB_RING_STATS)
+        if (!(y - lo < hi - lo)) zb_ring_misses++;
+#endif
+        return (y - lo < hi - lo) ? ring[y % R] : in[y];
+    }
+    ZB_HD uint32_t byte(uint32_t y) const
+    {
+        while (y >= N) { // what the reference's window buffer still holds behind the end of the input (cf. GAcc)
+            if (y < 2 * kWSize) return 0;
+            y -= kWSize;
+        }
+        return raw(y);
+    }
+    ZB_HD uint32_t word(uint32_t y) const
+    {
+        if (y + 4 <= N && y - lo < hi - lo && y + 4 <= hi) {
+            const uint32_t i = y % R;
+#if defined(__CUDA_ARCH__)
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (i & ~3u));
+            return __funnelshift_r(w[0], w[1], (i & 3u) * 8u);
+#else
+            return ring[i] | (ring[i + 1] << 8) | (ring[i + 2] << 16) | ((uint32_t)ring[i + 3] << 24);
+#endif
+        }
+        return byte(y) | (byte(y + 1) << 8) | (byte(y + 2) << 16) | (byte(y + 3) << 24);
+    }
+    // make [p - kRingBack, p + kRingAhead) resident (clipped to the padded input); uniform call
+    ZB_HD void ensure(uint32_t p)
+    {
+        const uint32_t npad = (N + 15u) & ~15u;
+        const uint32_t need = p + kRingAhead < npad ? p + kRingAhead : npad;
+        if (hi >= need) return;
+        uint32_t nh = ((p > kRingBack ? p - kRingBack : 0u) + R) & ~15u;
+        if (nh > npad) nh = npad;
+        CP::sync();
+        const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(ring)) & 15u) == 0;
+        for (uint32_t u = hi / 16 + CP::first(); u < nh / 16; u += CP::stride()) {
+            const uint32_t di = (u * 16u) % R;
+            if (vec) {
+                struct alignas(16) U16 { uint32_t w[4]; };
+                const U16 v = *reinterpret_cast<const U16 *>(in + (size_t)u * 16);
+                *reinterpret_cast<U16 *>(ring + di) = v;
+                if (di == 0) *reinterpret_cast<U16 *>(ring + R) = v;
+            } else {
+                for (uint32_t k = 0; k < 16; k++) {
+                    const uint8_t v = in[(size_t)u * 16 + k];
+                    ring[di + k] = v;
+                    if (di == 0) ring[R + k] = v;
+                }
+            }
+        }
+        hi = nh;
+        lo = nh > R ? nh - R : 0;
+        CP::sync();
+    }
+};
+
+// D: byte(y) (stale-window semantics behind the input, see GAcc), word(y) = little-endian 32 bits at y, ensure(p) before every step.
 // OPS: slide / compare256.  EMIT(Sym).  FLUSH(block_index, B): a full sym_buf was flushed (deflate_fast only).
 template <class D, class OPS>
 struct SerialLow {
-    const D &d;
+    D &d;
     uint16_t *head;   // 65536 entries (window indices)
     uint16_t *prev;   // 32768 entries; nullptr at level 1 (deflate_quick never reads it)
     uint32_t N;
     SerialLowParams sp;
     uint32_t B = 0, F = 0, p = 0;
 
-    ZB_HD SerialLow(const D &d_, uint16_t *h, uint16_t *pv, uint32_t n, const SerialLowParams &s) : d(d_), head(h), prev(pv), N(n), sp(s) {}
+    ZB_HD SerialLow(D &d_, uint16_t *h, uint16_t *pv, uint32_t n, const SerialLowParams &s) : d(d_), head(h), prev(pv), N(n), sp(s) {}
 
     // StandardHashCalc::quick_insert_value (hash_calc.rs:48-59); str is a window index
     ZB_HD uint32_t insert_value(uint32_t str, uint32_t val)
@@ -276,6 +360,7 @@ struct SerialLow {
     {
         nsym = 0;
         for (;;) {
+            d.ensure(p);
             uint32_t lookahead = F - p;
             if (lookahead < kMinLookahead) {
                 fill_window();
@@ -424,6 +509,7 @@ struct SerialLow {
         uint32_t fill = 0, nblk = 0;
         nsym = 0;
         for (;;) {
+            d.ensure(p);
             uint32_t lookahead = F - p;
             if (lookahead < kMinLookahead) {
                 fill_window();
