@@ -345,44 +345,16 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             continue;
         }
         if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
-            // full compare of the pending candidates.  A lane checks the first 32 bytes itself; a candidate that is still equal there
-            // (long matches: repetitive data, exactly where walks are long) is finished by the whole warp, 8 bytes per lane and one
-            // ballot, instead of up to 29 more dependent steps of one lane with the other 31 waiting.
-            uint32_t len = 0;
-            bool is_long = false;
             if (state == LS_PEND) {
-                uint32_t clen = 0, d0, d1;
+                uint32_t clen = 0, len;
                 const uint32_t pa = dbase + xr, pb = dbase + cand;
                 for (;;) {
-                    d0 = sld_u32u(pa + clen) ^ sld_u32u(pb + clen);
-                    d1 = sld_u32u(pa + clen + 4) ^ sld_u32u(pb + clen + 4);
-                    if ((d0 | d1) == 0 && clen + 8 < 32) { clen += 8; continue; }
+                    const uint32_t d0 = sld_u32u(pa + clen) ^ sld_u32u(pb + clen);
+                    const uint32_t d1 = sld_u32u(pa + clen + 4) ^ sld_u32u(pb + clen + 4);
+                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
                     break;
                 }
-                if (d0 | d1) len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : clen + 4 + ((__ffs(d1) - 1) >> 3);
-                else is_long = true;
-            }
-            uint32_t m_long = __ballot_sync(0xffffffffu, is_long);
-            while (m_long) {
-                const uint32_t leader = __ffs(m_long) - 1;
-                m_long &= m_long - 1;
-                const uint32_t bx = __shfl_sync(0xffffffffu, xr, leader), bc = __shfl_sync(0xffffffffu, cand, leader);
-                const uint32_t off = 32u + 8u * lane; // bytes 32 .. 287, only those below kMaxMatch count
-                uint32_t idx = 8;                     // first mismatch among my 8 bytes
-                if (off < kMaxMatch) {
-                    const uint32_t e0 = sld_u32u(dbase + bx + off) ^ sld_u32u(dbase + bc + off);
-                    const uint32_t e1 = sld_u32u(dbase + bx + off + 4) ^ sld_u32u(dbase + bc + off + 4);
-                    idx = e0 ? (uint32_t)(__ffs(e0) - 1) >> 3 : e1 ? 4u + ((uint32_t)(__ffs(e1) - 1) >> 3) : 8u;
-                }
-                const uint32_t mm = __ballot_sync(0xffffffffu, idx < 8);
-                uint32_t l = kMaxMatch;
-                if (mm) {
-                    const uint32_t src = __ffs(mm) - 1;
-                    l = 32u + 8u * src + __shfl_sync(0xffffffffu, idx, src);
-                }
-                if (lane == leader) len = l;
-            }
-            if (state == LS_PEND) {
                 if (len > kMaxMatch) len = kMaxMatch;
                 state = LS_WALK;
                 if (len > best) {
