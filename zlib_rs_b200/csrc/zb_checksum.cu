@@ -132,17 +132,22 @@ __device__ __forceinline__ uint32_t x2nmodp(uint64_t n, uint32_t k)
     return p;
 }
 
-// k_crc_partial: byte-sliced table CRC is bound by shared-memory lookups (one per input byte).  Two things decide its speed:
-//  * bank conflicts -- a 256-entry table hit by 32 lanes at random indices serialises ~3.5-fold.  Here every lane owns a private copy
-//    of the four slice tables in its own bank (entry (k, idx) of lane t lives at word (k*256 + idx)*32 + t: 128 KiB per CTA), so
-//    every lookup of a warp is one conflict-free wavefront;
-//  * issue slots -- per 32-bit word: 4 lookups, 4 address computations (shift + and + add), two 3-input xors.
-// One persistent CTA of 1024 threads per SM builds the tables once and loops over chunks; thread t computes the raw CRC of a
-// contiguous segment with 128-bit loads.  Chunks and segments are aligned to E = the last 16-byte boundary of the buffer (the
-// first ones are the short ones), so segment k of a chunk always has exactly (T-1-k) full segments behind it, every segment
-// start is 16-byte aligned, and every shift in the combine tree is by a full piece length.  The < 16 bytes behind E are
-// appended by k_crc_final.
+// k_crc_partial.  Byte-sliced table CRC costs one shared-memory lookup per input byte; what else the L1/shared pipe has to do decides
+// the speed (ncu, profiles/r02c: with one contiguous segment per THREAD every 128-bit load touches 32 different lines -- 32 tag
+// cycles per 512 bytes next to the 16 lookup wavefronts).  This version:
+//  * conflict-free lookups: every lane owns a private copy of the four slice tables in its own bank (entry (k, idx) of lane t at
+//    word (k*256 + idx)*32 + t, 128 KiB per CTA, 32 KiB aligned so that the entry offset is OR-ed into the address);
+//  * coalesced loads: a WARP owns a contiguous segment and reads it in rows of 512 bytes, lane t taking words 4t..4t+3.  A lane runs
+//    four independent registers, one per word column: register i sees every 128th word, so its step is R = (R ^ w) * x^4096 -- the
+//    slice tables are those of x^4096 instead of x^32, nothing else changes.  At the end of the segment register i is corrected by
+//    x^(-32 i) (the order of x is 2^32-1) and the 128 registers are XOR-ed: the raw CRC of the segment;
+//  * one persistent CTA of 32 warps per SM builds the tables once and loops over chunks of 32 segments.
+// Chunks and segments are aligned to E = the last 16-byte boundary of the buffer (the first ones are the short ones), so every
+// shift in the combine tree is by a full piece length and every row is 16-byte aligned; a short first segment starts with
+// (length mod 512) bytes that lane 0 absorbs bytewise.  The < 16 bytes behind E are appended by k_crc_final.
 constexpr uint32_t kCrcThreads = 1024;
+constexpr uint32_t kCrcWarps = kCrcThreads / 32;
+constexpr uint32_t kCrcRow = 512;
 constexpr uint32_t kCrcTabBytes = 4 * 256 * 32 * 4 + 32768; // + slack to align the tables to 32 KiB in the shared window
 
 template <uint32_t KOFF, uint32_t SHIFT>
@@ -156,70 +161,91 @@ __device__ __forceinline__ uint32_t crc_lds(uint32_t tb, uint32_t x)
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(KOFF));
     return v;
 }
-// one 32-bit step of the sliced CRC: x = data word ^ register; returns T3[b0] ^ T2[b1] ^ T1[b2] ^ T0[b3]
-__device__ __forceinline__ uint32_t crc_step(uint32_t tb, uint32_t x)
+// x * x^4096 for a 32-bit x, sliced by bytes
+__device__ __forceinline__ uint32_t crc_far(uint32_t tb, uint32_t x)
 {
-    return crc_lds<3u * 32768u, 0>(tb, x) ^ crc_lds<2u * 32768u, 1>(tb, x) ^ crc_lds<32768u, 2>(tb, x) ^ crc_lds<0u, 3>(tb, x);
+    return crc_lds<0u, 0>(tb, x) ^ crc_lds<32768u, 1>(tb, x) ^ crc_lds<2u * 32768u, 2>(tb, x) ^ crc_lds<3u * 32768u, 3>(tb, x);
 }
 
-__global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__restrict__ buf, uint64_t main_len, uint32_t seg, uint32_t nchunks,
+__global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__restrict__ buf, uint64_t main_len, uint32_t wseg, uint32_t nchunks,
                                                               uint32_t *__restrict__ part)
 {
     extern __shared__ __align__(16) uint8_t crc_smem[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(crc_smem);
     const uint32_t tab_base = (smem_base + 32767u) & ~32767u;
     uint32_t *tab = reinterpret_cast<uint32_t *>(crc_smem + (tab_base - smem_base)); // [4][256][32], 32 KiB aligned
-    __shared__ uint32_t t0[256];
-    __shared__ uint32_t segcrc[kCrcThreads];
-    __shared__ uint32_t shiftop[10];
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint32_t t0[256];      // the ordinary byte table (ragged heads)
+    __shared__ uint32_t cfix[128];    // x^(-32 i)
+    __shared__ uint32_t segcrc[kCrcWarps];
+    __shared__ uint32_t shiftop[5];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 256) {
         uint32_t c = tid;
         for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
         t0[tid] = c;
     }
-    if (tid >= 256 && tid < 266) shiftop[tid - 256] = x2nmodp((uint64_t)seg << (tid - 256), 3); // x^(8*seg*2^level)
-    __syncthreads();
-    for (uint32_t i = tid; i < 256 * 32; i += kCrcThreads) {
-        const uint32_t idx = i >> 5;
-        uint32_t c = t0[idx];
-        tab[i] = c; // T0
-        for (uint32_t t = 1; t < 4; t++) { c = t0[c & 0xff] ^ (c >> 8); tab[t * 8192 + i] = c; }
+    if (tid >= 256 && tid < 261) shiftop[tid - 256] = x2nmodp((uint64_t)wseg << (tid - 256), 3); // x^(8*wseg*2^level)
+    if (tid >= 512 && tid < 640) cfix[tid - 512] = x2nmodp(0xffffffffull - 32ull * (tid - 512), 0);
+    {
+        // far tables: T[k][b] = (b << 8k) * x^4096; thread t fills entry (k, b) = t for all 32 lanes
+        const uint32_t x4096 = x2nmodp(128, 5);
+        const uint32_t k = tid >> 8, b = tid & 255;
+        const uint32_t v = b ? multmodp(x4096, b << (8 * k)) : 0;
+        for (uint32_t l = 0; l < 32; l++) tab[(k * 256 + b) * 32 + l] = v;
     }
     __syncthreads();
     const uint32_t tb = tab_base | (lane * 4u);
-    const uint64_t chunk = (uint64_t)seg * kCrcThreads;
+    const uint64_t chunk = (uint64_t)wseg * kCrcWarps;
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         // chunk j covers [E - (nchunks-j)*C, E - (nchunks-j-1)*C) clipped at 0
         const uint64_t cend = main_len - (uint64_t)(nchunks - 1 - ch) * chunk;
         const uint64_t cbeg = cend > chunk ? cend - chunk : 0;
-        // segment tid covers [cend - (T-tid)*S, cend - (T-tid-1)*S) clipped at cbeg
-        const uint64_t back = (uint64_t)(kCrcThreads - 1 - tid) * seg;
+        // segment of this warp: [cend - (W-warp)*S, cend - (W-warp-1)*S) clipped at cbeg
+        const uint64_t back = (uint64_t)(kCrcWarps - 1 - warp) * wseg;
         uint32_t crc = 0;
         if (cend >= back && cend - back > cbeg) {
             const uint64_t send = cend - back;
-            const uint64_t sbeg = (send - cbeg > seg) ? send - seg : cbeg;
-            const uint8_t *p = buf + sbeg;
+            const uint64_t sbeg = (send - cbeg > wseg) ? send - wseg : cbeg;
             const uint32_t slen = (uint32_t)(send - sbeg);
-            uint32_t i = 0;
-            // only the first segment of the buffer can start unaligned
-            while (i < slen && (((uintptr_t)(p + i)) & 15)) { crc = t0[(crc ^ p[i]) & 0xff] ^ (crc >> 8); i++; }
-#pragma unroll 2
-            for (; i + 16 <= slen; i += 16) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + i));
-                crc = crc_step(tb, v.x ^ crc);
-                crc = crc_step(tb, v.y ^ crc);
-                crc = crc_step(tb, v.z ^ crc);
-                crc = crc_step(tb, v.w ^ crc);
+            const uint32_t rows = slen / kCrcRow, head = slen - rows * kCrcRow;
+            uint32_t rh = 0;
+            if (head && lane == 0) {
+                const uint8_t *p = buf + sbeg;
+                for (uint32_t i = 0; i < head; i++) rh = t0[(rh ^ p[i]) & 0xff] ^ (rh >> 8);
             }
-            for (; i < slen; i++) crc = t0[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+            const uint4 *rp = reinterpret_cast<const uint4 *>(buf + sbeg + head) + lane; // 16-byte aligned: E-anchored rows
+            uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+            uint32_t r = 0;
+#pragma unroll 1
+            for (; r + 4 <= rows; r += 4) { // four rows in flight
+                const uint4 a = __ldg(rp + (size_t)r * 32), b = __ldg(rp + (size_t)(r + 1) * 32);
+                const uint4 c = __ldg(rp + (size_t)(r + 2) * 32), d = __ldg(rp + (size_t)(r + 3) * 32);
+                r0 = crc_far(tb, r0 ^ a.x); r1 = crc_far(tb, r1 ^ a.y); r2 = crc_far(tb, r2 ^ a.z); r3 = crc_far(tb, r3 ^ a.w);
+                r0 = crc_far(tb, r0 ^ b.x); r1 = crc_far(tb, r1 ^ b.y); r2 = crc_far(tb, r2 ^ b.z); r3 = crc_far(tb, r3 ^ b.w);
+                r0 = crc_far(tb, r0 ^ c.x); r1 = crc_far(tb, r1 ^ c.y); r2 = crc_far(tb, r2 ^ c.z); r3 = crc_far(tb, r3 ^ c.w);
+                r0 = crc_far(tb, r0 ^ d.x); r1 = crc_far(tb, r1 ^ d.y); r2 = crc_far(tb, r2 ^ d.z); r3 = crc_far(tb, r3 ^ d.w);
+            }
+            for (; r < rows; r++) {
+                const uint4 a = __ldg(rp + (size_t)r * 32);
+                r0 = crc_far(tb, r0 ^ a.x); r1 = crc_far(tb, r1 ^ a.y); r2 = crc_far(tb, r2 ^ a.z); r3 = crc_far(tb, r3 ^ a.w);
+            }
+            // register i = 4*lane + k has every word one factor x^4096 too high by x^(32 i)
+            uint32_t acc = 0;
+            if (rows) {
+                acc = (r0 ? multmodp(cfix[4 * lane], r0) : 0) ^ (r1 ? multmodp(cfix[4 * lane + 1], r1) : 0) ^
+                      (r2 ? multmodp(cfix[4 * lane + 2], r2) : 0) ^ (r3 ? multmodp(cfix[4 * lane + 3], r3) : 0);
+                if (lane == 0 && rh) acc ^= multmodp(x2nmodp((uint64_t)rows * kCrcRow, 3), rh); // the ragged head sits in front of the rows
+            } else if (lane == 0) acc = rh;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+            crc = acc;
         }
-        segcrc[tid] = crc;
+        if (lane == 0) segcrc[warp] = crc;
         __syncthreads();
         // tree: at level l, segment i absorbs segment i + 2^l, which is 2^l full segments long
-        for (uint32_t l = 0; (1u << l) < kCrcThreads; l++) {
+        for (uint32_t l = 0; (1u << l) < kCrcWarps; l++) {
             const uint32_t s2 = 1u << l;
-            if ((tid & (2 * s2 - 1)) == 0) {
+            if (tid < kCrcWarps && (tid & (2 * s2 - 1)) == 0) {
                 const uint32_t left = segcrc[tid];
                 segcrc[tid] = (left ? multmodp(shiftop[l], left) : 0) ^ segcrc[tid + s2];
             }
@@ -308,12 +334,13 @@ cudaError_t launch_crc32(const uint8_t *d_buf, uint64_t len, uint32_t start, voi
     uint32_t tail_len = (uint32_t)((reinterpret_cast<uintptr_t>(d_buf) + len) & 15u);
     if (tail_len > len) tail_len = (uint32_t)len;
     const uint64_t main_len = len - tail_len;
-    // bytes per thread: enough segments to fill every SM once, at most 4 KiB (the combine tree costs ~2500 cycles per chunk)
-    uint64_t seg = (main_len + (uint64_t)n_sm * kCrcThreads - 1) / ((uint64_t)n_sm * kCrcThreads);
-    seg = (seg + 15) & ~15ull;
-    if (seg < 256) seg = 256;
-    if (seg > 4096) seg = 4096;
-    const uint64_t chunk = seg * kCrcThreads;
+    // bytes per warp segment: enough segments to fill every SM once, a multiple of the 512-byte row, 4 KiB .. 128 KiB (the combine
+    // epilogue of a chunk costs a few thousand cycles)
+    uint64_t seg = (main_len + (uint64_t)n_sm * kCrcWarps - 1) / ((uint64_t)n_sm * kCrcWarps);
+    seg = (seg + kCrcRow - 1) / kCrcRow * kCrcRow;
+    if (seg < 4096) seg = 4096;
+    if (seg > 131072) seg = 131072;
+    const uint64_t chunk = seg * kCrcWarps;
     const uint64_t nchunks = (main_len + chunk - 1) / chunk;
     if (nchunks * 4 > scratch_bytes) return cudaErrorInvalidValue;
     uint32_t *part = static_cast<uint32_t *>(d_scratch);
