@@ -200,42 +200,16 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
             continue;
         }
         if (m_pend && (__popc(m_pend) >= (int)thr || m_walk == 0)) {
-            // full compare: the first 32 bytes by the lane itself, the rest of a long candidate by the whole warp (cf. k_match)
-            uint32_t len = 0;
-            bool is_long = false;
             if (state == SS_PEND) {
-                uint32_t clen = 0, d0, d1;
+                uint32_t clen = 0, len;
                 const uint32_t pa = dadj + q, pb = dadj + cand;
                 for (;;) {
-                    d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
-                    d1 = qld_u32u(pa + clen + 4) ^ qld_u32u(pb + clen + 4);
-                    if ((d0 | d1) == 0 && clen + 8 < 32) { clen += 8; continue; }
+                    const uint32_t d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
+                    const uint32_t d1 = qld_u32u(pa + clen + 4) ^ qld_u32u(pb + clen + 4);
+                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
                     break;
                 }
-                if (d0 | d1) len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : clen + 4 + ((__ffs(d1) - 1) >> 3);
-                else is_long = true;
-            }
-            uint32_t m_long = __ballot_sync(0xffffffffu, is_long);
-            while (m_long) {
-                const uint32_t leader = __ffs(m_long) - 1;
-                m_long &= m_long - 1;
-                const uint32_t bq = __shfl_sync(0xffffffffu, q, leader), bc = __shfl_sync(0xffffffffu, cand, leader);
-                const uint32_t off = 32u + 8u * lane;
-                uint32_t idx = 8;
-                if (off < kMaxMatch) {
-                    const uint32_t e0 = qld_u32u(dadj + bq + off) ^ qld_u32u(dadj + bc + off);
-                    const uint32_t e1 = qld_u32u(dadj + bq + off + 4) ^ qld_u32u(dadj + bc + off + 4);
-                    idx = e0 ? (uint32_t)(__ffs(e0) - 1) >> 3 : e1 ? 4u + ((uint32_t)(__ffs(e1) - 1) >> 3) : 8u;
-                }
-                const uint32_t mm = __ballot_sync(0xffffffffu, idx < 8);
-                uint32_t ll = kMaxMatch;
-                if (mm) {
-                    const uint32_t src = __ffs(mm) - 1;
-                    ll = 32u + 8u * src + __shfl_sync(0xffffffffu, idx, src);
-                }
-                if (lane == leader) len = ll;
-            }
-            if (state == SS_PEND) {
                 if (len > kMaxMatch) len = kMaxMatch;
                 state = SS_WALK;
                 if (len > best) {
