@@ -44,6 +44,7 @@ def lib():
             getattr(L, f).argtypes = [ctypes.POINTER(ZoStream)] + [ctypes.c_int] * 4
         for f in ("zo_deflate", "zo_inflate", "zo_inflate_init"):
             getattr(L, f).argtypes = [ctypes.POINTER(ZoStream), ctypes.c_int]
+        L.zo_deflate_set_dictionary.argtypes = [ctypes.POINTER(ZoStream), ctypes.c_char_p, sz]
         for f in ("zo_deflate_end", "zo_inflate_end"):
             getattr(L, f).argtypes = [ctypes.POINTER(ZoStream)]
         _lib = L
@@ -65,6 +66,28 @@ def compress(data, level=6, window_bits=15, mem_level=8, strategy=0, flush=4):
     buf = ctypes.create_string_buffer(n.value)
     rc = lib().zo_compress_ex(buf, ctypes.byref(n), data, len(data), level, window_bits, mem_level, strategy, flush)
     return rc, buf.raw[: n.value]
+
+
+def compress_dict(data, dictionary, level=6, window_bits=15, mem_level=8, strategy=0):
+    """deflateInit2 + deflateSetDictionary (deflate.rs:498-564) + one deflate(Z_FINISH). Returns (rc, bytes, dictid/adler)."""
+    L = lib()
+    s = ZoStream()
+    assert L.zo_deflate_init(ctypes.byref(s), level, window_bits, mem_level, strategy) == 0
+    rc = L.zo_deflate_set_dictionary(ctypes.byref(s), bytes(dictionary), len(dictionary))
+    if rc != 0:
+        L.zo_deflate_end(ctypes.byref(s))
+        return rc, b"", 0
+    dictid = s.adler
+    data = bytes(data)
+    src = ctypes.create_string_buffer(data, len(data)) if data else ctypes.create_string_buffer(1)
+    cap = len(data) + (len(data) >> 3) + 1024
+    obuf = ctypes.create_string_buffer(cap)
+    s.next_in, s.avail_in = ctypes.addressof(src), len(data)
+    s.next_out, s.avail_out = ctypes.addressof(obuf), cap
+    rc = L.zo_deflate(ctypes.byref(s), 4)
+    out = obuf.raw[: cap - s.avail_out]
+    L.zo_deflate_end(ctypes.byref(s))
+    return (0 if rc == 1 else rc), out, dictid
 
 
 def uncompress(data, out_cap):

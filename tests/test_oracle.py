@@ -243,3 +243,22 @@ def test_calgary_mix_generator_is_pinned():
     assert len(d) == CALGARY_MIX_BYTES  # the hash is asserted inside the generator
     rc, out = O.compress(d[: 8 << 20], 9)
     assert rc == 0 and zlib.decompress(out) == d[: 8 << 20]
+
+
+def test_set_dictionary_restatement_against_stock_zlib():
+    """deflate::set_dictionary (zlib-rs/src/deflate.rs:498-564) in the oracle: streams inflate with the dictionary under stock zlib
+    (all dictionary lengths incl. >= 32 KiB and >= 64 KiB), DICTID is the dictionary's adler32, and the reference test's own
+    case (test-libz-rs-sys/src/deflate.rs:862-900: "hello" / "hello, hello!\\0") gives the bytes stock zlib gives.
+    The GPU engine does not take dictionaries yet (deflateSetDictionary returns Z_STREAM_ERROR); this pins the checker for that row."""
+    import zlib
+    from corpus import silesia_member
+    m = silesia_member(3)
+    for dl in (5, 1000, 32768, 40000, 70000):
+        dic, data = m[:dl], m[dl:dl + 100000]
+        for level in (0, 1, 2, 6, 9):
+            rc, out, did = O.compress_dict(data, dic, level)
+            assert rc == 0 and did == zlib.adler32(dic)
+            assert zlib.decompressobj(zdict=dic).decompress(out) == data, (dl, level)
+    rc, out, did = O.compress_dict(b"hello, hello!\0", b"hello", 6)
+    c = zlib.compressobj(6, zdict=b"hello")
+    assert out == c.compress(b"hello, hello!\0") + c.flush()
