@@ -135,8 +135,8 @@ __device__ __forceinline__ uint32_t x2nmodp(uint64_t n, uint32_t k)
 // k_crc_partial.  Byte-sliced table CRC costs one shared-memory lookup per input byte; what else the L1/shared pipe has to do decides
 // the speed (ncu, profiles/r02c: with one contiguous segment per THREAD every 128-bit load touches 32 different lines -- 32 tag
 // cycles per 512 bytes next to the 16 lookup wavefronts).  This version:
-//  * conflict-free lookups: every lane owns a private copy of the four slice tables in its own bank (entry (k, idx) of lane t at
-//    word (k*256 + idx)*32 + t, 128 KiB per CTA, 32 KiB aligned so that the entry offset is OR-ed into the address);
+//  * conflict-free lookups: every lane owns a private copy of the four slice tables in its own bank (128 KiB per CTA), laid out so
+//    that a lookup address is one byte-permute of the data word into the table base (crc_lds);
 //  * coalesced loads: a WARP owns a contiguous segment and reads it in rows of 512 bytes, lane t taking words 4t..4t+3.  A lane runs
 //    four independent registers, one per word column: register i sees every 128th word, so its step is R = (R ^ w) * x^4096 -- the
 //    slice tables are those of x^4096 instead of x^32, nothing else changes.  At the end of the segment register i is corrected by
@@ -148,23 +148,23 @@ __device__ __forceinline__ uint32_t x2nmodp(uint64_t n, uint32_t k)
 constexpr uint32_t kCrcThreads = 1024;
 constexpr uint32_t kCrcWarps = kCrcThreads / 32;
 constexpr uint32_t kCrcRow = 512;
-constexpr uint32_t kCrcTabBytes = 4 * 256 * 32 * 4 + 32768; // + slack to align the tables to 32 KiB in the shared window
+constexpr uint32_t kCrcTabBytes = 4 * 256 * 32 * 4 + 65536; // + slack to align the tables to 64 KiB in the shared window
 
-template <uint32_t KOFF, uint32_t SHIFT>
-__device__ __forceinline__ uint32_t crc_lds(uint32_t tb, uint32_t x)
+// Table layout: slice k (byte k of the word), entry idx, lane t at  base + (k >> 1) * 65536 + idx * 256 + (k & 1) * 128 + t * 4
+// with base 64 KiB aligned.  The bank is t whatever idx and k are, and the address is the base register with its second byte replaced
+// by the data byte: ONE byte-permute per lookup (PRMT {b3, b2, x_k, b0}), the slice pair offset rides in the LDS immediate.
+template <uint32_t K>
+__device__ __forceinline__ uint32_t crc_lds(uint32_t b_even, uint32_t b_odd, uint32_t x)
 {
-    // table word of byte ((x >> SHIFT*8) & 0xff) of slice KOFF/32768.  tb = 32 KiB-aligned table base | lane*4, so the entry offset
-    // (idx * 128, bits 7..14) is OR-ed in: one shift + one LOP3 per lookup; the slice offset rides in the LDS immediate
     uint32_t v;
-    const uint32_t sh = SHIFT == 0 ? x << 7 : SHIFT == 1 ? x >> 1 : SHIFT == 2 ? x >> 9 : x >> 17;
-    const uint32_t a = (sh & 0x7f80u) | tb;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(KOFF));
+    const uint32_t a = __byte_perm(x, (K & 1u) ? b_odd : b_even, 0x7604u | (K << 4));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"((K >> 1) * 65536u));
     return v;
 }
 // x * x^4096 for a 32-bit x, sliced by bytes
-__device__ __forceinline__ uint32_t crc_far(uint32_t tb, uint32_t x)
+__device__ __forceinline__ uint32_t crc_far(uint32_t b_even, uint32_t b_odd, uint32_t x)
 {
-    return crc_lds<0u, 0>(tb, x) ^ crc_lds<32768u, 1>(tb, x) ^ crc_lds<2u * 32768u, 2>(tb, x) ^ crc_lds<3u * 32768u, 3>(tb, x);
+    return crc_lds<0>(b_even, b_odd, x) ^ crc_lds<1>(b_even, b_odd, x) ^ crc_lds<2>(b_even, b_odd, x) ^ crc_lds<3>(b_even, b_odd, x);
 }
 
 __global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__restrict__ buf, uint64_t main_len, uint32_t wseg, uint32_t nchunks,
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__re
 {
     extern __shared__ __align__(16) uint8_t crc_smem[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(crc_smem);
-    const uint32_t tab_base = (smem_base + 32767u) & ~32767u;
-    uint32_t *tab = reinterpret_cast<uint32_t *>(crc_smem + (tab_base - smem_base)); // [4][256][32], 32 KiB aligned
+    const uint32_t tab_base = (smem_base + 65535u) & ~65535u;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(crc_smem + (tab_base - smem_base)); // 128 KiB, 64 KiB aligned (layout at crc_lds)
     __shared__ uint32_t t0[256];      // the ordinary byte table (ragged heads)
     __shared__ uint32_t cfix[128];    // x^(-32 i)
     __shared__ uint32_t segcrc[kCrcWarps];
@@ -191,10 +191,11 @@ __global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__re
         const uint32_t x4096 = x2nmodp(128, 5);
         const uint32_t k = tid >> 8, b = tid & 255;
         const uint32_t v = b ? multmodp(x4096, b << (8 * k)) : 0;
-        for (uint32_t l = 0; l < 32; l++) tab[(k * 256 + b) * 32 + l] = v;
+        uint32_t *e = tab + ((k >> 1) * 65536u + b * 256u + (k & 1u) * 128u) / 4u;
+        for (uint32_t l = 0; l < 32; l++) e[l] = v;
     }
     __syncthreads();
-    const uint32_t tb = tab_base | (lane * 4u);
+    const uint32_t tb = tab_base | (lane * 4u), tb1 = tb | 128u;
     const uint64_t chunk = (uint64_t)wseg * kCrcWarps;
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         // chunk j covers [E - (nchunks-j)*C, E - (nchunks-j-1)*C) clipped at 0
@@ -220,14 +221,14 @@ __global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__re
             for (; r + 4 <= rows; r += 4) { // four rows in flight
                 const uint4 a = __ldg(rp + (size_t)r * 32), b = __ldg(rp + (size_t)(r + 1) * 32);
                 const uint4 c = __ldg(rp + (size_t)(r + 2) * 32), d = __ldg(rp + (size_t)(r + 3) * 32);
-                r0 = crc_far(tb, r0 ^ a.x); r1 = crc_far(tb, r1 ^ a.y); r2 = crc_far(tb, r2 ^ a.z); r3 = crc_far(tb, r3 ^ a.w);
-                r0 = crc_far(tb, r0 ^ b.x); r1 = crc_far(tb, r1 ^ b.y); r2 = crc_far(tb, r2 ^ b.z); r3 = crc_far(tb, r3 ^ b.w);
-                r0 = crc_far(tb, r0 ^ c.x); r1 = crc_far(tb, r1 ^ c.y); r2 = crc_far(tb, r2 ^ c.z); r3 = crc_far(tb, r3 ^ c.w);
-                r0 = crc_far(tb, r0 ^ d.x); r1 = crc_far(tb, r1 ^ d.y); r2 = crc_far(tb, r2 ^ d.z); r3 = crc_far(tb, r3 ^ d.w);
+                r0 = crc_far(tb, tb1, r0 ^ a.x); r1 = crc_far(tb, tb1, r1 ^ a.y); r2 = crc_far(tb, tb1, r2 ^ a.z); r3 = crc_far(tb, tb1, r3 ^ a.w);
+                r0 = crc_far(tb, tb1, r0 ^ b.x); r1 = crc_far(tb, tb1, r1 ^ b.y); r2 = crc_far(tb, tb1, r2 ^ b.z); r3 = crc_far(tb, tb1, r3 ^ b.w);
+                r0 = crc_far(tb, tb1, r0 ^ c.x); r1 = crc_far(tb, tb1, r1 ^ c.y); r2 = crc_far(tb, tb1, r2 ^ c.z); r3 = crc_far(tb, tb1, r3 ^ c.w);
+                r0 = crc_far(tb, tb1, r0 ^ d.x); r1 = crc_far(tb, tb1, r1 ^ d.y); r2 = crc_far(tb, tb1, r2 ^ d.z); r3 = crc_far(tb, tb1, r3 ^ d.w);
             }
             for (; r < rows; r++) {
                 const uint4 a = __ldg(rp + (size_t)r * 32);
-                r0 = crc_far(tb, r0 ^ a.x); r1 = crc_far(tb, r1 ^ a.y); r2 = crc_far(tb, r2 ^ a.z); r3 = crc_far(tb, r3 ^ a.w);
+                r0 = crc_far(tb, tb1, r0 ^ a.x); r1 = crc_far(tb, tb1, r1 ^ a.y); r2 = crc_far(tb, tb1, r2 ^ a.z); r3 = crc_far(tb, tb1, r3 ^ a.w);
             }
             // register i = 4*lane + k has every word one factor x^4096 too high by x^(32 i)
             uint32_t acc = 0;
