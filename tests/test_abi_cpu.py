@@ -93,3 +93,19 @@ def test_null_buffer_checksums_and_combine_algebra():
             Lo.zo_adler32_combine(a % 65521 | ((a >> 16) % 65521) << 16, b % 65521 | ((b >> 16) % 65521) << 16, n)
     assert L.zError(-3) == b"data error" and L.zError(-5) == b"buffer error"
     assert L.compressBound(0) >= 13 and L.compressBound(1 << 20) >= (1 << 20) + 13
+
+
+def test_c_client_links_and_fails_loudly_without_a_device(tmp_path):
+    """tests/c_client/pipe_client.c: a plain C program (header + -lz_b200) with zpipe's call sequence.  Without a CUDA device
+    deflateInit returns Z_MEM_ERROR ("no CUDA device") -- never a CPU path; on the GPU box the same binary round-trips a file
+    (tests/test_gpu_parity.py::test_c_client_round_trip)."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "tests", "c_client")], stdout=subprocess.DEVNULL)
+    import torch
+    if torch.cuda.is_available():
+        return
+    f = tmp_path / "in.bin"
+    f.write_bytes(b"hello hello hello" * 100)
+    r = subprocess.run([os.path.join(root, "tests", "c_client", "_build", "pipe_client"), str(f)], capture_output=True, text=True)
+    assert r.returncode == 77 and "no CUDA device" in r.stderr

@@ -440,3 +440,17 @@ def test_streaming_inflate():
         assert got or z.eof
         out += got
     assert bytes(out) == d and z.adler == zlib.adler32(d)
+
+
+def test_c_client_round_trip(tmp_path):
+    """A C program that only knows include/zlib_b200.h and -lz_b200 (tests/c_client/pipe_client.c, zpipe's call sequence)."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    subprocess.check_call(["make", "-C", os.path.join(root, "tests", "c_client")], stdout=subprocess.DEVNULL)
+    d = silesia_member(4)[:700000]
+    f = tmp_path / "in.bin"
+    f.write_bytes(d)
+    for level in (6, 1, 9):
+        r = subprocess.run([os.path.join(root, "tests", "c_client", "_build", "pipe_client"), str(f), str(level)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert ("out=%d " % len(O.compress(d, level)[1])) in r.stdout and ("adler=%08x" % zlib.adler32(d)) in r.stdout
