@@ -217,14 +217,21 @@ __global__ void __launch_bounds__(kCrcThreads) k_crc_partial(const uint8_t *__re
             const uint4 *rp = reinterpret_cast<const uint4 *>(buf + sbeg + head) + lane; // 16-byte aligned: E-anchored rows
             uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
             uint32_t r = 0;
+            // four rows per step, the next four already in flight (a warp has nothing else to overlap its loads with)
+            uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a, d = a;
+            if (rows >= 4) { a = __ldg(rp); b = __ldg(rp + 32); c = __ldg(rp + 64); d = __ldg(rp + 96); }
 #pragma unroll 1
-            for (; r + 4 <= rows; r += 4) { // four rows in flight
-                const uint4 a = __ldg(rp + (size_t)r * 32), b = __ldg(rp + (size_t)(r + 1) * 32);
-                const uint4 c = __ldg(rp + (size_t)(r + 2) * 32), d = __ldg(rp + (size_t)(r + 3) * 32);
+            for (; r + 4 <= rows; r += 4) {
+                uint4 na = a, nb = b, nc = c, nd = d;
+                if (r + 8 <= rows) {
+                    const uint4 *np = rp + (size_t)(r + 4) * 32;
+                    na = __ldg(np); nb = __ldg(np + 32); nc = __ldg(np + 64); nd = __ldg(np + 96);
+                }
                 r0 = crc_far(tb, tb1, r0 ^ a.x); r1 = crc_far(tb, tb1, r1 ^ a.y); r2 = crc_far(tb, tb1, r2 ^ a.z); r3 = crc_far(tb, tb1, r3 ^ a.w);
                 r0 = crc_far(tb, tb1, r0 ^ b.x); r1 = crc_far(tb, tb1, r1 ^ b.y); r2 = crc_far(tb, tb1, r2 ^ b.z); r3 = crc_far(tb, tb1, r3 ^ b.w);
                 r0 = crc_far(tb, tb1, r0 ^ c.x); r1 = crc_far(tb, tb1, r1 ^ c.y); r2 = crc_far(tb, tb1, r2 ^ c.z); r3 = crc_far(tb, tb1, r3 ^ c.w);
                 r0 = crc_far(tb, tb1, r0 ^ d.x); r1 = crc_far(tb, tb1, r1 ^ d.y); r2 = crc_far(tb, tb1, r2 ^ d.z); r3 = crc_far(tb, tb1, r3 ^ d.w);
+                a = na; b = nb; c = nc; d = nd;
             }
             for (; r < rows; r++) {
                 const uint4 a = __ldg(rp + (size_t)r * 32);
