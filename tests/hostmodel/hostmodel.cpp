@@ -164,7 +164,7 @@ static void put_bits(std::vector<uint8_t> &out, uint64_t bitpos, uint64_t val, u
 // syms -> blocks -> trees -> bit stream.  blockB(b): window base when block b is flushed.  quick: one static block cut into pieces.
 template <class BF>
 static int encode_stream(const uint8_t *data, uint32_t N, int level, const std::vector<Sym> &syms, BF &&blockB, bool quick, bool fixed, uint32_t block_syms,
-                         uint8_t *dst, uint32_t cap, uint32_t *out_len, int *data_type_out)
+                         uint8_t *dst, uint32_t cap, uint32_t *out_len, int *data_type_out, uint32_t cinfo = 7)
 {
     // ---- blocks ----
     HuffTables T;
@@ -199,7 +199,7 @@ static int encode_stream(const uint8_t *data, uint32_t N, int level, const std::
     // ---- scan + pack ----
     std::vector<uint8_t> out(2, 0);
     uint32_t lf = (level < 2 || fixed) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3; // deflate.rs:1591-1601
-    uint32_t h = ((8 + (7 << 4)) << 8) | (lf << 6);
+    uint32_t h = ((8 + (cinfo << 4)) << 8) | (lf << 6);
     h += 31 - (h % 31);
     out[0] = (uint8_t)(h >> 8); out[1] = (uint8_t)h;
     uint64_t bit = 16;
@@ -475,4 +475,64 @@ extern "C" int hm_deflate_low(const uint8_t *data, uint32_t N, int level, int fi
     const uint32_t finalB = run_low(data, N, level, block_syms, syms, blockB);
     return encode_stream(data, N, level, syms, [&](uint32_t b, const BlockDesc &bd) { return (bd.last || b >= blockB.size()) ? finalB : blockB[b]; }, level == 1,
                          fixed != 0, level == 1 ? kBlockSyms : block_syms, dst, cap, out_len, data_type_out);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Windows smaller than 32 KiB: serial_medium with the DynWin policy over the whole input (what k_tail runs for inputs that fit it).
+// ------------------------------------------------------------------------------------------
+struct WinAcc {
+    const uint8_t *data; uint32_t N, w; const uint16_t *L; const uint32_t *holes;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 2 * w) return 0; y -= w; }
+        return data[y];
+    }
+    uint32_t link(uint32_t y) const { return y + 4 <= N ? L[y] : 0; }
+    bool inserted(uint32_t y) const { return !((holes[y >> 5] >> (y & 31)) & 1u); }
+};
+
+static uint32_t run_small_window(const uint8_t *data, uint32_t N, int level, int wbits, std::vector<Sym> &syms, std::vector<uint32_t> &symB)
+{
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), ins((N >> 5) + 2, 0);
+    WinAcc a{data, N, 1u << wbits, L.data(), holes.data()};
+    return serial_medium(a, N, 0, ins.data(), (uint32_t)ins.size(), level_params(level),
+                         [&](Sym s, uint32_t B) { syms.push_back(s); symB.push_back(B); }, DynWin{1u << wbits});
+}
+
+extern "C" int hm_oracle_trace_w(const uint8_t *data, uint32_t N, int level, int wbits, int mem_level, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    zo_stream s;
+    memset(&s, 0, sizeof s);
+    if (zo_deflate_init(&s, level, wbits, mem_level, 0) != 0) return -1;
+    TraceCtx t{out, cap, 0};
+    zo_deflate_set_trace(&s, trace_cb, &t);
+    std::vector<uint8_t> dst(zo_compress_bound(N) + N / 4 + 1024);
+    s.next_in = data; s.avail_in = N; s.next_out = dst.data(); s.avail_out = (uint32_t)dst.size();
+    int rc = zo_deflate(&s, ZO_FINISH);
+    zo_deflate_end(&s);
+    *nsyms = t.n;
+    return rc == ZO_STREAM_END ? 0 : -2;
+}
+
+extern "C" int hm_parse_small_window(const uint8_t *data, uint32_t N, int level, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    std::vector<Sym> syms;
+    std::vector<uint32_t> symB;
+    run_small_window(data, N, level, wbits, syms, symB);
+    for (size_t i = 0; i < syms.size() && i < cap; i++) out[i] = SymOut{syms[i].pos, syms[i].dist, syms[i].lc};
+    *nsyms = (uint32_t)syms.size();
+    return 0;
+}
+
+extern "C" int hm_deflate_small_window(const uint8_t *data, uint32_t N, int level, int wbits, int mem_level, uint8_t *dst, uint32_t cap,
+                                       uint32_t *out_len, int *data_type_out)
+{
+    const uint32_t block_syms = (1u << (mem_level + 6)) - 1;
+    std::vector<Sym> syms;
+    std::vector<uint32_t> symB;
+    const uint32_t finalB = run_small_window(data, N, level, wbits, syms, symB);
+    return encode_stream(data, N, level, syms, [&](uint32_t, const BlockDesc &bd) { return bd.last ? finalB : symB[bd.sym_begin + bd.sym_count - 1]; },
+                         false, false, block_syms, dst, cap, out_len, data_type_out, (uint32_t)(wbits - 8));
 }

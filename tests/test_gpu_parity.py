@@ -212,11 +212,13 @@ def test_reference_golden_vectors_all_one_shot(v, eng):
     d = bytes.fromhex(v["input_hex"])
     out, res = eng.deflate(d, level=v["level"], strategy=v["strategy"], window_bits=v["window_bits"], mem_level=v["mem_level"])
     wb = v["window_bits"] - 16 if v["window_bits"] > 15 else abs(v["window_bits"])
+    lvl = 6 if v["level"] == -1 else v["level"]
     fits = len(d) + 262 <= (1 << max(wb, 9))
-    assert res.exact_parity == (1 if fits else 0)
-    if fits:
+    serial = 3 <= lvl <= 6 and v["strategy"] in (0, 1, 4) and len(d) <= 32000  # hash_calc_difference, longest_match_difference
+    assert res.exact_parity == (1 if fits or serial else 0)
+    if fits or serial:
         assert out == bytes.fromhex(v["expected_hex"])
-    else:  # hash_calc_difference, longest_match_difference: 512-byte windows that slide
+    else:  # fill_window_out_of_bounds: Z_HUFFMAN_ONLY with a 512-byte window and 765 bytes
         assert zlib.decompress(out, v["window_bits"] if v["window_bits"] > 15 else 15) == d
 
 
@@ -272,8 +274,25 @@ def test_small_windows_that_fit_are_exact(eng):
         for level in (0, 1, 2, 6, 9):
             out, res = eng.deflate(d, level=level, window_bits=wb)
             assert res.exact_parity == 1 and out == O.compress(d, level, wb)[1], (wb, level)
-        out, res = eng.deflate(d + b"x", level=6, window_bits=wb)  # one byte more: 32 KiB engine, CINFO 7, still a valid stream
+        out, res = eng.deflate(d + b"x", level=9, window_bits=wb)  # one byte more: 32 KiB engine, CINFO 7, still a valid stream
         assert res.exact_parity == 0 and zlib.decompress(out) == d + b"x"
+
+
+def test_small_windows_serial_path_levels_3_to_6(eng):
+    """windowBits 9..14 with inputs that slide the window: levels 3..6 run the exact serial simulator (k_tail, DynWin) when the input
+    fits it (<= 32000 bytes) -- the case of the reference's hash_calc_difference / longest_match_difference vectors."""
+    for wb in (9, 10, 12, 14):
+        for src in (synthetic_mix(31000, wb), silesia_member(9)[:30000], silesia_member(1)[2000:33000], bytes(20000)):
+            for n in (len(src), 5000, 700):
+                d = src[:n]
+                for level in (3, 4, 6):
+                    out, res = eng.deflate(d, level=level, window_bits=wb)
+                    assert res.exact_parity == 1 and out == O.compress(d, level, wb)[1], (wb, n, level)
+    d = silesia_member(9)[:30000]
+    assert eng.deflate(d, level=6, window_bits=-10)[0] == O.compress(d, 6, -10)[1]
+    assert eng.deflate(d, level=5, window_bits=26, mem_level=5)[0] == O.compress(d, 5, 26, 5)[1]
+    z = Z.Deflate(6, window_bits=9)
+    assert z.deflate(d, Z.Z_FINISH) == O.compress(d, 6, 9)[1]
 
 
 def test_other_levels_and_strategies_valid_streams(eng):

@@ -132,3 +132,25 @@ def test_low_levels_serial_restatement(level):
     for mem in (1, 4, 9):
         assert _deflate_low(d, level, 0, mem) == O.compress(d, level, 15, mem, 0)[1]
     assert _deflate_low(d, level, 1) == O.compress(d, level, 15, 8, 4)[1]  # Z_FIXED
+
+
+def test_small_window_serial_path():
+    """serial_medium with the DynWin policy (what k_tail runs for windowBits 9..14 when the input slides the window and fits the serial
+    path): symbols and bytes equal the oracle's, and the reference's two small-window vectors are reproduced."""
+    import json
+    def dfl(data, level, wbits, mem=8):
+        cap = len(data) + len(data) // 4 + 1024
+        buf = ctypes.create_string_buffer(cap)
+        n, dt = ctypes.c_uint32(0), ctypes.c_int(0)
+        assert H().hm_deflate_small_window(data, len(data), level, wbits, mem, buf, cap, ctypes.byref(n), ctypes.byref(dt)) == 0
+        return buf.raw[: n.value]
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+    for v in kat["vectors"]:
+        if v["name"] in ("hash_calc_difference", "longest_match_difference"):
+            assert dfl(bytes.fromhex(v["input_hex"]), v["level"], max(v["window_bits"], 9), v["mem_level"]) == bytes.fromhex(v["expected_hex"])
+    for wb in (9, 11, 14):
+        for src in (synthetic_mix(31000, wb), silesia_member(9)[:30000], silesia_member(2)[:31000]):
+            for n in (len(src), 700):
+                for level in (3, 4, 5, 6):
+                    d = src[:n]
+                    assert dfl(d, level, wb) == O.compress(d, level, wb)[1], (wb, n, level)

@@ -62,6 +62,22 @@ ZB_HD LevelParams level_params(int level)
 
 ZB_HD uint32_t hash_u32(uint32_t v) { return (v * 2654435761u) >> 16; }
 
+// Window size policy.  The parallel kernels only know the 32 KiB window (FullWin: compile-time constants); the serial simulator
+// also runs with a smaller window (DynWin; windowBits 9..14, deflate.rs:286-321) for inputs that fit the serial path.
+struct FullWin {
+    ZB_HD uint32_t wsize() const { return kWSize; }
+    ZB_HD uint32_t maxdist() const { return kMaxDist; }
+    ZB_HD uint32_t t0() const { return kT0; }
+};
+struct DynWin {
+    uint32_t w;
+    ZB_HD uint32_t wsize() const { return w; }
+    ZB_HD uint32_t maxdist() const { return w - kMinLookahead; }
+    ZB_HD uint32_t t0() const { return 2 * w - kMinLookahead; }
+};
+template <class WN>
+ZB_HD uint32_t wbase_w(const WN &wn, uint32_t p) { return p <= wn.t0() ? 0u : wn.wsize() * (1u + (p - wn.t0() - 1u) / wn.wsize()); }
+
 // Window base (absolute) in force at a loop-top at absolute position p, after that loop-top's
 // fill_window check (deflate.rs:1776-1806): slides happen at the first loop-top beyond base+65274.
 ZB_HD uint32_t wbase(uint32_t p) { return p <= kT0 ? 0u : kWSize * (1u + (p - kT0 - 1u) / kWSize); }
@@ -88,8 +104,8 @@ struct Match {
 
 // longest_match (non-SLOW variant, longest_match.rs:15-350) at absolute position x.  `cap` is
 // state.lookahead at the time (:262-264).  Initial best_len is 2 (prev_length is always 0 here).
-template <class A>
-ZB_HD Match lm_walk(const A &a, uint32_t x, uint32_t cap, const LevelParams &lp)
+template <class A, class WN = FullWin>
+ZB_HD Match lm_walk(const A &a, uint32_t x, uint32_t cap, const LevelParams &lp, const WN wn = WN())
 {
     Match r{0, 0};
     uint32_t best = 2;
@@ -101,7 +117,7 @@ ZB_HD Match lm_walk(const A &a, uint32_t x, uint32_t cap, const LevelParams &lp)
         if (d == 0) break;
         cur -= d;
         uint32_t dist = x - cur;
-        if (dist > (first ? kMaxDist : kMaxDist - 1)) break; // medium.rs:76 / longest_match.rs:44,84
+        if (dist > (first ? wn.maxdist() : wn.maxdist() - 1)) break; // medium.rs:76 / longest_match.rs:44,84
         if (cur == 0) break;                                   // window index 0 is never matched
         if (!a.inserted(cur)) continue;                        // a hole is not on the chain
         first = false;
@@ -144,15 +160,15 @@ struct PMatch {
 };
 
 // fizzle_matches (medium.rs:264-331).  B = window base in force.  Returns true when committed.
-template <class A>
-ZB_HD bool fizzle(const A &a, uint32_t B, PMatch &current, PMatch &next)
+template <class A, class WN = FullWin>
+ZB_HD bool fizzle(const A &a, uint32_t B, PMatch &current, PMatch &next, const WN wn = WN())
 {
     if (current.len <= 1) return false;
     if (current.len > 1 + (next.ms - B)) return false;
     if (current.len > 1 + (next.ss - B)) return false;
     if (a.byte(next.ms + 1 - current.len) != a.byte(next.ss + 1 - current.len)) return false;
     uint32_t nsw = next.ss - B;
-    uint32_t limit = B + (nsw > kMaxDist ? nsw - kMaxDist : 0);
+    uint32_t limit = B + (nsw > wn.maxdist() ? nsw - wn.maxdist() : 0);
     PMatch c = current, n = next;
     uint32_t changed = 0;
     for (;;) {
@@ -263,27 +279,28 @@ struct SerialAcc {
 };
 
 // Returns the window base in force when the final block is flushed (needed for the stored-block rule).
-template <class SA, class E>
+template <class SA, class E, class WN = FullWin>
 ZB_HDN uint32_t serial_medium(const SA &a0, uint32_t N, uint32_t p0, uint32_t *ins_bitmap, uint32_t ins_words,
-                              const LevelParams &lp, E &&emit)
+                              const LevelParams &lp, E &&emit, const WN wn = WN())
 {
+    const uint32_t kW = wn.wsize(), kMD = wn.maxdist(), kT = wn.t0();
     SerialAcc<SA> a{a0, p0, ins_words, ins_bitmap};
     for (uint32_t i = 0; i < ins_words; i++) ins_bitmap[i] = 0;
     // window state at a canonical mid-stream loop-top p0 (before its own fill check)
     // window state as left by the previous loop-top (see DESIGN.md "window schedule"): the base of p0-1
     // is either the true pre-check base or already the post-check one; both give the same state after
     // p0's own fill_window check below.
-    uint32_t B = p0 == 0 ? 0 : wbase(p0 - 1);
-    uint32_t F = (uint64_t)B + 2 * kWSize < N ? B + 2 * kWSize : N;
+    uint32_t B = p0 == 0 ? 0 : wbase_w(wn, p0 - 1);
+    uint32_t F = (uint64_t)B + 2 * kW < N ? B + 2 * kW : N;
     uint32_t p = p0;
     PMatch cur{0, 0, 0, 0}, next{0, 0, 0, 0};
     for (;;) {
         uint32_t lookahead = F - p;
         if (lookahead < kMinLookahead) {
             // fill_window (deflate.rs:1776-1861)
-            if (p - B >= kWSize + kMaxDist) B += kWSize;
+            if (p - B >= kW + kMD) B += kW;
             if (F < N) {
-                F = (uint64_t)B + 2 * kWSize < N ? B + 2 * kWSize : N;
+                F = (uint64_t)B + 2 * kW < N ? B + 2 * kW : N;
                 // quick_insert_string(strstart-1) (deflate.rs:1836-1838).  p-1 is the last byte of the previous
                 // symbol and already the head of its bucket, EXCEPT when a 258-byte match started exactly at
                 // base+65274: insert_match skipped it (lookahead 262 <= 258+4, medium.rs:212) and this call
@@ -305,7 +322,7 @@ ZB_HDN uint32_t serial_medium(const SA &a0, uint32_t N, uint32_t p0, uint32_t *i
                 bool already = a.inserted(p); // quick_insert_string returns head == p: dist 0 -> literal
                 a.set_inserted(p);
                 if (!already) {
-                    Match m = lm_walk(a, p, lookahead, lp);
+                    Match m = lm_walk(a, p, lookahead, lp, wn);
                     if (m.len >= 4) { cur.len = m.len; cur.ms = m.start; }
                 }
             }
@@ -333,7 +350,7 @@ ZB_HDN uint32_t serial_medium(const SA &a0, uint32_t N, uint32_t p0, uint32_t *i
             }
         }
         // look ahead one (medium.rs:103-153)
-        if (!lp.early_exit && lookahead > kMinLookahead && (cur.ss + cur.len - B) < kT0) {
+        if (!lp.early_exit && lookahead > kMinLookahead && (cur.ss + cur.len - B) < kT) {
             uint32_t ns = cur.ss + cur.len;
             bool already = a.inserted(ns);
             a.set_inserted(ns);
@@ -341,11 +358,11 @@ ZB_HDN uint32_t serial_medium(const SA &a0, uint32_t N, uint32_t p0, uint32_t *i
             next.ms = 0;
             next.len = 1;
             if (!already) {
-                Match m = lm_walk(a, ns, lookahead, lp);
+                Match m = lm_walk(a, ns, lookahead, lp, wn);
                 if (m.len >= 4) {
                     next.len = m.len;
                     next.ms = m.start;
-                    fizzle(a, B, cur, next);
+                    fizzle(a, B, cur, next, wn);
                 }
             }
         } else {

@@ -275,6 +275,16 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const bool small_ok = wb_eff < 15 && (uint64_t)N + kMinLookahead <= (1ull << wb_eff);
     bool exact = wb_eff == 15 || small_ok;
     jb.cinfo = small_ok ? (uint32_t)(wb_eff - 8) : 7u;
+    jb.wsize = kWSize;
+    // A small window that the input does leave: levels 3..6 run the exact serial simulator over the whole input when it fits
+    // k_tail's range (one thread, ~3 MB/s) -- the reference's own small-window vectors are of this kind.
+    const bool serial_win = wb_eff < 15 && !small_ok && N <= 32000u && level >= 3 && level <= 6 && strategy != 2 && strategy != 3;
+    if (serial_win) {
+        jb.wsize = 1u << wb_eff;
+        jb.cinfo = (uint32_t)(wb_eff - 8);
+        jb.tail_start = 0;
+        exact = true;
+    }
     if (level != 0 && !jb.huffman_only) {
         if (level < 3 && !serial_low) { eng_level = 3; exact = strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
         if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level

@@ -807,8 +807,24 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
 // ------------------------------------------------------------------------------------------------
 // k_tail: exact serial simulation from the tail entry to the end of the stream (one thread).
 // ------------------------------------------------------------------------------------------------
+struct GAccW { // GAcc with a window smaller than 32 KiB: only what the window buffer holds behind the input differs
+    GAcc g;
+    uint32_t w;
+    __device__ __forceinline__ uint32_t byte(uint32_t y) const
+    {
+        while (y >= g.N) {
+            if (y < 2 * w) return 0;
+            y -= w;
+        }
+        return g.data[y];
+    }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { return g.link(y); }
+    __device__ __forceinline__ bool inserted(uint32_t y) const { return g.inserted(y); }
+};
+
 // One thread: the loop is a chain of dependent instructions, so it runs at the issue latency of a single thread whatever memory
 // it reads (staging the window in shared memory was measured slower: more address arithmetic on the same chain).
+// With jb.wsize < 32 KiB the whole (small) input is parsed here with that window (windowBits 9..14, deflate.rs:286-321).
 __global__ void __launch_bounds__(32) k_tail(JobBufs jb)
 {
     __shared__ uint32_t ins[1024];
@@ -820,11 +836,14 @@ __global__ void __launch_bounds__(32) k_tail(JobBufs jb)
     Sym *syms = jb.syms + n_mid;
     uint32_t *sb = jb.sym_base;
     if (jb.N - p0 > 1024u * 32u - 64u) { atomicOr(&jb.info->error, 4u); return; }
-    const uint32_t fb = serial_medium(a, jb.N, p0, ins, 1024u, jb.lp, [&](const Sym &s, uint32_t B) {
+    auto emit = [&](const Sym &s, uint32_t B) {
         syms[k] = s;
         sb[k] = B;
         k++;
-    });
+    };
+    uint32_t fb;
+    if (jb.wsize == kWSize) fb = serial_medium(a, jb.N, p0, ins, 1024u, jb.lp, emit);
+    else fb = serial_medium(GAccW{a, jb.wsize}, jb.N, p0, ins, 1024u, jb.lp, emit, DynWin{jb.wsize});
     jb.info->n_syms = n_mid + k;
     jb.info->final_base = fb;
     jb.info->n_blocks = (n_mid + k) / jb.block_syms + 1;

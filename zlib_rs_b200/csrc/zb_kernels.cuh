@@ -93,6 +93,7 @@ struct JobBufs {
     uint32_t block_syms;      // symbols per deflate block: lit_bufsize - 1 = (1 << (memLevel + 6)) - 1 (deflate.rs:321, sym_buf.rs:23)
     uint32_t serial_mode;     // 1: deflate_quick (level 1), 2: deflate_fast (level 2) -- k_serial_low, zb_serial.h
     uint32_t *block_base;     // serial levels: window base in force when block b was flushed
+    uint32_t wsize;           // window size of the serial small-window path (k_tail over the whole input), kWSize otherwise
     uint32_t cinfo;           // zlib header CINFO = windowBits - 8 (7 unless the whole input fits a smaller window's match range)
 };
 
