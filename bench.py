@@ -178,6 +178,14 @@ def main():
         v, _ = cpu_sample(tar, reps=2)
         cpu_b = {"value": v, "unit": "GiB/s", "cores": 1, "kind": "port",
                  "sample": "whole silesia-small.tar, level 6, best of 2, single host thread (oracle restatement of zlib-rs)"}
+        try:  # orientation only: stock zlib 1.3 on the same core -- other algorithms, other bytes
+            import zlib as _z
+            t_ = time.perf_counter()
+            _z.compress(tar, 6)
+            cpu_b["stock_zlib_1_3_GiBps"] = len(tar) / (time.perf_counter() - t_) / GIB
+            cpu_b["host_cpus"] = os.cpu_count()
+        except Exception:
+            pass
 
     def step(i, timed):
         src = ins[i % ROT]
