@@ -435,13 +435,14 @@ struct LowAcc {
 };
 
 template <uint32_t R>
-static uint32_t run_low_ring(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
+static uint32_t run_low_ring(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB,
+                             uint32_t wsize)
 {
     std::vector<uint16_t> head(65536, 0), prev(32768, 0);
     std::vector<uint8_t> padded(N + 64, 0), ring(R + 16, 0xAA);
     if (N) memcpy(padded.data(), data, N);
-    RingAcc<R, ScalarCopy> a(ring.data(), padded.data(), N);
-    SerialLow<RingAcc<R, ScalarCopy>, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms));
+    RingAcc<R, ScalarCopy> a(ring.data(), padded.data(), N, wsize);
+    SerialLow<RingAcc<R, ScalarCopy>, ScalarOps> m(a, head.data(), level == 2 ? prev.data() : nullptr, N, serial_low_params(level, block_syms, wsize));
     uint32_t n = 0, fb;
     auto emit_at = [&](uint32_t i, Sym s) { if (syms.size() <= i) syms.resize(i + 1); syms[i] = s; };
     if (level == 1) fb = m.template run_quick<HostWarp>(emit_at, n);
@@ -451,9 +452,10 @@ static uint32_t run_low_ring(const uint8_t *data, uint32_t N, int level, uint32_
 }
 
 // the ring sizes of k_serial_low: 64 KiB next to the 128 KiB head table at level 1, 35824 B next to head + prev at level 2
-static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB)
+static uint32_t run_low(const uint8_t *data, uint32_t N, int level, uint32_t block_syms, std::vector<Sym> &syms, std::vector<uint32_t> &blockB,
+                        uint32_t wsize = kWSize)
 {
-    return level == 1 ? run_low_ring<65536>(data, N, level, block_syms, syms, blockB) : run_low_ring<35824>(data, N, level, block_syms, syms, blockB);
+    return level == 1 ? run_low_ring<65536>(data, N, level, block_syms, syms, blockB, wsize) : run_low_ring<35824>(data, N, level, block_syms, syms, blockB, wsize);
 }
 
 extern "C" int hm_parse_low(const uint8_t *data, uint32_t N, int level, SymOut *out, uint32_t cap, uint32_t *nsyms)
@@ -535,4 +537,46 @@ extern "C" int hm_deflate_small_window(const uint8_t *data, uint32_t N, int leve
     const uint32_t finalB = run_small_window(data, N, level, wbits, syms, symB);
     return encode_stream(data, N, level, syms, [&](uint32_t, const BlockDesc &bd) { return bd.last ? finalB : symB[bd.sym_begin + bd.sym_count - 1]; },
                          false, false, block_syms, dst, cap, out_len, data_type_out, (uint32_t)(wbits - 8));
+}
+
+// Z_HUFFMAN_ONLY (deflate/algorithm/huff.rs:9-46) with any window size: every byte a literal; the window base only matters for the
+// stored-block rule.  deflate_huff refills when lookahead == 0, so the base moves when strstart reaches 2w + k*w.
+static uint32_t huff_base(uint32_t q, uint32_t w) { return q < 2 * w ? 0 : w * (1 + (q - 2 * w) / w); }
+static uint32_t huff_final_base(uint32_t N, uint32_t w)
+{
+    // the last fill_window call (lookahead == 0 at strstart == N) still slides when strstart >= w + max_dist (deflate.rs:1787)
+    uint32_t B = N == 0 ? 0 : huff_base(N - 1, w);
+    if (N - B >= 2 * w - kMinLookahead) B += w;
+    return B;
+}
+extern "C" int hm_deflate_huff(const uint8_t *data, uint32_t N, int wbits, int mem_level, uint8_t *dst, uint32_t cap, uint32_t *out_len, int *dt)
+{
+    const uint32_t w = 1u << wbits, block_syms = (1u << (mem_level + 6)) - 1;
+    std::vector<Sym> syms(N);
+    for (uint32_t p = 0; p < N; p++) syms[p] = Sym{0, data[p], p};
+    return encode_stream(data, N, 1 /* header level flags 0: strategy >= Z_HUFFMAN_ONLY */, syms, [&](uint32_t, const BlockDesc &bd) {
+        return bd.last ? huff_final_base(N, w) : huff_base(syms[bd.sym_begin + bd.sym_count - 1].pos, w); }, false, false,
+        block_syms, dst, cap, out_len, dt, (uint32_t)(wbits - 8));
+}
+
+
+extern "C" int hm_parse_low_w(const uint8_t *data, uint32_t N, int level, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    std::vector<Sym> syms;
+    std::vector<uint32_t> blockB;
+    run_low(data, N, level, kBlockSyms, syms, blockB, 1u << wbits);
+    for (size_t i = 0; i < syms.size() && i < cap; i++) out[i] = SymOut{syms[i].pos, syms[i].dist, syms[i].lc};
+    *nsyms = (uint32_t)syms.size();
+    return 0;
+}
+
+extern "C" int hm_deflate_low_w(const uint8_t *data, uint32_t N, int level, int wbits, int mem_level, uint8_t *dst, uint32_t cap,
+                                uint32_t *out_len, int *data_type_out)
+{
+    const uint32_t block_syms = (1u << (mem_level + 6)) - 1;
+    std::vector<Sym> syms;
+    std::vector<uint32_t> blockB;
+    const uint32_t finalB = run_low(data, N, level, level == 1 ? kBlockSyms : block_syms, syms, blockB, 1u << wbits);
+    return encode_stream(data, N, level, syms, [&](uint32_t b, const BlockDesc &bd) { return (bd.last || b >= blockB.size()) ? finalB : blockB[b]; }, level == 1,
+                         false, level == 1 ? kBlockSyms : block_syms, dst, cap, out_len, data_type_out, (uint32_t)(wbits - 8));
 }

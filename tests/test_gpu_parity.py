@@ -207,19 +207,13 @@ ALL_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["flush"] =
 
 @pytest.mark.parametrize("v", ALL_KATS, ids=[v["name"] for v in ALL_KATS])
 def test_reference_golden_vectors_all_one_shot(v, eng):
-    """Every one-shot deflate vector of the reference's tests (any level / strategy / memLevel / wrapper).  Window sizes below
-    32 KiB are exact when the input never leaves the smaller window's match range (the engine says so in exact_parity)."""
+    """Every one-shot deflate vector of the reference's tests (any level / strategy / memLevel / wrapper / window size)."""
     d = bytes.fromhex(v["input_hex"])
     out, res = eng.deflate(d, level=v["level"], strategy=v["strategy"], window_bits=v["window_bits"], mem_level=v["mem_level"])
-    wb = v["window_bits"] - 16 if v["window_bits"] > 15 else abs(v["window_bits"])
-    lvl = 6 if v["level"] == -1 else v["level"]
-    fits = len(d) + 262 <= (1 << max(wb, 9))
-    serial = 3 <= lvl <= 6 and v["strategy"] in (0, 1, 4) and len(d) <= 32000  # hash_calc_difference, longest_match_difference
-    assert res.exact_parity == (1 if fits or serial else 0)
-    if fits or serial:
-        assert out == bytes.fromhex(v["expected_hex"])
-    else:  # fill_window_out_of_bounds: Z_HUFFMAN_ONLY with a 512-byte window and 765 bytes
-        assert zlib.decompress(out, v["window_bits"] if v["window_bits"] > 15 else 15) == d
+    # every vector is reproduced: 32 KiB windows; smaller ones through the fits rule, the serial paths (levels 1..6) or because the
+    # window does not enter (level 0) / only enters the stored-block rule (Z_HUFFMAN_ONLY)
+    assert res.exact_parity == 1
+    assert out == bytes.fromhex(v["expected_hex"])
 
 
 @pytest.mark.parametrize("level", [1, 2])
@@ -293,6 +287,26 @@ def test_small_windows_serial_path_levels_3_to_6(eng):
     assert eng.deflate(d, level=5, window_bits=26, mem_level=5)[0] == O.compress(d, 5, 26, 5)[1]
     z = Z.Deflate(6, window_bits=9)
     assert z.deflate(d, Z.Z_FINISH) == O.compress(d, 6, 9)[1]
+
+
+def test_small_windows_levels_0_1_2_and_huffman_only(eng):
+    """windowBits 9..14 at any input size: level 0 (the window does not enter), Z_HUFFMAN_ONLY (only the stored-block rule sees the
+    window base) and levels 1 / 2 (zb_serial.h emulates the window literally)."""
+    rng = np.random.default_rng(11)
+    srcs = [synthetic_mix(300000, 9), silesia_member(9)[:300000], rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(), silesia_member(7)[:200000]]
+    for wb in (9, 10, 12, 14):
+        for src in srcs:
+            for n in (len(src), 70000, 3 * (1 << wb) - 100, 1100, 700):
+                d = src[:n]
+                for level, strategy in ((0, 0), (1, 0), (2, 0), (6, 2)):
+                    out, res = eng.deflate(d, level=level, strategy=strategy, window_bits=wb)
+                    assert res.exact_parity == 1 and out == O.compress(d, level, wb, 8, strategy)[1], (wb, n, level, strategy)
+        d = srcs[3][:50000]
+        for mem in (1, 9):
+            for level, strategy in ((1, 0), (2, 0), (6, 2)):
+                assert eng.deflate(d, level=level, strategy=strategy, window_bits=wb, mem_level=mem)[0] == O.compress(d, level, wb, mem, strategy)[1]
+    d = rng.integers(0, 256, 3 * 32768 - 100, dtype=np.uint8).tobytes()  # the end-of-input slide of deflate_huff, memLevel 9 blocks
+    assert eng.deflate(d, level=6, strategy=2, mem_level=9)[0] == O.compress(d, 6, 15, 9, 2)[1]
 
 
 def test_other_levels_and_strategies_valid_streams(eng):

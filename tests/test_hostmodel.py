@@ -154,3 +154,26 @@ def test_small_window_serial_path():
                 for level in (3, 4, 5, 6):
                     d = src[:n]
                     assert dfl(d, level, wb) == O.compress(d, level, wb)[1], (wb, n, level)
+
+
+def test_small_windows_serial_levels_and_huffman_only():
+    """windowBits 9..14: zb_serial.h with the window size as a parameter (levels 1, 2) and the window-base rule of
+    Z_HUFFMAN_ONLY (k_literal_syms / k_block_hist: base moves at 2w + k*w, one more slide at the end of the input)."""
+    def run(fn, *args):
+        d = args[0]
+        cap = len(d) + len(d) // 4 + 2048
+        buf = ctypes.create_string_buffer(cap)
+        n, dt = ctypes.c_uint32(0), ctypes.c_int(0)
+        assert getattr(H(), fn)(d, len(d), *args[1:], buf, cap, ctypes.byref(n), ctypes.byref(dt)) == 0
+        return buf.raw[: n.value]
+    rng = np.random.default_rng(5)
+    srcs = [synthetic_mix(200000, 9), silesia_member(9)[:200000], rng.integers(0, 256, 100000, dtype=np.uint8).tobytes()]
+    for wb in (9, 12, 14, 15):
+        w = 1 << wb
+        for src in srcs:
+            for n in (len(src), 3 * w - 100, 2 * w, 1100, 700):
+                d = src[: min(n, len(src))]
+                for level in (1, 2):
+                    assert run("hm_deflate_low_w", d, level, wb, 8) == O.compress(d, level, wb)[1], (wb, n, level)
+                for mem in (1, 8, 9):
+                    assert run("hm_deflate_huff", d, wb, mem) == O.compress(d, 6, wb, mem, 2)[1], (wb, n, mem)

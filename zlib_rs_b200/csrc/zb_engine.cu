@@ -285,6 +285,13 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         jb.tail_start = 0;
         exact = true;
     }
+    // level 0 does not depend on the window at all (stored.rs copies straight from the input); Z_HUFFMAN_ONLY only through the
+    // stored-block rule (window base at flush time, k_block_hist); levels 1 and 2 emulate the window literally (zb_serial.h)
+    if (wb_eff < 15 && (level == 0 || (strategy == 2 && level != 0) || serial_low)) {
+        jb.wsize = 1u << wb_eff;
+        jb.cinfo = (uint32_t)(wb_eff - 8);
+        exact = true;
+    }
     if (level != 0 && !jb.huffman_only) {
         if (level < 3 && !serial_low) { eng_level = 3; exact = strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
         if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level

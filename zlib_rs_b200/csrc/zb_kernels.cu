@@ -892,8 +892,8 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
             if (jb.serial_mode) {
                 Bf = jb.serial_mode == 2 ? jb.block_base[b] : 0; // recorded at the flush (deflate_quick has no stored decision)
             } else if (jb.huffman_only) {
-                const uint32_t q = jb.syms[li].pos;
-                Bf = q < 2 * kWSize ? 0 : kWSize * (1 + (q - 2 * kWSize) / kWSize);
+                const uint32_t q = jb.syms[li].pos, w = jb.wsize;
+                Bf = q < 2 * w ? 0 : w * (1 + (q - 2 * w) / w);
             } else if (jb.slow_mode == 2) {
                 Bf = base_at(jb.syms[li].pos, jb.N);     // Z_RLE tallies a symbol at its own loop-top
             } else if (jb.slow_mode) {
@@ -1127,8 +1127,12 @@ __global__ void __launch_bounds__(256) k_literal_syms(JobBufs jb)
         jb.info->n_mid_syms = jb.N;
         jb.info->n_syms = jb.N;
         jb.info->n_blocks = jb.N / jb.block_syms + 1;
-        // deflate_huff refills only when lookahead == 0: the base moves when strstart reaches 64 KiB + k*32 KiB
-        jb.info->final_base = jb.N < 2 * kWSize ? 0 : kWSize * (1 + (jb.N - 2 * kWSize) / kWSize);
+        // deflate_huff refills only when lookahead == 0: the base moves when strstart reaches 2w + k*w; the last fill_window call
+        // (strstart == N) still slides when strstart >= w + max_dist (deflate.rs:1787)
+        const uint32_t w = jb.wsize, q = jb.N ? jb.N - 1 : 0;
+        uint32_t B = q < 2 * w ? 0 : w * (1 + (q - 2 * w) / w);
+        if (jb.N - B >= 2 * w - kMinLookahead) B += w;
+        jb.info->final_base = B;
     }
     if (p < jb.N) jb.syms[p] = Sym{0, jb.in[p], p};
 }

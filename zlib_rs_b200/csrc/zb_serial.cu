@@ -14,12 +14,12 @@ struct WarpCopy { // RingAcc's refill on a warp
 };
 
 struct WarpOps {
-    static __device__ __forceinline__ void slide(uint16_t *t, uint32_t n)
+    static __device__ __forceinline__ void slide(uint16_t *t, uint32_t n, uint32_t wsize)
     {
         uint32_t *w = reinterpret_cast<uint32_t *>(t);
-        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t lane = threadIdx.x & 31, sub = wsize | (wsize << 16);
         __syncwarp();
-        for (uint32_t i = lane; i < n / 2; i += 32) w[i] = __vsubus2(w[i], 0x80008000u); // per-halfword saturating - 32768
+        for (uint32_t i = lane; i < n / 2; i += 32) w[i] = __vsubus2(w[i], sub); // per-halfword saturating subtraction of the window size
         __syncwarp();
     }
     template <class D>
@@ -68,8 +68,8 @@ __device__ __forceinline__ void serial_low_body(const JobBufs &jb, uint8_t *smem
     }
     __syncwarp();
     using Acc = RingAcc<R, WarpCopy>;
-    Acc a(ring, jb.in, jb.N);
-    SerialLow<Acc, WarpOps> m(a, head, prev, jb.N, serial_low_params(kFast ? 2 : 1, jb.block_syms));
+    Acc a(ring, jb.in, jb.N, jb.wsize);
+    SerialLow<Acc, WarpOps> m(a, head, prev, jb.N, serial_low_params(kFast ? 2 : 1, jb.block_syms, jb.wsize));
     Sym *syms = jb.syms;
     uint32_t n = 0, fb;
     if (!kFast) {

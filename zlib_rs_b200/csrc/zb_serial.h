@@ -20,19 +20,20 @@ struct SerialLowParams {
     uint32_t level;                       // 1 = deflate_quick, 2 = deflate_fast
     uint32_t good, lazy, nice, chain;     // deflate/algorithm/mod.rs:69-82 rows 1..2
     uint32_t block_syms;                  // lit_bufsize - 1 (sym_buf.rs:23): symbols per block of deflate_fast
+    uint32_t wsize;                       // 1 << windowBits (512 .. 32768)
 };
-ZB_HD SerialLowParams serial_low_params(int level, uint32_t block_syms)
+ZB_HD SerialLowParams serial_low_params(int level, uint32_t block_syms, uint32_t wsize = kWSize)
 {
-    if (level == 1) return {1, 0, 0, 0, 0, block_syms};
-    return {2, 4, 4, 8, 4, block_syms};
+    if (level == 1) return {1, 0, 0, 0, 0, block_syms, wsize};
+    return {2, 4, 4, 8, 4, block_syms, wsize};
 }
 
 // Scalar reference operations (host model; the CUDA kernel substitutes warp-cooperative versions).
 struct ScalarOps {
     // slide_hash (deflate/slide_hash.rs:11-47): saturating subtraction of the window size
-    static ZB_HD void slide(uint16_t *t, uint32_t n)
+    static ZB_HD void slide(uint16_t *t, uint32_t n, uint32_t w)
     {
-        for (uint32_t i = 0; i < n; i++) t[i] = t[i] >= kWSize ? (uint16_t)(t[i] - kWSize) : 0;
+        for (uint32_t i = 0; i < n; i++) t[i] = t[i] >= w ? (uint16_t)(t[i] - w) : 0;
     }
     // compare256 (deflate/compare256.rs:4-39) on absolute positions
     template <class D>
@@ -127,8 +128,9 @@ struct RingAcc {
     uint8_t *ring;     // R + 16 bytes
     const uint8_t *in; // N bytes, zero padded by at least 16
     uint32_t N;
+    uint32_t W;              // window size (what the reference's window buffer holds behind the input depends on it)
     uint32_t lo = 0, hi = 0; // the ring holds absolute [lo, hi); multiples of 16
-    ZB_HD RingAcc(uint8_t *r, const uint8_t *i, uint32_t n) : ring(r), in(i), N(n) {}
+    ZB_HD RingAcc(uint8_t *r, const uint8_t *i, uint32_t n, uint32_t w = kWSize) : ring(r), in(i), N(n), W(w) {}
     ZB_HD uint32_t raw(uint32_t y) const // y < N
     {
 #if defined(ZB_RING_STATS)
@@ -139,8 +141,8 @@ struct RingAcc {
     ZB_HD uint32_t byte(uint32_t y) const
     {
         while (y >= N) { // what the reference's window buffer still holds behind the end of the input (cf. GAcc)
-            if (y < 2 * kWSize) return 0;
-            y -= kWSize;
+            if (y < 2 * W) return 0;
+            y -= W;
         }
         return raw(y);
     }
@@ -198,8 +200,10 @@ struct SerialLow {
     uint32_t N;
     SerialLowParams sp;
     uint32_t B = 0, F = 0, p = 0;
+    uint32_t WS, MD; // window size, max_dist = W - MIN_LOOKAHEAD (deflate.rs:1423)
 
-    ZB_HD SerialLow(D &d_, uint16_t *h, uint16_t *pv, uint32_t n, const SerialLowParams &s) : d(d_), head(h), prev(pv), N(n), sp(s) {}
+    ZB_HD SerialLow(D &d_, uint16_t *h, uint16_t *pv, uint32_t n, const SerialLowParams &s)
+        : d(d_), head(h), prev(pv), N(n), sp(s), WS(s.wsize), MD(s.wsize - kMinLookahead) {}
 
     // StandardHashCalc::quick_insert_value (hash_calc.rs:48-59); str is a window index
     ZB_HD uint32_t insert_value(uint32_t str, uint32_t val)
@@ -207,7 +211,7 @@ struct SerialLow {
         const uint32_t hm = hash_u32(val);
         const uint32_t hd = head[hm];
         if (hd != (str & 0xffffu)) {
-            if (prev) prev[str & (kWSize - 1)] = (uint16_t)hd;
+            if (prev) prev[str & (WS - 1)] = (uint16_t)hd;
             head[hm] = (uint16_t)str;
         }
         return hd;
@@ -219,12 +223,12 @@ struct SerialLow {
     {
         for (;;) {
             const uint32_t sw = p - B;
-            uint32_t more = 2 * kWSize - (F - p) - sw;
-            if (sw >= kWSize + kMaxDist) {
-                B += kWSize;
-                OPS::slide(head, 65536u);
-                if (prev) OPS::slide(prev, kWSize);
-                more += kWSize;
+            uint32_t more = 2 * WS - (F - p) - sw;
+            if (sw >= WS + MD) {
+                B += WS;
+                OPS::slide(head, 65536u, WS);
+                if (prev) OPS::slide(prev, WS, WS);
+                more += WS;
             }
             if (F >= N) break; // avail_in == 0
             const uint32_t n = N - F < more ? N - F : more;
@@ -245,7 +249,7 @@ struct SerialLow {
         const uint32_t sw = p - B, lookahead = F - p;
         uint32_t best = 2, chain = sp.chain;
         if (best >= sp.good) chain >>= 2;
-        const uint32_t limit = sw > kMaxDist ? sw - kMaxDist : 0;
+        const uint32_t limit = sw > MD ? sw - MD : 0;
         const bool early_exit = sp.level < 5;
         for (;;) {
             if (cur >= sw) break;
@@ -270,7 +274,7 @@ struct SerialLow {
                 }
                 // next in chain or return (:136-160)
                 if (--chain == 0) { found = false; break; }
-                cur = prev[cur & (kWSize - 1)];
+                cur = prev[cur & (WS - 1)];
                 if (cur <= limit) { found = false; break; }
             }
             if (!found) return best;
@@ -284,7 +288,7 @@ struct SerialLow {
                 break;
             }
             if (--chain == 0) return best;
-            cur = prev[cur & (kWSize - 1)];
+            cur = prev[cur & (WS - 1)];
             if (cur <= limit) return best;
         }
         return best;
@@ -323,7 +327,7 @@ struct SerialLow {
                     hh = lower ? sw0 + top_bit(lower) : head[hsh[l]];
                     const uint32_t sw = sw0 + l;
                     // quick.rs:113-119: distance in range and the first four bytes equal => a match of at least 4
-                    if (hh < sw && sw - hh <= kMaxDist && d.word(B + hh) == val[l]) e = 1;
+                    if (hh < sw && sw - hh <= MD && d.word(B + hh) == val[l]) e = 1;
                 }
                 cand[l] = hh;
                 eq[l] = e;
@@ -373,7 +377,7 @@ struct SerialLow {
                 const uint32_t sw = p - B;
                 const uint32_t val = d.word(p);
                 const uint32_t hh = insert_value(sw, val);
-                if (hh < sw && sw - hh <= kMaxDist) {
+                if (hh < sw && sw - hh <= MD) {
                     const uint32_t c = B + hh;
                     if (val == d.word(c)) {
                         uint32_t len = OPS::compare256(d, p + 2, c + 2) + 2;
@@ -419,14 +423,14 @@ struct SerialLow {
                 uint32_t is_match = 0, best = 2, start = 0;
                 if (l >= s) {
                     const uint32_t sw = sw0 + l;
-                    const uint32_t limit = sw > kMaxDist ? sw - kMaxDist : 0;
+                    const uint32_t limit = sw > MD ? sw - MD : 0;
                     uint32_t pm = peers[l] & (inserted | bit_range(s, l));
                     bool in_table = false;
                     uint32_t cur, chain = sp.chain;
                     if (pm) { const uint32_t j = top_bit(pm); pm &= ~(1u << j); cur = sw0 + j; }
                     else { cur = head[hsh[l]]; in_table = true; }
                     // fast.rs:45: dist in range, hash_head != 0
-                    if (cur < sw && sw - cur <= kMaxDist && cur != 0) {
+                    if (cur < sw && sw - cur <= MD && cur != 0) {
                         for (;;) {
                             const uint32_t c = B + cur;
                             const uint32_t x0 = val[l] ^ d.word(c);
@@ -438,7 +442,7 @@ struct SerialLow {
                             if (--chain == 0) break;
                             if (pm) { const uint32_t j = top_bit(pm); pm &= ~(1u << j); cur = sw0 + j; }
                             else if (!in_table) { cur = head[hsh[l]]; in_table = true; }
-                            else cur = prev[cur & (kWSize - 1)];
+                            else cur = prev[cur & (WS - 1)];
                             if (cur <= limit) break;
                         }
                         is_match = best >= 4 ? 1u : 0u;
@@ -490,7 +494,7 @@ struct SerialLow {
         W::sync();
         ZB_FOR_LANES(W, l) {
             if ((inserted >> l) & 1u) {
-                prev[(sw0 + l) & (kWSize - 1)] = (uint16_t)pred[l];
+                prev[(sw0 + l) & (WS - 1)] = (uint16_t)pred[l];
                 const uint32_t mine = peers[l] & inserted;
                 if ((mine >> l) == 1u) head[hsh[l]] = (uint16_t)(sw0 + l);
             }
@@ -523,7 +527,7 @@ struct SerialLow {
                 const uint32_t sw = p - B;
                 const uint32_t val = d.word(p);
                 const uint32_t hh = insert_value(sw, val);
-                if (hh < sw && sw - hh <= kMaxDist && hh != 0) {
+                if (hh < sw && sw - hh <= MD && hh != 0) {
                     uint32_t start = 0;
                     uint32_t len = longest_match(hh, start);
                     if (len >= 4) {
@@ -532,7 +536,7 @@ struct SerialLow {
                         if (len <= sp.lazy && lookahead >= 4) {
                             // insert_string(strstart + 1, len - 1) (hash_calc.rs:61-82)
                             const uint32_t str = sw + 1, count = len - 1;
-                            const uint32_t avail = 2 * kWSize - str;
+                            const uint32_t avail = 2 * WS - str;
                             const uint32_t n = avail < count + 3 ? avail : count + 3;
                             for (uint32_t i = 0; i + 4 <= n; i++) insert_at(str + i);
                             p += len;
