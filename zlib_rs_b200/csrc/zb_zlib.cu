@@ -232,8 +232,8 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     if (final && !d->any_segment) {
         // the one-shot path: byte-identical to the reference's deflate(Z_FINISH) at every level, strategy and memLevel (32 KiB window)
         d->out.resize(base + cap);
-        rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + base, cap, 0, d->level, d->strategy,
-                           d->wrap == 0 ? -15 : d->wrap == 2 ? 31 : 15, ZB_FLAG_MEMLEVEL(d->mem_level), &r);
+        rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + base, cap, 0, d->level, d->strategy, d->window_bits,
+                           ZB_FLAG_MEMLEVEL(d->mem_level), &r);
         if (rc != ZB_OK) { d->out.resize(base); strm->msg = zb_last_error(); return map_rc(rc); }
         d->out.resize(base + r.out_bytes);
         strm->adler = r.check;
