@@ -4,6 +4,8 @@
 // the oracle on a machine without a GPU.  Never linked into the shipped library.
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <utility>
 #include <string.h>
 #include <vector>
 #include "../../zlib_rs_b200/csrc/zb_core.h"
@@ -579,4 +581,63 @@ extern "C" int hm_deflate_low_w(const uint8_t *data, uint32_t N, int level, int 
     const uint32_t finalB = run_low(data, N, level, level == 1 ? kBlockSyms : block_syms, syms, blockB, 1u << wbits);
     return encode_stream(data, N, level, syms, [&](uint32_t b, const BlockDesc &bd) { return (bd.last || b >= blockB.size()) ? finalB : blockB[b]; }, level == 1,
                          false, level == 1 ? kBlockSyms : block_syms, dst, cap, out_len, data_type_out, (uint32_t)(wbits - 8));
+}
+
+// ------------------------------------------------------------------------------------------
+// Experiment (round-2 planning): how many fixed-point iterations does the level-6 parse need from a given initial
+// hole set, and how many 32 KiB tiles change per iteration?  mode 0: no holes (what the engine does); mode 1: holes guessed from the
+// data alone -- a greedy walk that takes the nearest chain candidate and treats matches >= 257 as long.
+// stats[2*i] = changed hole words, stats[2*i+1] = dirty 32 KiB tiles of iteration i.
+// ------------------------------------------------------------------------------------------
+extern "C" int hm_iter_experiment(const uint8_t *data, uint32_t N, int level, int mode, uint32_t *stats, uint32_t cap, uint32_t *iters_out)
+{
+    LevelParams lp = level_params(level);
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), newholes((N >> 5) + 2, 0);
+    std::vector<uint32_t> M(N + 1024, 0), nxt(N + 1, 0);
+    uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    if (mode == 1) {
+        uint32_t p = 0;
+        while (p + 262 < tail_start) {
+            uint32_t d = L[p], len = 0;
+            if (d) { while (len < 258 && data[p + len] == data[p - d + len]) len++; }
+            if (len >= 257) {
+                for (uint32_t y = p + 1; y + 1 < p + len; y++) holes[y >> 5] |= 1u << (y & 31);
+                p += len;
+            } else p += len >= 4 ? len : 1;
+        }
+    }
+    HostAcc a{data, N, L.data(), holes.data(), M.data()};
+    uint32_t iters = 0;
+    std::vector<uint32_t> path;
+    for (;;) {
+        for (uint32_t x = 0; x < N; x++) {
+            Match m = (x + kMSafe <= N) ? lm_walk(a, x, 0xffffffffu, lp) : Match{0, 0};
+            M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+        }
+        for (uint32_t p = 0; p < tail_start; p++) { uint32_t ns; nxt[p] = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns); }
+        path.clear();
+        uint32_t p = 0;
+        while (p < tail_start && nxt[p] < tail_start) { path.push_back(p); p = nxt[p]; }
+        std::fill(newholes.begin(), newholes.end(), 0);
+        for (uint32_t q : path) {
+            uint32_t ns;
+            macro_step(a, q, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy)
+                    for (uint32_t y = s.pos + 1; y + 1 < s.pos + s.lc + 3; y++) newholes[y >> 5] |= 1u << (y & 31);
+            }, &ns);
+        }
+        uint32_t changed = 0, tiles = 0, last_tile = 0xffffffffu;
+        for (uint32_t w = 0; w < holes.size(); w++)
+            if (holes[w] != newholes[w]) { changed++; const uint32_t t = w / 1024; if (t != last_tile) { tiles++; last_tile = t; } }
+        if (2 * iters + 1 < cap) { stats[2 * iters] = changed; stats[2 * iters + 1] = tiles; }
+        iters++;
+        if (!changed) break;
+        holes = newholes;
+        a.holes = holes.data();
+        if (iters > 64) return -1;
+    }
+    *iters_out = iters;
+    return 0;
 }
