@@ -78,12 +78,10 @@ def deflate_huff(d, wb, mem):
     return buf.raw[: n.value]
 
 
-def main():
-    secs = float(sys.argv[1]) if len(sys.argv) > 1 else 60
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+def run(secs, seed, max_cases=1 << 60):
     rng = np.random.default_rng(seed)
     t0, cases, bad = time.time(), 0, 0
-    while time.time() - t0 < secs:
+    while time.time() - t0 < secs and cases < max_cases:
         d = gen(rng)
         which = int(rng.integers(0, 6))
         try:
@@ -125,7 +123,8 @@ def main():
             open(fn, "wb").write(d)
             print("MISMATCH", tag, len(d), fn, flush=True)
     print("cases", cases, "mismatches", bad, "seconds", round(time.time() - t0, 1))
+    return cases, bad
 
 
 if __name__ == "__main__":
-    main()
+    run(float(sys.argv[1]) if len(sys.argv) > 1 else 60, int(sys.argv[2]) if len(sys.argv) > 2 else 1)

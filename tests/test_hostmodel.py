@@ -177,3 +177,13 @@ def test_small_windows_serial_levels_and_huffman_only():
                     assert run("hm_deflate_low_w", d, level, wb, 8) == O.compress(d, level, wb)[1], (wb, n, level)
                 for mem in (1, 8, 9):
                     assert run("hm_deflate_huff", d, wb, mem) == O.compress(d, 6, wb, mem, 2)[1], (wb, n, mem)
+
+
+def test_fuzz_smoke():
+    """A short, seeded run of scripts/fuzz_hostmodel.py: structured random inputs through every host-model path against the oracle."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_hostmodel", os.path.join(ROOT, "scripts", "fuzz_hostmodel.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    cases, bad = m.run(60, 7, max_cases=150)
+    assert cases == 150 and bad == 0
