@@ -106,3 +106,15 @@ def calgary_mix(n=CALGARY_MIX_BYTES):
         assert hashlib.sha256(out).hexdigest() == CALGARY_MIX_SHA256
     _cache[key] = out
     return out
+
+
+def periodic_mutated(n, period, nmut, seed):
+    """A period of random bytes repeated to n bytes with nmut single-byte mutations: long matches whose sources sit in the holes of
+    earlier long matches -- the input class on which the hole fixed point needs the most iterations (found by scripts/fuzz_hostmodel.py)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    per = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
+    b = bytearray((per * (n // period + 1))[:n])
+    for _ in range(nmut):
+        b[int(rng.integers(0, n))] = int(rng.integers(0, 256))
+    return bytes(b)

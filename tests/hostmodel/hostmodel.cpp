@@ -107,7 +107,7 @@ extern "C" int hm_parse_parallel(const uint8_t *data, uint32_t N, int level, Sym
         if (newholes == holes) break;
         holes = newholes;
         a.holes = holes.data();
-        if (iters > 64) return -1;
+        if (iters > N / 257u + 64u) return -1;
     }
     // P3: symbols
     uint32_t n = 0;
@@ -273,7 +273,7 @@ extern "C" int hm_deflate(const uint8_t *data, uint32_t N, int level, uint8_t *d
         if (newholes == holes) break;
         holes = newholes;
         a.holes = holes.data();
-        if (iters > 64) return -1;
+        if (iters > N / 257u + 64u) return -1;
     }
     std::vector<Sym> syms;
     std::vector<uint32_t> symB;
@@ -636,7 +636,7 @@ extern "C" int hm_iter_experiment(const uint8_t *data, uint32_t N, int level, in
         if (!changed) break;
         holes = newholes;
         a.holes = holes.data();
-        if (iters > 64) return -1;
+        if (iters > N / 257u + 64u) return -1;
     }
     *iters_out = iters;
     return 0;

@@ -472,7 +472,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     if (!h_info->holes_changed) break;
                     n_dirty = 0;
                     for (uint32_t i = 0; i < nmt; i++) n_dirty += h_dirty[i] != 0;
-                    if (iters > 4096) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; }
+                    if (iters > N / 257u + 4096u) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; } // every iteration settles at least one long match
                 }
             }
             if (jb.tail_start > 0) {
