@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as O
 import zlib_rs_b200 as Z
-from corpus import calgary_mix, silesia_gz, silesia_member, silesia_tar, synthetic_mix
+from corpus import calgary_mix, periodic_mutated, silesia_gz, silesia_member, silesia_tar, synthetic_mix
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -307,6 +307,16 @@ def test_small_windows_levels_0_1_2_and_huffman_only(eng):
                 assert eng.deflate(d, level=level, strategy=strategy, window_bits=wb, mem_level=mem)[0] == O.compress(d, level, wb, mem, strategy)[1]
     d = rng.integers(0, 256, 3 * 32768 - 100, dtype=np.uint8).tobytes()  # the end-of-input slide of deflate_huff, memLevel 9 blocks
     assert eng.deflate(d, level=6, strategy=2, mem_level=9)[0] == O.compress(d, 6, 15, 9, 2)[1]
+
+
+def test_hole_fixed_point_worst_case_class(eng):
+    """Periodic data with a few mutations: long matches whose sources lie in the holes of earlier long matches.  The fixed point
+    needs dozens of iterations here (the front advances a few KiB per iteration) -- slow, and still the reference's bytes."""
+    for (n, period, nmut, seed) in ((200003, 222, 30, 1), (200003, 74, 20, 2), (150000, 37, 40, 4), (400000, 1000, 25, 5)):
+        d = periodic_mutated(n, period, nmut, seed)
+        for level in (3, 5, 6):
+            out, res = eng.deflate(d, level=level)
+            assert res.exact_parity == 1 and out == O.compress(d, level)[1], (n, period, level, res.iterations)
 
 
 def test_other_levels_and_strategies_valid_streams(eng):
