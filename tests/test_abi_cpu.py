@@ -109,3 +109,17 @@ def test_c_client_links_and_fails_loudly_without_a_device(tmp_path):
     f.write_bytes(b"hello hello hello" * 100)
     r = subprocess.run([os.path.join(root, "tests", "c_client", "_build", "pipe_client"), str(f)], capture_output=True, text=True)
     assert r.returncode == 77 and "no CUDA device" in r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement on the host cores) prints one JSON line with the contract's keys."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GiB/s" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["metric"] == "deflate_level6_raw_input_throughput_silesia_small_tar" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
