@@ -293,7 +293,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         exact = true;
     }
     if (level != 0 && !jb.huffman_only) {
-        if (level < 3 && !serial_low) { eng_level = 3; exact = strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
+        if (level < 3 && !serial_low) { eng_level = 3; exact = exact && strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
         if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level
         else if (level > 6) { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
     }
