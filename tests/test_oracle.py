@@ -262,3 +262,37 @@ def test_set_dictionary_restatement_against_stock_zlib():
     rc, out, did = O.compress_dict(b"hello, hello!\0", b"hello", 6)
     c = zlib.compressobj(6, zdict=b"hello")
     assert out == c.compress(b"hello, hello!\0") + c.flush()
+
+
+def test_gzip_with_header_reference_check():
+    """zlib-rs/src/deflate.rs:3897-3985 (gzip_with_header): level 6, gzip wrapper, a gz_header with extra / name / comment / hcrc,
+    input "Hello World\\n": the reference asserts an 81-byte stream that inflates back.  Stock gzip parses the header fields."""
+    import ctypes, gzip, io
+    L = O.lib()
+
+    class GzHeader(ctypes.Structure):
+        _fields_ = [("text", ctypes.c_int), ("time", ctypes.c_ulong), ("xflags", ctypes.c_int), ("os", ctypes.c_int),
+                    ("extra", ctypes.c_char_p), ("extra_len", ctypes.c_uint), ("extra_max", ctypes.c_uint),
+                    ("name", ctypes.c_char_p), ("name_max", ctypes.c_uint), ("comment", ctypes.c_char_p), ("comm_max", ctypes.c_uint),
+                    ("hcrc", ctypes.c_int), ("done", ctypes.c_int)]
+
+    extra, name, comment = b"some extra stuff\0", b"nomen est omen\0", b"such comment\0"
+    h = GzHeader(0, 0, 0, 0, extra, len(extra), 0, name, 0, comment, 0, 1, 0)
+    s = O.ZoStream()
+    assert L.zo_deflate_init(ctypes.byref(s), 6, 31, 8, 0) == 0
+    L.zo_deflate_set_header.argtypes = [ctypes.POINTER(O.ZoStream), ctypes.POINTER(GzHeader)]
+    assert L.zo_deflate_set_header(ctypes.byref(s), ctypes.byref(h)) == 0
+    data = b"Hello World\n"
+    src = ctypes.create_string_buffer(data, len(data))
+    out = ctypes.create_string_buffer(256)
+    s.next_in, s.avail_in = ctypes.addressof(src), len(data)
+    s.next_out, s.avail_out = ctypes.addressof(out), 256
+    assert L.zo_deflate(ctypes.byref(s), 4) == 1
+    n = 256 - s.avail_out
+    L.zo_deflate_end(ctypes.byref(s))
+    stream = out.raw[:n]
+    assert n == 81
+    assert gzip.decompress(stream) == data
+    assert stream[3] == 0x02 | 0x04 | 0x08 | 0x10  # FHCRC | FEXTRA | FNAME | FCOMMENT
+    assert extra in stream and name in stream and comment in stream
+    assert O.uncompress is not None and O.inflate_stream(stream, 31)[1] == data
