@@ -65,12 +65,12 @@ struct SAcc { // shared-memory window of k_match
     }
 };
 
-struct SAccR { // shared-memory window of k_match; links are already bridged over holes
+struct SAccR { // shared-memory window of k_match; links are already bridged over holes, "no link" is staged as 0xffff
     const uint8_t *sdata;
     const uint16_t *sL;
     uint32_t ws;
     __device__ __forceinline__ uint32_t byte(uint32_t y) const { return sdata[y - ws]; }
-    __device__ __forceinline__ uint32_t link(uint32_t y) const { return sL[y - ws]; }
+    __device__ __forceinline__ uint32_t link(uint32_t y) const { const uint32_t v = sL[y - ws]; return v == 0xffffu ? 0u : v; }
     __device__ __forceinline__ bool inserted(uint32_t) const { return true; }
 };
 
@@ -245,7 +245,8 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 // with short chains never wait for lanes with long ones.
 constexpr uint32_t kBatch = 8;
 constexpr uint32_t kWalkBurst = 4; // walk steps between two schedule checks
-enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3 };
+constexpr uint32_t kCmpBurst = 4;  // 8-byte compare steps per compare burst
+enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3, LS_FIN = 4 };
 
 // explicit shared-space loads on 32-bit shared addresses (keeps address-space conversions out of the hot loop)
 __device__ __forceinline__ uint32_t sld_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -268,6 +269,20 @@ struct DiffMaps { // changed-hole bitmaps of the staged window with exclusive pr
     }
 };
 
+// Unaligned little-endian 64-bit read from shared memory: three aligned words and two funnel shifts.
+__device__ __forceinline__ void sld_u64u(uint32_t a, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t al = a & ~3u, sh = (a & 3u) * 8u;
+    const uint32_t w0 = sld_u32(al), w1 = sld_u32(al + 4), w2 = sld_u32(al + 8);
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+// Schedule: a lane is IDLE (needs a position), WALKing its chain, PENDing a compare with the candidate it stopped at, or FINished
+// (result to be stored).  One pass of the outer loop runs a burst of walk steps for the walking lanes (a tight loop: two
+// shared-memory loads and a handful of integer instructions per candidate; a lane leaves it at its first event -- filter hit,
+// budget, end of chain), then a burst of compare steps once enough lanes wait for one, stores the finished results and refills
+// idle lanes once enough of them are idle.  The staged links hold 0xffff for "no link" so that the walk needs one range test.
 __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sbm,
                                                 const DiffMaps dm, uint32_t ws, uint32_t te, uint32_t *s_next)
 {
@@ -279,19 +294,93 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     uint32_t *const Mout = jb.M + ws;
     uint16_t *const RDout = jb.SK + ws;
     // per-lane state, all positions relative to ws
-    uint32_t xr = 0, cr = 0, best = 2, chain = 0, res = 0, cand = 0;
-    uint32_t dn = 0;    // staged link of cr, loaded one step ahead (the staged links never lead to a hole, see k_match)
-    uint32_t xb = 0;    // byte of x at index `best`: a longer match must reproduce it (one-byte filter first)
-    uint32_t xw0 = 0;   // first four bytes of x: second-stage filter before a full compare is scheduled
-    uint32_t fbase = 0; // dbase + best
-    uint32_t lowr = 0;  // lowest admissible candidate (relative): x - lim
+    uint32_t xr = 0;     // the position being matched
+    uint32_t cr = 0;     // WALK: the next candidate to test (inside the window); PEND: the candidate being compared
+    uint32_t dn = 0;     // staged link of cr (loaded when cr was tested)
+    uint32_t best = 2, chain = 0, res = 0;
+    uint32_t xb = 0;     // byte of x at index `best`: a longer match must reproduce it (the walk's only filter)
+    uint32_t fbase = 0;  // dbase + best
+    uint32_t lowr = 0;   // lowest admissible candidate (relative)
+    uint32_t clen = 0;   // PEND: bytes known equal so far
+    uint32_t rd = 0;     // FIN: reach code to store
     uint32_t state = LS_IDLE;
     for (;;) {
-        const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
+        // ---- walk burst
+        if (state == LS_WALK) {
+            if (chain > kWalkBurst) {
+                // exits carry no extra state: what happened is re-derived from fb / dn / cr after the loop
+                uint32_t fb;
+                bool more = false;
+#pragma unroll
+                for (uint32_t k = 0; k < kWalkBurst; k++) {
+                    fb = sld_u8(fbase + cr);
+                    dn = sld_u16(lbase + 2 * cr);
+                    if (fb == xb) break;
+                    chain--;
+                    if (cr < lowr + dn) break; // the chain ends or leaves the window
+                    cr -= dn;
+                    if (k + 1 == kWalkBurst) more = true;
+                }
+                if (!more) {
+                    if (fb == xb) { state = LS_PEND; clen = 0; }
+                    else { rd = 0xffffu; state = LS_FIN; }
+                }
+            } else {
+                const uint32_t fb = sld_u8(fbase + cr);
+                dn = sld_u16(lbase + 2 * cr);
+                if (fb == xb) { state = LS_PEND; clen = 0; }
+                else if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; } // budget
+                else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
+                else cr -= dn;
+            }
+        }
+        // ---- compare burst
         const uint32_t m_walk = __ballot_sync(0xffffffffu, state == LS_WALK);
         const uint32_t m_pend = __ballot_sync(0xffffffffu, state == LS_PEND);
-        if ((m_idle | m_walk | m_pend) == 0) break;
-        if (m_idle && (__popc(m_idle) >= (int)kBatch || m_walk == 0)) {
+        if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
+            if (state == LS_PEND) {
+                uint32_t pa = dbase + xr + clen, pb = dbase + cr + clen;
+                uint32_t len = 0;
+                bool resolved = false;
+#pragma unroll 1
+                for (uint32_t k = 0; k < kCmpBurst; k++) {
+                    uint32_t a0, a1, b0, b1;
+                    sld_u64u(pa, a0, a1);
+                    sld_u64u(pb, b0, b1);
+                    const uint32_t d0 = a0 ^ b0, d1 = a1 ^ b1;
+                    if ((d0 | d1) != 0 || clen + 8 >= kMaxMatch) {
+                        len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                        resolved = true;
+                        break;
+                    }
+                    clen += 8; pa += 8; pb += 8;
+                }
+                if (resolved) {
+                    if (len > kMaxMatch) len = kMaxMatch;
+                    state = LS_WALK;
+                    if (len > best) {
+                        best = len;
+                        res = (len << 16) | (xr - cr);
+                        if (best >= nice) { rd = xr - cr; state = LS_FIN; }
+                        else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
+                    }
+                    if (state == LS_WALK) { // on to the next candidate
+                        if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; }
+                        else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
+                        else cr -= dn;
+                    }
+                }
+            }
+        }
+        // ---- results
+        if (state == LS_FIN) { Mout[xr] = res; RDout[xr] = (uint16_t)rd; state = LS_IDLE; }
+        // ---- refill
+        const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
+        const uint32_t m_busy = __ballot_sync(0xffffffffu, state == LS_WALK || state == LS_PEND);
+        if ((m_idle | m_busy) == 0) break; // every lane is done
+        if (m_idle == 0) continue;
+        if (__popc(m_idle) < (int)kBatch && m_busy != 0) continue;
+        {
             // warp-aggregated fetch of consecutive positions
             uint32_t base = 0;
             const uint32_t leader = __ffs(m_idle) - 1;
@@ -303,10 +392,9 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 else if (x + kMSafe > N) { jb.M[x] = 0; }
                 else {
                     xr = x - ws;
-                    xw0 = sld_u32u(dbase + xr);
                     bool skip = false;
                     if (filt) { // only buckets in which a hole changed can have a different M ...
-                        const uint32_t h = hash_u32(xw0);
+                        const uint32_t h = hash_u32(sld_u32u(dbase + xr));
                         skip = !((sbm[h >> 5] >> (h & 31)) & 1u);
                         if (!skip) {
                             // ... and only if the change can alter the previous walk (its reach and how it ended are in RD):
@@ -314,15 +402,15 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                             //  * a lost candidate (inserted -> hole) if it was the best one, or -- when the walk ended on its
                             //    budget -- anywhere in the reach (one more candidate gets examined);
                             //  * the nearest candidate now sits exactly at the window limit (only a first candidate may, medium.rs:76).
-                            const uint32_t rd = RDout[xr];
-                            const bool on_budget = rd != 0xffffu && (rd & 0x8000u);
-                            const uint32_t lo = rd == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - (rd & 0x7fffu);
+                            const uint32_t rdo = RDout[xr];
+                            const bool on_budget = rdo != 0xffffu && (rdo & 0x8000u);
+                            const uint32_t lo = rdo == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - (rdo & 0x7fffu);
                             bool redo = DiffMaps::any(dm.del, dm.pdel, lo, xr);
                             if (!redo) {
                                 if (on_budget) redo = DiffMaps::any(dm.add, dm.padd, lo, xr);
                                 else {
                                     const uint32_t m = Mout[xr];
-                                    if (m) { const uint32_t h = xr - (m & 0xffffu); redo = (dm.add[h >> 5] >> (h & 31)) & 1u; }
+                                    if (m) { const uint32_t h2 = xr - (m & 0xffffu); redo = (dm.add[h2 >> 5] >> (h2 & 31)) & 1u; }
                                 }
                             }
                             if (!redo) redo = sld_u16(lbase + 2 * xr) == kMaxDist;
@@ -330,57 +418,21 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                         }
                     }
                     if (!skip) {
-                        cr = xr; best = 2; chain = budget; res = 0;
-                        dn = sld_u16(lbase + 2 * cr);
-                        fbase = dbase + 2;
-                        xb = sld_u8(fbase + xr);
                         // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
                         // absolute position 0 is never a candidate
+                        const uint32_t d0 = sld_u16(lbase + 2 * xr);
                         lowr = xr > kMaxDist ? xr - kMaxDist : 0;
                         if (ws == 0 && lowr == 0) lowr = 1;
-                        state = LS_WALK;
+                        if (xr < lowr + d0) { Mout[xr] = 0; RDout[xr] = 0xffffu; } // no candidate in the window
+                        else {
+                            cr = xr - d0;
+                            if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
+                            best = 2; chain = budget; res = 0;
+                            fbase = dbase + 2;
+                            xb = sld_u8(fbase + xr);
+                            state = LS_WALK;
+                        }
                     }
-                }
-            }
-            continue;
-        }
-        if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
-            if (state == LS_PEND) {
-                uint32_t clen = 0, len;
-                const uint32_t pa = dbase + xr, pb = dbase + cand;
-                for (;;) {
-                    const uint32_t d0 = sld_u32u(pa + clen) ^ sld_u32u(pb + clen);
-                    const uint32_t d1 = sld_u32u(pa + clen + 4) ^ sld_u32u(pb + clen + 4);
-                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
-                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
-                    break;
-                }
-                if (len > kMaxMatch) len = kMaxMatch;
-                state = LS_WALK;
-                if (len > best) {
-                    best = len;
-                    res = (len << 16) | (xr - cand);
-                    if (best >= nice) { Mout[xr] = res; RDout[xr] = (uint16_t)(xr - cand); state = LS_IDLE; }
-                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
-                }
-                if (state == LS_WALK && --chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)((xr - cand) | 0x8000u); state = LS_IDLE; }
-            }
-            continue;
-        }
-#pragma unroll
-        for (uint32_t burst = 0; burst < kWalkBurst; burst++) {
-            if (state == LS_WALK) {
-                // dn = link of cr (loaded during the previous step); the three loads below are independent of each other
-                if (dn == 0 || cr < lowr + dn) { Mout[xr] = res; RDout[xr] = 0xffffu; state = LS_IDLE; } // chain ends or leaves the window
-                else {
-                    cr -= dn;
-                    dn = sld_u16(lbase + 2 * cr);
-                    const uint32_t fb = sld_u8(fbase + cr);
-                    const uint32_t dw = sld_u32u(dbase + cr) ^ xw0;
-                    if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
-                    // the byte at `best` and the first 3 (best == 2) / 4 bytes must match for a longer match
-                    if (fb == xb && (best == 2 ? (dw & 0x00ffffffu) : dw) == 0) { cand = cr; state = LS_PEND; }
-                    else if (--chain == 0) { Mout[xr] = res; RDout[xr] = (uint16_t)((xr - cr) | 0x8000u); state = LS_IDLE; }
                 }
             }
         }
@@ -467,7 +519,12 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
         const uint32_t nl = (te - ws + 7) / 8; // 8 links per uint4
         const uint4 *ls = reinterpret_cast<const uint4 *>(jb.Lr + ws);
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
-        for (uint32_t i = tid; i < nl; i += nthr) ld[i] = ls[i];
+        for (uint32_t i = tid; i < nl; i += nthr) {
+            // "no link" (0) is staged as 0xffff: the walk's range test then also ends the chain
+            uint4 v = ls[i];
+            v.x |= __vcmpeq2(v.x, 0u); v.y |= __vcmpeq2(v.y, 0u); v.z |= __vcmpeq2(v.z, 0u); v.w |= __vcmpeq2(v.w, 0u);
+            ld[i] = v;
+        }
     }
     __syncthreads();
     const long long t_1 = clock64();
