@@ -44,6 +44,8 @@ typedef struct zb_deflate_result {
     uint32_t gpu_launches; /* kernels launched for this call */
     int32_t exact_parity;  /* 1: bytes equal zlib-rs' deflate(Z_FINISH) at this level/strategy/memLevel; 0: valid stream only */
     float gpu_ms;          /* device time of the call (CUDA events), copies included when buffers are on the host */
+    uint32_t bits_used;    /* bits used in the last byte of the deflate data, 1..8 (deflateUsed, zlib-rs/src/deflate.rs:129) */
+    uint32_t reserved;
 } zb_deflate_result;
 
 /* One engine = one CUDA device + stream + grow-only device buffers.  Not thread safe; create one per thread. */
@@ -64,6 +66,8 @@ ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_
                                concatenate into one stream (pigz-style sharding) */
 #define ZB_FLAG_LOW_PARALLEL 2u /* levels 1 and 2: use the parallel level-3 kernel set instead of the exact warp-serial
                                    deflate_quick / deflate_fast (valid stream, smaller, not byte-identical; exact_parity = 0) */
+#define ZB_FLAG_CHECK_ADLER 4u /* raw stream (window_bits < 0), but also return the adler32 of the input in res->check: */
+#define ZB_FLAG_CHECK_CRC 8u   /* ... or its crc32 -- for callers that write the zlib / gzip framing themselves (gz_header, FDICT) */
 #define ZB_FLAG_MEMLEVEL(m) ((uint32_t)(m) << 8) /* deflateInit2's memLevel 1..9 (0 = default 8): lit_bufsize = 1 << (memLevel + 6)
                                                     sets the symbols per block (zlib-rs/src/deflate.rs:321, deflate/sym_buf.rs:23) */
 ZB_API int zb_deflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
@@ -82,6 +86,30 @@ typedef struct zb_inflate_result {
 
 ZB_API int zb_inflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                int window_bits, zb_inflate_result *res);
+
+/* Streaming building block (what inflate() of the zlib ABI runs on, zlib-rs/src/inflate.rs:2376-2457): decode the COMPLETE deflate
+ * blocks of a raw deflate segment.  src/dict/dst are host buffers; decoding starts at bit `start_bit` of src with the last
+ * `dict_len` (<= 32768) bytes of earlier output as the window.  Returns ZB_OK with
+ *   out_bytes   output of the complete blocks (a block that the input does not finish is not part of it and is decoded again by
+ *               the next call, which passes end_bit as its start_bit),
+ *   end_bit     the bit behind the last complete block,
+ *   final_block 1 when the BFINAL block was completed (end_bit is the bit behind its end-of-block code),
+ *   need_input  1 when the input ended inside a block,
+ *   sync_point  1 when it ended exactly in front of a stored block's LEN/NLEN (inflateSyncPoint),
+ *   check       check_start updated with the output (check_kind 1 adler32, 2 crc32, 0 none);
+ * ZB_E_BUF when dst_cap cannot hold the complete blocks (nothing is consumed), ZB_E_DATA with the reference's message on a
+ * corrupt block. */
+typedef struct zb_inflate_seg {
+    uint64_t out_bytes;
+    uint64_t end_bit;
+    uint32_t final_block, need_input, sync_point;
+    uint32_t check;
+    uint32_t gpu_launches;
+    float gpu_ms;
+    char msg[64];
+} zb_inflate_seg;
+ZB_API int zb_inflate_blocks(zb_engine *e, const void *src, size_t src_len, uint64_t start_bit, const void *dict, size_t dict_len,
+                             void *dst, size_t dst_cap, int check_kind, uint32_t check_start, zb_inflate_seg *out);
 
 ZB_API int zb_adler32(zb_engine *e, uint32_t start, const void *buf, size_t len, int on_device, uint32_t *out, float *gpu_ms);
 ZB_API int zb_crc32(zb_engine *e, uint32_t start, const void *buf, size_t len, int on_device, uint32_t *out, float *gpu_ms);

@@ -30,6 +30,7 @@ typedef const void *voidpc;
 typedef size_t z_size_t;
 typedef long z_off_t;
 typedef long long z_off64_t;
+typedef unsigned int z_crc_t;
 
 typedef voidpf (*alloc_func)(voidpf opaque, uInt items, uInt size);
 typedef void (*free_func)(voidpf opaque, voidpf address);
@@ -136,6 +137,7 @@ ZB_EXPORT int deflateCopy(z_streamp dest, z_streamp source);
 ZB_EXPORT int deflateSetHeader(z_streamp strm, gz_headerp head);
 ZB_EXPORT uLong deflateBound(z_streamp strm, uLong sourceLen);
 ZB_EXPORT int deflateTune(z_streamp strm, int good_length, int max_lazy, int nice_length, int max_chain);
+ZB_EXPORT int deflateUsed(z_streamp strm, int *bits); /* libz-rs-sys/src/lib.rs:1800 */
 
 /* inflate: :935 inflateInit_, :968 inflateInit2_, :637 inflate, :661 inflateEnd, :1040 inflateReset, :1065 inflateReset2,
  * :1006 inflateSetDictionary, :793 inflateSync, :716 inflateCopy, :841 inflateMark, :1131 inflatePrime */
@@ -171,6 +173,7 @@ ZB_EXPORT uLong crc32_combine64(uLong crc1, uLong crc2, z_off64_t len2);
 ZB_EXPORT uLong crc32_combine_gen(z_off_t len2);
 ZB_EXPORT uLong crc32_combine_gen64(z_off64_t len2);
 ZB_EXPORT uLong crc32_combine_op(uLong crc1, uLong crc2, uLong op);
+ZB_EXPORT const z_crc_t *get_crc_table(void); /* libz-rs-sys/src/lib.rs:253 */
 
 #define deflateInit(strm, level) deflateInit_((strm), (level), ZLIB_VERSION, (int)sizeof(z_stream))
 #define inflateInit(strm) inflateInit_((strm), ZLIB_VERSION, (int)sizeof(z_stream))

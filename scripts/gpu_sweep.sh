@@ -1,0 +1,7 @@
+#!/bin/bash
+# probe every variant under zlib_rs_b200/variants (scripts/variant_probe.py): golden check + timings
+mkdir -p gpurun_out
+for so in zlib_rs_b200/variants/libz_b200_*.so; do
+  name=$(basename $so .so); name=${name#libz_b200_}
+  echo "== $name $(ZB_LIB_PATH=$PWD/$so timeout 120 python scripts/variant_probe.py ${2:-6} 2>&1 | tail -1)"
+done 2>&1 | tee gpurun_out/sweep_${1:-s}.log

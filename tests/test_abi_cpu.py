@@ -92,7 +92,12 @@ def test_null_buffer_checksums_and_combine_algebra():
         assert L.adler32_combine64(a % 65521 | ((a >> 16) % 65521) << 16, b % 65521 | ((b >> 16) % 65521) << 16, n) == \
             Lo.zo_adler32_combine(a % 65521 | ((a >> 16) % 65521) << 16, b % 65521 | ((b >> 16) % 65521) << 16, n)
     assert L.zError(-3) == b"data error" and L.zError(-5) == b"buffer error"
-    assert L.compressBound(0) >= 13 and L.compressBound(1 << 20) >= (1 << 20) + 13
+    # deflate::compress_bound's documented values (zlib-rs/src/deflate.rs:2966-2968) and the oracle's restatement
+    assert (L.compressBound(1024), L.compressBound(4096), L.compressBound(65536)) == (1161, 4617, 73737)
+    Lo.zo_compress_bound.restype = ctypes.c_size_t
+    Lo.zo_compress_bound.argtypes = [ctypes.c_size_t]
+    for n in (0, 1, 8, 9, 100, 1 << 20, 15736320):
+        assert L.compressBound(n) == Lo.zo_compress_bound(n)
 
 
 def test_c_client_links_and_fails_loudly_without_a_device(tmp_path):

@@ -15,7 +15,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libz_b200.so")
+LIB_PATH = os.environ.get("ZB_LIB_PATH") or os.path.join(_HERE, "libz_b200.so")  # ZB_LIB_PATH: kernel-variant sweeps (scripts/build_variants.sh)
 
 Z_OK, Z_STREAM_END, Z_NEED_DICT = 0, 1, 2
 Z_ERRNO, Z_STREAM_ERROR, Z_DATA_ERROR, Z_MEM_ERROR, Z_BUF_ERROR, Z_VERSION_ERROR = -1, -2, -3, -4, -5, -6
@@ -38,7 +38,8 @@ class ZStream(ctypes.Structure):
 class DeflateResult(ctypes.Structure):
     _fields_ = [("out_bytes", ctypes.c_uint64), ("check", ctypes.c_uint32), ("data_type", ctypes.c_int32),
                 ("iterations", ctypes.c_uint32), ("n_symbols", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32),
-                ("gpu_launches", ctypes.c_uint32), ("exact_parity", ctypes.c_int32), ("gpu_ms", ctypes.c_float)]
+                ("gpu_launches", ctypes.c_uint32), ("exact_parity", ctypes.c_int32), ("gpu_ms", ctypes.c_float),
+                ("bits_used", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class InflateResult(ctypes.Structure):

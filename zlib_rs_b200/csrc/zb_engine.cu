@@ -73,6 +73,9 @@ int Engine::init(int dev)
     device = dev;
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&evf, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(upload_tables());
@@ -103,6 +106,9 @@ Engine::~Engine()
     if (d_check) cudaFree(d_check);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (evf) cudaEventDestroy(evf);
+    if (evt) cudaEventDestroy(evt);
+    if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -152,7 +158,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_MCHG, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -243,6 +249,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     RES(S_HDIFF, (size_t)nwords * 8, hdiff, uint32_t *)
     jb.hdiff_words = nwords;
     RES(S_HCOARSE, (size_t)(N >> 10) + 16, hcoarse, uint8_t *)
+    RES(S_MCHG, (((size_t)N >> 8) + 16) * 4 + 64, mchg, uint8_t *)
     RES(S_BLOCKS, (size_t)max_blocks * sizeof(BlockDesc), blocks, BlockDesc *)
     RES(S_BBASE, (size_t)max_blocks * 4, block_base, uint32_t *)
     uint32_t *d_freq;
@@ -314,8 +321,8 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     CK(cudaMemsetAsync(d_out, 0, out_cap, st));
     // checksum of the input (deflate.rs:1705-1713 computes it while filling the window)
     pbegin();
-    if (wrap == 1) { CK(launch_adler32(d_in, n, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
-    else if (wrap == 2) { CK(launch_crc32(d_in, n, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in, n, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    else if (wrap == 2 || (wrap == 0 && (flags & ZB_FLAG_CHECK_CRC))) { CK(launch_crc32(d_in, n, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
     else CK(cudaMemsetAsync(d_check, 0, 4, st));
     pend(8, 2);
 
@@ -389,7 +396,12 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     // few dirty tiles: small pieces on many SMs, few warps each (the walk of a sparse piece is issue-bound per warp)
                     // one wave of CTAs if possible: the per-piece latency, not the throughput, bounds a sparse pass
                     jb.match_sub = n_dirty > 9 ? kMatchSub : n_dirty > 2 ? 2048 : 512;
-                    const uint32_t mthreads = n_dirty > 2 ? 1024 : 256;
+                    uint32_t mthreads = n_dirty > 2 ? 1024 : 256;
+                    if (n_dirty > 9) { // experiment knobs for the dense passes (not part of the interface)
+                        static const char *e_sub = getenv("ZB_MSUB"), *e_thr = getenv("ZB_MTHREADS");
+                        if (e_sub) jb.match_sub = (uint32_t)atoi(e_sub);
+                        if (e_thr) mthreads = (uint32_t)atoi(e_thr);
+                    }
                     uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     uint32_t n_ptiles = npt, first_ptile = 0;
                     jb.match_list = nullptr;
@@ -432,7 +444,9 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                         nsub = nm ? nm : 1;
                         n_ptiles = np_ ? np_ : 1;
                     }
-                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 + ((kWSize + jb.match_sub) / 32 + 1) * 4 * 4 + 8192;
+                    // the dirty-bucket map and the changed-hole bitmaps are only staged from the second iteration on
+                    const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 +
+                                           (iters > 1 ? ((kWSize + jb.match_sub) / 32 + 1) * 4 * 4 + 8192 : 64);
                     jb.use_bucket_map = iters > 1;
                     pbegin();
                     k_match<<<nsub, mthreads, msmem, st>>>(jb);
@@ -448,10 +462,6 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     pend(3, 3);
                     pbegin();
                     k_holes<<<(nlists * kLongPerSub + 255) / 256, 256, 0, st>>>(jb, nlists);
-                    CK(cudaMemsetAsync(jb.tile_dirty, 0, nmt, st));
-                    CK(cudaMemsetAsync(jb.bucket_map, 0, 8192, st));
-                    CK(cudaMemsetAsync(jb.hcoarse, 0, (size_t)(N >> 10) + 16, st));
-                    CK(cudaMemsetAsync(&d_info->holes_changed, 0, 4, st));
                     k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
                     pend(4, 2);
                     launches += 7;
@@ -475,6 +485,12 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     if (iters > N / 257u + 4096u) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; } // every iteration settles at least one long match
                 }
             }
+            // the serial tail (one thread) and the symbols of the path write disjoint parts of syms[]: side by side
+            CK(cudaEventRecord(evf, st));
+            CK(cudaStreamWaitEvent(st2, evf, 0));
+            k_tail<<<1, 32, 0, st2>>>(jb);
+            launches++;
+            CK(cudaEventRecord(evt, st2));
             if (jb.tail_start > 0) {
                 pbegin();
                 k_emit<<<(jb.tail_start + 255) / 256, 256, 0, st>>>(jb);
@@ -482,8 +498,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 pend(4, 1);
             }
             pbegin();
-            k_tail<<<1, 32, 0, st>>>(jb);
-            launches++;
+            CK(cudaStreamWaitEvent(st, evt, 0));
             pend(5, 1);
             }
         }
@@ -534,6 +549,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     res->gpu_launches = launches;
     res->exact_parity = exact ? 1 : 0;
     res->gpu_ms = ms;
+    res->bits_used = (uint32_t)(h_info->total_bits & 7u) ? (uint32_t)(h_info->total_bits & 7u) : 8u;
     return ZB_OK;
 }
 
@@ -624,6 +640,13 @@ int zb_inflate(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, 
 {
     if (!z) return ZB_E_NODEVICE;
     return z->e.inflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, window_bits, res);
+}
+
+int zb_inflate_blocks(zb_engine *z, const void *src, size_t n, uint64_t start_bit, const void *dict, size_t dict_len, void *dst, size_t cap,
+                      int check_kind, uint32_t check_start, zb_inflate_seg *out)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.inflate_blocks(src, n, start_bit, dict, dict_len, dst, cap, check_kind, check_start, out);
 }
 
 int zb_adler32(zb_engine *z, uint32_t start, const void *buf, size_t len, int on_dev, uint32_t *out, float *ms)

@@ -15,7 +15,8 @@ struct Engine {
     static constexpr int kSlots = 40;
     struct Buf { void *p = nullptr; size_t cap = 0; };
     int device = -1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr; // st2: the serial tail runs beside k_emit
+    cudaEvent_t evf = nullptr, evt = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Buf bufs[kSlots];
     void *h_stage = nullptr;
@@ -43,6 +44,8 @@ struct Engine {
                 int window_bits, uint32_t flags, zb_deflate_result *res);
     int inflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int window_bits,
                 zb_inflate_result *res);
+    int inflate_blocks(const void *src, size_t n, uint64_t start_bit, const void *dict, size_t dict_len, void *dst, size_t dst_cap,
+                       int check_kind, uint32_t check_start, zb_inflate_seg *out);
     int checksum(bool crc, uint32_t start, const void *buf, size_t len, bool on_dev, uint32_t *out, float *ms);
 };
 

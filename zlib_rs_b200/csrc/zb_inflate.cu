@@ -33,6 +33,19 @@ struct InfState { // device result block
     uint32_t trailer_check; // value stored in the stream
     uint32_t trailer_len;   // gzip ISIZE
     uint32_t kind;          // 0 raw, 1 zlib, 2 gzip
+    // block-granular resume point (segment mode): the bit after the last COMPLETE block, and the output produced up to there
+    uint64_t blk_bit, blk_out;
+    uint32_t final_done;    // the BFINAL block was decoded completely
+    uint32_t stored_wait;   // stopped in front of the LEN/NLEN bytes of a stored block with an empty bit buffer (inflateSyncPoint)
+};
+
+// Segment mode of k_inflate (the streaming inflate() of zb_zlib.cu): raw deflate blocks starting at bit `start_bit` of src, with the
+// previous `dict_len` (<= 32768) bytes of output as the window.
+struct InfSeg {
+    uint64_t start_bit;
+    const uint8_t *dict;
+    uint32_t dict_len;
+    uint32_t on; // 0: whole stream with header and trailer (one-shot)
 };
 
 __device__ static const uint16_t d_lbase[31] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 0, 0};
@@ -121,7 +134,7 @@ struct InfShared {
 enum Cmd { C_NONE = 0, C_REFILL, C_FLUSH, C_COPY, C_DONE };
 
 __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src, uint64_t n, uint8_t *__restrict__ dst, uint64_t cap,
-                                                int window_bits, InfState *res)
+                                                int window_bits, InfState *res, InfSeg seg)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InfShared &S = *reinterpret_cast<InfShared *>(smem_raw);
@@ -143,6 +156,20 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
     uint32_t copy_len = 0, copy_dist = 0;
     uint32_t gz_fl = 0, gz_xl = 0;
 
+    // segment mode: the window in front of the segment occupies ring positions [0, D0); output position D0 + i is dst[i]
+    const uint64_t D0 = seg.on ? seg.dict_len : 0;
+    uint64_t blk_bit = seg.start_bit, blk_out = D0;
+    uint32_t final_done = 0, stored_wait = 0;
+    if (seg.on) {
+        for (uint32_t i = lane; i < seg.dict_len; i += 32) S.out[i] = seg.dict[i];
+        ifill = seg.start_bit >> 3;
+        oflush = D0;
+        ipos = seg.start_bit >> 3;
+        opos = D0;
+        consumed_bits = 8 * (seg.start_bit >> 3);
+        mode = 1;
+        kind = 0;
+    }
     if (lane == 0) {
         uint32_t root;
         uint32_t sym = 0;
@@ -159,7 +186,11 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
 #define NEED(nb) do { while (bits < (nb)) { hold |= (uint64_t)((ipos < n) ? S.in[ipos & (kInRing - 1)] : 0) << bits; ipos++; bits += 8; } } while (0)
 #define BITS(nb) ((uint32_t)(hold & ((1ull << (nb)) - 1)))
 #define DROP(nb) do { const uint32_t nb_ = (nb); hold >>= nb_; bits -= nb_; consumed_bits += nb_; } while (0)
-#define FAIL(code) do { err = (code); mode = 5; } while (0)
+// An error found after bits beyond the end of the input were consumed is a consequence of the zero padding, not of the data:
+// truncation has priority (the reference never interprets bits it does not have, inflate.rs NEEDBITS / PULLBYTE).
+#define FAIL(code) do { err = consumed_bits > 8 * n ? (uint32_t)IE_TRUNCATED : (uint32_t)(code); mode = 5; } while (0)
+// the next nb bits have been peeked but not dropped yet: are they all real?
+#define REAL(nb) (consumed_bits + (nb) <= 8 * n)
 
     for (;;) {
         uint32_t cmd = C_NONE;
@@ -173,6 +204,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
                 if (mode == 0) {
                     if (window_bits < 0) { mode = 1; continue; }
                     NEED(16);
+                    if (!REAL(16)) { FAIL(IE_TRUNCATED); continue; }
                     const uint32_t h = BITS(16);
                     if ((window_bits > 15) && h == 0x8b1f) { // gzip (inflate.rs:934-946)
                         kind = 2;
@@ -218,18 +250,25 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
                     continue;
                 }
                 if (mode == 1) {
-                    if (last) { DROP(bits & 7); mode = 4; continue; }
+                    if (seg.on && consumed_bits < seg.start_bit) { const uint32_t k0 = (uint32_t)(seg.start_bit & 7); NEED(k0); DROP(k0); continue; }
+                    if (last) {
+                        if (seg.on) { final_done = 1; blk_bit = consumed_bits; blk_out = opos; mode = 5; continue; } // the caller frames the trailer
+                        DROP(bits & 7); mode = 4; continue;
+                    }
+                    blk_bit = consumed_bits; blk_out = opos; // everything before this block header is complete
                     NEED(3);
                     last = (int)BITS(1);
                     const uint32_t type = (BITS(3) >> 1);
                     DROP(3);
                     if (type == 0) {
                         DROP(bits & 7);
+                        stored_wait = consumed_bits == 8 * n; // every real bit used up, LEN/NLEN still to come
                         NEED(32);
                         const uint32_t v = BITS(32);
                         DROP(32);
                         if ((v & 0xffff) != ((v >> 16) ^ 0xffff)) { FAIL(IE_STORED_LEN); continue; }
                         stored_left = v & 0xffff;
+                        stored_wait = 0;
                         mode = 2;
                     } else if (type == 1) {
                         lencode = S.lenfix; distcode = S.distfix; lenbits = 9; distbits = 5;
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
                     uint32_t k = 0;
                     while (stored_left && k < 4096) {
                         if (ifill < n && ifill - ipos < 16) break;
-                        if (opos >= cap) { FAIL(IE_OUTPUT_FULL); break; }
+                        if (opos - D0 >= cap) { FAIL(IE_OUTPUT_FULL); break; }
                         NEED(8);
                         S.out[opos & (kOutRing - 1)] = (uint8_t)BITS(8);
                         DROP(8);
@@ -304,7 +343,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
                         }
                         DROP(here.bits);
                         if (here.op == 0) {
-                            if (opos >= cap) { FAIL(IE_OUTPUT_FULL); break; }
+                            if (opos - D0 >= cap) { FAIL(IE_OUTPUT_FULL); break; }
                             S.out[opos & (kOutRing - 1)] = (uint8_t)here.val;
                             opos++;
                             continue;
@@ -326,7 +365,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
                         ex = here.op & 15;
                         if (ex) { dist += BITS(ex); DROP(ex); }
                         if (dist > opos) { FAIL(IE_TOO_FAR); break; }
-                        if (opos + len > cap) { FAIL(IE_OUTPUT_FULL); break; }
+                        if (opos - D0 + len > cap) { FAIL(IE_OUTPUT_FULL); break; }
                         if (consumed_bits > 8 * n) { FAIL(IE_TRUNCATED); break; }
                         if (len >= 24) { copy_len = len; copy_dist = dist; cmd = C_COPY; break; }
                         for (uint32_t j = 0; j < len; j++) S.out[(opos + j) & (kOutRing - 1)] = S.out[(opos + j - dist) & (kOutRing - 1)];
@@ -362,8 +401,8 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
         } else if (cmd == C_FLUSH || cmd == C_DONE) {
             const uint64_t opos0 = __shfl_sync(0xffffffffu, opos, 0);
             const uint64_t upto = cmd == C_DONE ? opos0 : oflush + kOutRing / 2; // the trigger guarantees opos0 >= upto
-            const uint64_t end = upto > cap ? cap : upto;
-            for (uint64_t i = oflush + lane; i < end; i += 32) dst[i] = S.out[i & (kOutRing - 1)];
+            const uint64_t end = upto - D0 > cap ? cap + D0 : upto;
+            for (uint64_t i = oflush + lane; i < end; i += 32) dst[i - D0] = S.out[i & (kOutRing - 1)];
             if (end > oflush) oflush = end;
             __syncwarp();
             if (cmd == C_DONE) break;
@@ -391,8 +430,12 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
         }
     }
     if (lane == 0) {
-        res->out_bytes = opos;
+        res->out_bytes = opos - D0;
         res->in_bytes = (consumed_bits + 7) >> 3;
+        res->blk_bit = blk_bit;
+        res->blk_out = blk_out - D0;
+        res->final_done = final_done;
+        res->stored_wait = stored_wait;
         res->err = err;
         res->trailer_check = tr_check;
         res->trailer_len = tr_len;
@@ -402,6 +445,7 @@ __global__ void __launch_bounds__(32) k_inflate(const uint8_t *__restrict__ src,
 #undef BITS
 #undef DROP
 #undef FAIL
+#undef REAL
 }
 
 // ================================================================================================
@@ -617,7 +661,12 @@ __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n,
         for (;;) {
             uint32_t v, d;
             const int t = dec_symbol(S, br, lm, dm, v, d);
-            if (t == 0) { o++; continue; }
+            if (t == 0) {
+                // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
+                o++;
+                if ((o & 63u) == 0 && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; break; }
+                continue;
+            }
             if (t == 1) {
                 o += v;
                 if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; break; }
@@ -718,7 +767,7 @@ __global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t 
     if (warp == 0) {
         // ---- decoding warp
         BitRd br;
-        uint32_t lm = 0, dm = 0, done = 0;
+        uint32_t lm = 0, dm = 0, done = 0, produced = 0;
         if (lane == 0) {
             uint32_t lenbits = 0, distbits = 0, bf;
             const int rc = dec_setup(S.d, src, n, b.start_bit, br, lenbits, distbits, &bf);
@@ -735,9 +784,10 @@ __global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t 
                 while (!done && cnt < 32) {
                     uint32_t v, d;
                     const int t = dec_symbol(S.d, br, lm, dm, v, d);
-                    if (t == 0) S.d.q[q][cnt++] = v;
-                    else if (t == 1) S.d.q[q][cnt++] = (v << 16) | d;
+                    if (t == 0) { S.d.q[q][cnt++] = v; produced++; }
+                    else if (t == 1) { S.d.q[q][cnt++] = (v << 16) | d; produced += v; }
                     else { done = 1; if (t < 0) S.d.err = 1; }
+                    if (produced > b.out_len) { done = 1; S.d.err = 1; } // k_inf_scan measured this block: cannot happen, but never loop
                 }
                 S.d.qn[q] = cnt;
                 S.d.qfin[q] = done;
@@ -953,7 +1003,7 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         }
     }
     if (!done) {
-        k_inflate<<<1, 32, sizeof(InfShared), st>>>(d_src, n, d_dst, dst_cap, window_bits, dis);
+        k_inflate<<<1, 32, sizeof(InfShared), st>>>(d_src, n, d_dst, dst_cap, window_bits, dis, InfSeg{0, nullptr, 0, 0});
         launches += 1;
         CKI(cudaMemcpyAsync(his, dis, sizeof(InfState), cudaMemcpyDeviceToHost, st));
         CKI(cudaStreamSynchronize(st));
@@ -988,6 +1038,60 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     CKI(cudaEventElapsedTime(&res->gpu_ms, ev0, ev1));
     res->status = status;
     res->gpu_launches = launches;
+    return status;
+}
+
+// Streaming building block: decode the COMPLETE deflate blocks of a raw segment (host buffers).  See zb_engine.h.
+int Engine::inflate_blocks(const void *src, size_t n, uint64_t start_bit, const void *dict, size_t dict_len, void *dst, size_t dst_cap,
+                           int check_kind, uint32_t check_start, zb_inflate_seg *out)
+{
+    if (!out || (!src && n) || (!dst && dst_cap) || dict_len > kWSize || (dict_len && !dict) || start_bit > 8ull * n) return ZB_E_PARAM;
+    memset(out, 0, sizeof *out);
+    CKI(cudaSetDevice(device));
+    int rc;
+    void *p;
+    CKI(cudaEventRecord(ev0, st));
+    if ((rc = reserve(19 /*S_INF0*/, n + kWSize + 128, &p)) != ZB_OK) return rc;
+    uint8_t *d_src = static_cast<uint8_t *>(p);
+    uint8_t *d_dict = d_src + ((n + 63) & ~(size_t)63);
+    if (n) CKI(cudaMemcpyAsync(d_src, src, n, cudaMemcpyHostToDevice, st));
+    if (dict_len) CKI(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, st));
+    if ((rc = reserve(20 /*S_INF1*/, dst_cap + 64, &p)) != ZB_OK) return rc;
+    uint8_t *d_dst = static_cast<uint8_t *>(p);
+    InfState *dis = static_cast<InfState *>(d_inf_state), *his = static_cast<InfState *>(h_inf_state);
+    k_inflate<<<1, 32, sizeof(InfShared), st>>>(d_src, n, d_dst, dst_cap, -15, dis, InfSeg{start_bit, d_dict, (uint32_t)dict_len, 1});
+    launches = 1;
+    CKI(cudaMemcpyAsync(his, dis, sizeof(InfState), cudaMemcpyDeviceToHost, st));
+    CKI(cudaStreamSynchronize(st));
+    CKI(cudaGetLastError());
+    int status = ZB_OK;
+    const bool truncated = his->err == IE_TRUNCATED;
+    if (his->err == IE_OUTPUT_FULL) status = ZB_E_BUF;
+    else if (his->err != IE_OK && !truncated) { status = ZB_E_DATA; snprintf(out->msg, sizeof out->msg, "%s", inf_msg(his->err)); }
+    // what the complete blocks produced is final, whatever happened behind them
+    out->out_bytes = status == ZB_E_BUF ? 0 : his->blk_out;
+    out->end_bit = status == ZB_E_BUF ? start_bit : his->blk_bit;
+    out->final_block = his->final_done;
+    out->need_input = truncated;
+    out->sync_point = truncated && his->stored_wait;
+    uint32_t check = check_start;
+    if (check_kind && out->out_bytes) {
+        void *d_ck;
+        const size_t ck_bytes = ((size_t)out->out_bytes / 16384 + 16) * 8;
+        if ((rc = reserve(18 /*S_CK*/, ck_bytes, &d_ck)) != ZB_OK) return rc;
+        if (check_kind == 2) CKI(launch_crc32(d_dst, out->out_bytes, check_start, d_ck, ck_bytes, d_check, st));
+        else CKI(launch_adler32(d_dst, out->out_bytes, check_start, d_ck, ck_bytes, d_check, st));
+        launches += 2;
+        CKI(cudaMemcpyAsync(h_info, d_check, 4, cudaMemcpyDeviceToHost, st));
+        CKI(cudaStreamSynchronize(st));
+        check = *reinterpret_cast<uint32_t *>(h_info);
+    }
+    out->check = check;
+    if (out->out_bytes) CKI(cudaMemcpyAsync(dst, d_dst, out->out_bytes, cudaMemcpyDeviceToHost, st));
+    CKI(cudaEventRecord(ev1, st));
+    CKI(cudaStreamSynchronize(st));
+    CKI(cudaEventElapsedTime(&out->gpu_ms, ev0, ev1));
+    out->gpu_launches = launches;
     return status;
 }
 

@@ -243,10 +243,28 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 // compare.  Position fetches and compares are batched -- they run only when at least kBatch lanes want them
 // (or nobody can walk) -- so the common walk step is not diluted by the rarer, longer code paths, and lanes
 // with short chains never wait for lanes with long ones.
-constexpr uint32_t kBatch = 8;
-constexpr uint32_t kWalkBurst = 4; // walk steps between two schedule checks
-constexpr uint32_t kCmpBurst = 4;  // 8-byte compare steps per compare burst
-enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3, LS_FIN = 4 };
+#ifndef ZB_T_IDLE
+#define ZB_T_IDLE 8
+#endif
+#ifndef ZB_T_CMP
+#define ZB_T_CMP 8
+#endif
+#ifndef ZB_WALK_BURST
+#define ZB_WALK_BURST 4
+#endif
+#ifndef ZB_CMP_BURST
+#define ZB_CMP_BURST 4
+#endif
+constexpr uint32_t kBatch = ZB_T_IDLE;         // idle lanes that trigger a refill
+constexpr uint32_t kBatchCmp = ZB_T_CMP;       // pending lanes that trigger a compare burst
+constexpr uint32_t kWalkBurst = ZB_WALK_BURST; // walk steps between two schedule checks
+constexpr uint32_t kCmpBurst = ZB_CMP_BURST;   // 8-byte compare steps per compare burst
+#ifdef ZB_QUICK16
+#define kHitState LS_HIT
+#else
+#define kHitState LS_PEND
+#endif
+enum { LS_IDLE = 0, LS_WALK = 1, LS_PEND = 2, LS_DONE = 3, LS_FIN = 4, LS_HIT = 5 };
 
 // explicit shared-space loads on 32-bit shared addresses (keeps address-space conversions out of the hot loop)
 __device__ __forceinline__ uint32_t sld_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -303,6 +321,9 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     uint32_t lowr = 0;   // lowest admissible candidate (relative)
     uint32_t clen = 0;   // PEND: bytes known equal so far
     uint32_t rd = 0;     // FIN: reach code to store
+#ifdef ZB_QUICK16
+    uint32_t xw0 = 0, xw1 = 0, xw2 = 0, xw3 = 0; // first 16 bytes of x: a filter hit is compared against them at once
+#endif
     uint32_t state = LS_IDLE;
     for (;;) {
         // ---- walk burst
@@ -322,22 +343,48 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     if (k + 1 == kWalkBurst) more = true;
                 }
                 if (!more) {
-                    if (fb == xb) { state = LS_PEND; clen = 0; }
+                    if (fb == xb) { state = kHitState; clen = 0; }
                     else { rd = 0xffffu; state = LS_FIN; }
                 }
             } else {
                 const uint32_t fb = sld_u8(fbase + cr);
                 dn = sld_u16(lbase + 2 * cr);
-                if (fb == xb) { state = LS_PEND; clen = 0; }
+                if (fb == xb) { state = kHitState; clen = 0; }
                 else if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; } // budget
                 else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
                 else cr -= dn;
             }
         }
+#ifdef ZB_QUICK16
+        // ---- a filter hit is compared with the first 16 bytes of x right away (three out of four compares end there)
+        if (state == LS_HIT) {
+            const uint32_t pb = dbase + cr, al = pb & ~3u, sh = (pb & 3u) * 8u;
+            const uint32_t w0 = sld_u32(al), w1 = sld_u32(al + 4), w2 = sld_u32(al + 8), w3 = sld_u32(al + 12), w4 = sld_u32(al + 16);
+            const uint32_t d0 = __funnelshift_r(w0, w1, sh) ^ xw0, d1 = __funnelshift_r(w1, w2, sh) ^ xw1;
+            const uint32_t d2 = __funnelshift_r(w2, w3, sh) ^ xw2, d3 = __funnelshift_r(w3, w4, sh) ^ xw3;
+            if ((d0 | d1 | d2 | d3) == 0) { state = LS_PEND; clen = 16; }
+            else {
+                const uint32_t dl = d0 ? d0 : d1 ? d1 : d2 ? d2 : d3;
+                const uint32_t len = (d0 ? 0u : d1 ? 4u : d2 ? 8u : 12u) + ((__ffs(dl) - 1) >> 3);
+                state = LS_WALK;
+                if (len > best) {
+                    best = len;
+                    res = (len << 16) | (xr - cr);
+                    if (best >= nice) { rd = xr - cr; state = LS_FIN; }
+                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
+                }
+                if (state == LS_WALK) { // on to the next candidate
+                    if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; }
+                    else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
+                    else cr -= dn;
+                }
+            }
+        }
+#endif
         // ---- compare burst
         const uint32_t m_walk = __ballot_sync(0xffffffffu, state == LS_WALK);
         const uint32_t m_pend = __ballot_sync(0xffffffffu, state == LS_PEND);
-        if (m_pend && (__popc(m_pend) >= (int)kBatch || m_walk == 0)) {
+        if (m_pend && (__popc(m_pend) >= (int)kBatchCmp || m_walk == 0)) {
             if (state == LS_PEND) {
                 uint32_t pa = dbase + xr + clen, pb = dbase + cr + clen;
                 uint32_t len = 0;
@@ -373,7 +420,10 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             }
         }
         // ---- results
-        if (state == LS_FIN) { Mout[xr] = res; RDout[xr] = (uint16_t)rd; state = LS_IDLE; }
+        if (state == LS_FIN) {
+            if (filt && Mout[xr] != res) jb.mchg[(ws + xr) >> 6] = 1; // k_nxt redoes only the macro steps that read a changed M
+            Mout[xr] = res; RDout[xr] = (uint16_t)rd; state = LS_IDLE;
+        }
         // ---- refill
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
         const uint32_t m_busy = __ballot_sync(0xffffffffu, state == LS_WALK || state == LS_PEND);
@@ -423,13 +473,24 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                         const uint32_t d0 = sld_u16(lbase + 2 * xr);
                         lowr = xr > kMaxDist ? xr - kMaxDist : 0;
                         if (ws == 0 && lowr == 0) lowr = 1;
-                        if (xr < lowr + d0) { Mout[xr] = 0; RDout[xr] = 0xffffu; } // no candidate in the window
+                        if (xr < lowr + d0) { // no candidate in the window
+                            if (filt && Mout[xr] != 0) jb.mchg[(ws + xr) >> 6] = 1;
+                            Mout[xr] = 0; RDout[xr] = 0xffffu;
+                        }
                         else {
                             cr = xr - d0;
                             if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
                             best = 2; chain = budget; res = 0;
                             fbase = dbase + 2;
                             xb = sld_u8(fbase + xr);
+#ifdef ZB_QUICK16
+                            {
+                                const uint32_t pa = dbase + xr, al = pa & ~3u, sh = (pa & 3u) * 8u;
+                                const uint32_t w0 = sld_u32(al), w1 = sld_u32(al + 4), w2 = sld_u32(al + 8), w3 = sld_u32(al + 12), w4 = sld_u32(al + 16);
+                                xw0 = __funnelshift_r(w0, w1, sh); xw1 = __funnelshift_r(w1, w2, sh);
+                                xw2 = __funnelshift_r(w2, w3, sh); xw3 = __funnelshift_r(w3, w4, sh);
+                            }
+#endif
                             state = LS_WALK;
                         }
                     }
@@ -556,6 +617,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             Match m = lm_walk(a, x, 0xffffffffu, lp);
             if (m.len) v = (m.len << 16) | (x - m.start);
         }
+        if (jb.use_bucket_map && jb.M[x] != v) jb.mchg[x >> 6] = 1;
         jb.M[x] = v;
         jb.SK[x] = 0xffffu; // reach unknown: any changed hole of the bucket in the window invalidates
     }
@@ -586,6 +648,16 @@ __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
     if (!path_tile_dirty(jb, tile)) return;
     const uint32_t p = tile * kPathTile + (blockIdx.x % per) * 1024 + threadIdx.x;
     if (p >= jb.tail_start) return;
+    if (jb.use_bucket_map) {
+        // A macro step reads M only at positions [p, p + delta] (its loop-tops and look-ahead positions, the last one being the
+        // next canonical loop-top), data bytes and the window schedule: if no M in that range changed in this iteration's match
+        // pass, nxt[p] stands.
+        const uint32_t old = jb.nxt[p];
+        const uint32_t b0 = p >> 6, b1 = min(p + (old & 0xffffu), jb.N) >> 6;
+        bool chg = false;
+        for (uint32_t b = b0; b <= b1; b++) chg = chg || jb.mchg[b];
+        if (!chg) return;
+    }
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
     const uint32_t long_len = 16 * jb.lp.lazy;
     uint32_t ns = 0;
@@ -798,6 +870,15 @@ __global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
 __global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        // the per-iteration flags that k_holes_cmp (next launch) sets, and the changed-M flags k_nxt (previous launch) consumed
+        const uint32_t nthr = gridDim.x * blockDim.x;
+        for (uint32_t i = t; i < jb.nmt; i += nthr) jb.tile_dirty[i] = 0;
+        for (uint32_t i = t; i < 2048; i += nthr) jb.bucket_map[i] = 0;
+        for (uint32_t i = t; i < (jb.N >> 10) + 16; i += nthr) jb.hcoarse[i] = 0;
+        for (uint32_t i = t; i < (jb.N >> 8) + 16; i += nthr) reinterpret_cast<uint32_t *>(jb.mchg)[i] = 0; // 1 byte / 64 positions
+        if (t == 0) jb.info->holes_changed = 0;
+    }
     const uint32_t list = t / kLongPerSub, slot = t % kLongPerSub;
     if (list >= nlists || slot >= jb.long_cnt[list]) return;
     const uint32_t p = jb.long_list[(size_t)list * kLongPerSub + slot];
@@ -843,7 +924,7 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
     if (a != b) {
         jb.hcoarse[w >> 5] = 1;
         const uint32_t t = (w * 32) / kMatchTile;
-        atomicAdd(&jb.info->holes_changed, 1u); // number of changed bitmap words
+        jb.info->holes_changed = 1u; // iteration control: some word changed (plain store, every writer stores the same value)
         jb.tile_dirty[t] = 1;
         if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
         jb.holes[w] = b;

@@ -49,6 +49,7 @@ struct JobBufs {
     uint32_t *hdiff;      // two bitmaps of hdiff_words words: positions that became holes / stopped being holes in the last iteration
     uint32_t hdiff_words;
     uint8_t *hcoarse;     // one flag per 1024 positions: some hole changed there
+    uint8_t *mchg;        // one flag per 64 positions: k_match stored a different M there in this iteration (k_nxt's filter)
     uint32_t *holes;      // bitmap, (N >> 5) + 2 words
     uint32_t *holes_new;
     uint32_t *M;          // N + kPad

@@ -70,18 +70,34 @@ struct DState {
     std::vector<uint8_t> in, out;
     size_t out_pos;
     gz_header *gzhead;
+    int bits_used;    // deflateUsed: bits used in the last byte written (8 after a byte-aligned end)
 };
 
+// Streaming inflate state.  The stream is processed at the granularity of deflate blocks: header and trailer bytes are framing and
+// are parsed here; the blocks are decoded on the GPU by zb_inflate_blocks() (complete blocks only -- a block whose end has not
+// arrived yet stays in `in` and is decoded by a later call), or by the block-parallel one-shot decoder when a whole stream is there.
+enum IPhase { IP_HEAD = 0, IP_DICT, IP_BLOCKS, IP_TRAILER, IP_DONE, IP_BAD };
 struct IState {
     uint32_t magic;
-    int window_bits;
-    int status; // 0 collecting, 1 output ready, 2 done, -1 bad
-    std::vector<uint8_t> in, out;
-    size_t out_pos;
-    size_t last_attempt;
-    int result;
+    int window_bits;   // as given to inflateInit2 / inflateReset2
+    int wrap;          // bit 0 zlib, bit 1 gzip, bit 2 validate the check value (inflate.rs: state.wrap)
+    int wbits;         // 0: take it from the zlib header
+    int phase;
+    int gzip;          // -1 no header seen yet, 0 zlib stream, 1 gzip stream (gzip_flags of the reference >= 0)
+    int result;        // latched return code of IP_BAD
     char msg[64];
-    uint64_t consumed;
+    std::vector<uint8_t> in;      // compressed bytes not consumed yet; decoding resumes at bit `bit_off` of in[0]
+    uint32_t bit_off;
+    std::vector<uint8_t> window;  // last <= 32768 bytes of output (or the preset dictionary)
+    std::vector<uint8_t> out;     // decoded, not yet delivered
+    size_t out_pos;
+    uint32_t check;               // running adler32 / crc32 of the output
+    uint64_t total;               // output bytes decoded so far (gzip ISIZE)
+    uint32_t dictid;
+    bool have_dict, tried_oneshot, sync_point;
+    size_t tried_len;             // in.size() at the last decode attempt that needed more input
+    gz_header *head;
+    uint32_t dmax;
 };
 
 DState *dstate(z_streamp s)
@@ -216,9 +232,38 @@ int deflateResetKeep(z_streamp strm)
     d->check = d->wrap == 2 ? 0 : 1;
     d->check_len = 0;
     d->in.clear(); d->out.clear(); d->out_pos = 0;
+    d->bits_used = 0;
     return Z_OK;
 }
 int deflateReset(z_streamp strm) { return deflateResetKeep(strm); }
+
+// gzip header of a stream with deflateSetHeader fields (zlib-rs/src/deflate.rs:2574-2697): FTEXT/FHCRC/FEXTRA/FNAME/FCOMMENT flags,
+// mtime, XFL from level/strategy, OS, then extra (16-bit length), name and comment (zero terminated) and the low 16 bits of the
+// crc32 of everything before it.  Pure framing; the header crc is computed by the crc32 kernel like every other checksum here.
+static int gzip_header_bytes(const DState *d, std::vector<uint8_t> &h)
+{
+    const uint8_t xfl = d->level == 9 ? 2 : (d->strategy >= Z_HUFFMAN_ONLY || d->level < 2) ? 4 : 0;
+    const gz_header *g = d->gzhead;
+    h.clear();
+    if (!g) { const uint8_t b[10] = {31, 139, 8, 0, 0, 0, 0, 0, xfl, 3}; h.assign(b, b + 10); return Z_OK; }
+    const uint8_t flags = (uint8_t)((g->text ? 1 : 0) + (g->hcrc ? 2 : 0) + (g->extra ? 4 : 0) + (g->name ? 8 : 0) + (g->comment ? 16 : 0));
+    const uint32_t t = (uint32_t)g->time;
+    const uint8_t b[10] = {31, 139, 8, flags, (uint8_t)t, (uint8_t)(t >> 8), (uint8_t)(t >> 16), (uint8_t)(t >> 24), xfl, (uint8_t)g->os};
+    h.assign(b, b + 10);
+    if (g->extra) {
+        h.push_back((uint8_t)g->extra_len); h.push_back((uint8_t)(g->extra_len >> 8));
+        h.insert(h.end(), g->extra, g->extra + (g->extra_len & 0xffffu));
+    }
+    if (g->name) h.insert(h.end(), g->name, g->name + strlen(reinterpret_cast<const char *>(g->name)) + 1);
+    if (g->comment) h.insert(h.end(), g->comment, g->comment + strlen(reinterpret_cast<const char *>(g->comment)) + 1);
+    if (g->hcrc) {
+        uint32_t c = 0;
+        zb_engine *e = engine();
+        if (!e || zb_crc32(e, 0, h.data(), h.size(), 0, &c, nullptr) != ZB_OK) return Z_MEM_ERROR;
+        h.push_back((uint8_t)c); h.push_back((uint8_t)(c >> 8));
+    }
+    return Z_OK;
+}
 
 static int run_segment(z_streamp strm, DState *d, bool final)
 {
@@ -229,6 +274,28 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     const size_t base = d->out.size();
     const size_t cap = zb_deflate_bound(n) + 64;
     int rc;
+    if (final && !d->any_segment && d->wrap == 2 && d->gzhead) {
+        // one-shot gzip stream with a caller-supplied header: the engine writes the raw deflate data and returns the crc32 of the
+        // input; header and trailer (crc32, isize; deflate.rs:2773-2785) are framing
+        std::vector<uint8_t> h;
+        rc = gzip_header_bytes(d, h);
+        if (rc != Z_OK) { strm->msg = kNoDevice; return rc; }
+        d->out.insert(d->out.end(), h.begin(), h.end());
+        const size_t b1 = d->out.size();
+        d->out.resize(b1 + cap);
+        const int wb = d->window_bits - 16;
+        rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + b1, cap, 0, d->level, d->strategy, -wb,
+                           ZB_FLAG_CHECK_CRC | ZB_FLAG_MEMLEVEL(d->mem_level), &r);
+        if (rc != ZB_OK) { d->out.resize(base); strm->msg = zb_last_error(); return map_rc(rc); }
+        d->out.resize(b1 + r.out_bytes);
+        for (int i = 0; i < 4; i++) d->out.push_back((uint8_t)(r.check >> (8 * i)));
+        for (int i = 0; i < 4; i++) d->out.push_back((uint8_t)((uint32_t)n >> (8 * i)));
+        strm->adler = r.check;
+        d->bits_used = (int)r.bits_used;
+        if (strm->data_type == Z_UNKNOWN) strm->data_type = r.data_type;
+        d->in.clear();
+        return Z_OK;
+    }
     if (final && !d->any_segment) {
         // the one-shot path: byte-identical to the reference's deflate(Z_FINISH) at every level, strategy and memLevel (32 KiB window)
         d->out.resize(base + cap);
@@ -237,6 +304,7 @@ static int run_segment(z_streamp strm, DState *d, bool final)
         if (rc != ZB_OK) { d->out.resize(base); strm->msg = zb_last_error(); return map_rc(rc); }
         d->out.resize(base + r.out_bytes);
         strm->adler = r.check;
+        d->bits_used = (int)r.bits_used;
         if (strm->data_type == Z_UNKNOWN) strm->data_type = r.data_type;
         d->in.clear();
         return Z_OK;
@@ -249,9 +317,10 @@ static int run_segment(z_streamp strm, DState *d, bool final)
             h += 31 - (h % 31);
             d->out.push_back((uint8_t)(h >> 8)); d->out.push_back((uint8_t)h);
         } else if (d->wrap == 2) {
-            const uint8_t xfl = d->level == 9 ? 2 : (d->strategy >= Z_HUFFMAN_ONLY || d->level < 2) ? 4 : 0;
-            const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, xfl, 3};
-            d->out.insert(d->out.end(), g, g + 10);
+            std::vector<uint8_t> h;
+            rc = gzip_header_bytes(d, h);
+            if (rc != Z_OK) { strm->msg = kNoDevice; return rc; }
+            d->out.insert(d->out.end(), h.begin(), h.end());
         }
         d->header_done = true;
     }
@@ -262,6 +331,7 @@ static int run_segment(z_streamp strm, DState *d, bool final)
                        (final ? 0 : ZB_FLAG_NOT_LAST) | ZB_FLAG_MEMLEVEL(d->mem_level), &r);
     if (rc != ZB_OK) { d->out.resize(b2); strm->msg = zb_last_error(); return map_rc(rc); }
     d->out.resize(b2 + r.out_bytes);
+    d->bits_used = (int)r.bits_used;
     // running check value over all consumed input (segment checks chained with the combine algebra)
     uint32_t seg = 0;
     if (d->wrap == 1) { zb_adler32(e, 1, d->in.data(), n, 0, &seg, nullptr); d->check = adler_combine(d->check, seg, n); }
@@ -387,19 +457,72 @@ int deflateCopy(z_streamp dest, z_streamp source)
 }
 int deflateSetHeader(z_streamp strm, gz_headerp head)
 {
+    // deflate::set_header (zlib-rs/src/deflate.rs:3151-3161): only a gzip stream takes a header; the fields are written with the
+    // gzip header of the next segment (gzip_header_bytes above)
     DState *d = dstate(strm);
     if (!d || d->wrap != 2) return Z_STREAM_ERROR;
-    d->gzhead = head; // fields other than the defaults are not emitted by the engine yet
+    d->gzhead = head;
     return Z_OK;
 }
+
+namespace {
+// zlib-rs/src/deflate.rs:2975-2994, 3163-3184: compress_bound_help / deflate_quick_overhead
+size_t quick_overhead(size_t x) { return (x * (9 - 8) + 7) >> 3; }
+size_t bound_help(size_t n, size_t wrap_len) { return n + (n == 0 ? 1 : 0) + (n < 9 ? 1 : 0) + quick_overhead(n) + ((3 + 15 + 6) >> 3) + wrap_len; }
+}
+
 uLong deflateBound(z_streamp strm, uLong sourceLen)
 {
-    (void)strm;
-    return (uLong)zb_deflate_bound(sourceLen) + 32;
+    // deflate::bound (zlib-rs/src/deflate.rs:3193-3285)
+    const size_t n = sourceLen;
+    const size_t comp_len = n + ((n + 7) >> 3) + ((n + 63) >> 6) + 5;
+    DState *d = dstate(strm);
+    if (!d) return (uLong)(comp_len + 6);
+    size_t wrap_len = 6;
+    if (d->wrap == 0) wrap_len = 0;
+    else if (d->wrap == 1) wrap_len = 6; // (+4 once a dictionary is set: strstart != 0)
+    else if (d->wrap == 2) {
+        wrap_len = 18;
+        if (const gz_header *g = d->gzhead) {
+            if (g->extra) wrap_len += 2 + g->extra_len;
+            if (g->name) wrap_len += strlen(reinterpret_cast<const char *>(g->name)) + 1;
+            if (g->comment) wrap_len += strlen(reinterpret_cast<const char *>(g->comment)) + 1;
+            if (g->hcrc) wrap_len += 2;
+        }
+    }
+    int wb = d->window_bits < 0 ? -d->window_bits : d->window_bits > 15 ? d->window_bits - 16 : d->window_bits;
+    if (wb == 8) wb = 9;
+    if (wb != MAX_WBITS) {
+        if (d->level == 0) return (uLong)(n + (n >> 5) + (n >> 7) + (n >> 11) + 7 + wrap_len);
+        return (uLong)(comp_len + wrap_len);
+    }
+    return (uLong)bound_help(n, wrap_len);
 }
-int deflateTune(z_streamp strm, int, int, int, int) { return dstate(strm) ? Z_OK : Z_STREAM_ERROR; }
 
-uLong compressBound(uLong sourceLen) { return (uLong)zb_deflate_bound(sourceLen) + 32; }
+int deflateTune(z_streamp strm, int good_length, int max_lazy, int nice_length, int max_chain)
+{
+    // deflate::tune (zlib-rs/src/deflate.rs:2699-2713) overwrites the four matcher parameters of the level.  The kernels take them
+    // from the level table; a request that changes nothing is accepted, anything else is refused rather than silently ignored.
+    DState *d = dstate(strm);
+    if (!d) return Z_STREAM_ERROR;
+    static const int tab[10][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {4, 4, 8, 4}, {4, 6, 16, 6}, {4, 12, 32, 24}, {8, 16, 32, 32},
+                                   {8, 16, 128, 128}, {8, 32, 128, 256}, {32, 128, 258, 1024}, {32, 258, 258, 4096}};
+    const int *t = tab[d->level];
+    if (good_length == t[0] && max_lazy == t[1] && nice_length == t[2] && max_chain == t[3]) return Z_OK;
+    strm->msg = "deflateTune: matcher parameters other than the level's own are not implemented by the B200 engine";
+    return Z_STREAM_ERROR;
+}
+
+int deflateUsed(z_streamp strm, int *bits)
+{
+    // libz-rs-sys/src/lib.rs:1800-1810
+    DState *d = dstate(strm);
+    if (!d) return Z_STREAM_ERROR;
+    if (bits) *bits = d->bits_used;
+    return Z_OK;
+}
+
+uLong compressBound(uLong sourceLen) { return (uLong)bound_help(sourceLen, 6); } // deflate::compress_bound (deflate.rs:2975)
 
 int compress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen, int level)
 {
@@ -593,37 +716,52 @@ int uncompress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLe
 }
 
 // ---------------------------------------------------------------- checksums
-static void need_engine_or_die()
+// The checksum entry points cannot report an error (zlib's signatures), and nothing may abort across the C boundary
+// (SURVEY.md 8b): without a usable device they say so on stderr once and return the value for an empty buffer.  There is no CPU
+// fallback that could return a silently different kind of answer.
+static bool checksum_failed(const char *what)
 {
-    if (!engine()) {
-        fprintf(stderr, "libz_b200: %s (%s); adler32/crc32 have no CPU fallback\n", kNoDevice, zb_last_error());
-        abort();
+    static bool told = false;
+    if (!told) {
+        told = true;
+        fprintf(stderr, "libz_b200: %s needs a CUDA device and has no CPU fallback (%s); returning the initial value\n", what, zb_last_error());
     }
+    return true;
 }
 uLong adler32_z(uLong adler, const Bytef *buf, z_size_t len)
 {
     if (!buf) return 1; // libz-rs-sys/src/lib.rs:307-312
-    need_engine_or_die();
     uint32_t out = 0;
-    if (zb_adler32(engine(), (uint32_t)adler, buf, len, 0, &out, nullptr) != ZB_OK) {
-        fprintf(stderr, "libz_b200: adler32 failed: %s\n", zb_last_error());
-        abort();
-    }
+    zb_engine *e = engine();
+    if (!e || zb_adler32(e, (uint32_t)adler, buf, len, 0, &out, nullptr) != ZB_OK) { checksum_failed("adler32"); return 1; }
     return out;
 }
 uLong adler32(uLong adler, const Bytef *buf, uInt len) { return adler32_z(adler, buf, len); }
 uLong crc32_z(uLong crc, const Bytef *buf, z_size_t len)
 {
     if (!buf) return 0; // libz-rs-sys/src/lib.rs:150-155
-    need_engine_or_die();
     uint32_t out = 0;
-    if (zb_crc32(engine(), (uint32_t)crc, buf, len, 0, &out, nullptr) != ZB_OK) {
-        fprintf(stderr, "libz_b200: crc32 failed: %s\n", zb_last_error());
-        abort();
-    }
+    zb_engine *e = engine();
+    if (!e || zb_crc32(e, (uint32_t)crc, buf, len, 0, &out, nullptr) != ZB_OK) { checksum_failed("crc32"); return 0; }
     return out;
 }
 uLong crc32(uLong crc, const Bytef *buf, uInt len) { return crc32_z(crc, buf, len); }
+const z_crc_t *get_crc_table(void)
+{
+    // libz-rs-sys/src/lib.rs:252-255 -> crc32::get_crc_table: braid table 0, i.e. the byte-wise table of 0xedb88320.  A constant
+    // table for callers that roll their own CRC; generated on first use (it is not how this library computes crc32).
+    static z_crc_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t n = 0; n < 256; n++) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+        ready = true;
+    }
+    return table;
+}
 uLong adler32_combine64(uLong a1, uLong a2, z_off64_t len2) { return len2 < 0 ? 0xffffffffUL : adler_combine((uint32_t)a1, (uint32_t)a2, (uint64_t)len2); }
 uLong adler32_combine(uLong a1, uLong a2, z_off_t len2) { return adler32_combine64(a1, a2, len2); }
 uLong crc32_combine_gen64(z_off64_t len2) { return x2nmodp((uint64_t)len2, 3); }
