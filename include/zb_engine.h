@@ -87,6 +87,11 @@ typedef struct zb_inflate_result {
 ZB_API int zb_inflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                int window_bits, zb_inflate_result *res);
 
+#define ZB_INF_CHECK_ADLER 1u /* zb_inflate_ex on a raw stream (window_bits < 0): also return the adler32 ... */
+#define ZB_INF_CHECK_CRC 2u   /* ... or the crc32 of the output in res->check (for callers that parse header and trailer themselves) */
+ZB_API int zb_inflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
+                         int window_bits, uint32_t flags, zb_inflate_result *res);
+
 /* Streaming building block (what inflate() of the zlib ABI runs on, zlib-rs/src/inflate.rs:2376-2457): decode the COMPLETE deflate
  * blocks of a raw deflate segment.  src/dict/dst are host buffers; decoding starts at bit `start_bit` of src with the last
  * `dict_len` (<= 32768) bytes of earlier output as the window.  Returns ZB_OK with

@@ -153,6 +153,20 @@ ZB_EXPORT int inflateSync(z_streamp strm);
 ZB_EXPORT int inflateCopy(z_streamp dest, z_streamp source);
 ZB_EXPORT long inflateMark(z_streamp strm);
 ZB_EXPORT int inflatePrime(z_streamp strm, int bits, int value);
+/* :1233 inflateResetKeep, :901 inflateSyncPoint, :2287 inflateGetDictionary, :1199 inflateUndermine, :1216 inflateValidate,
+ * :1252 inflateCodesUsed, :697-780 inflateBackInit_ / inflateBack / inflateBackEnd */
+ZB_EXPORT int inflateResetKeep(z_streamp strm);
+ZB_EXPORT int inflateSyncPoint(z_streamp strm);
+ZB_EXPORT int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength);
+ZB_EXPORT int inflateUndermine(z_streamp strm, int subvert);
+ZB_EXPORT int inflateValidate(z_streamp strm, int check);
+ZB_EXPORT unsigned long inflateCodesUsed(z_streamp strm);
+typedef unsigned (*in_func)(void *, const unsigned char **);
+typedef int (*out_func)(void *, unsigned char *, unsigned);
+ZB_EXPORT int inflateBackInit_(z_streamp strm, int windowBits, unsigned char *window, const char *version, int stream_size);
+ZB_EXPORT int inflateBack(z_streamp strm, in_func in, void *in_desc, out_func out, void *out_desc);
+ZB_EXPORT int inflateBackEnd(z_streamp strm);
+#define inflateBackInit(strm, windowBits, window) inflateBackInit_((strm), (windowBits), (window), ZLIB_VERSION, (int)sizeof(z_stream))
 
 /* one-shot: :1447 compress, :1529 compress2, :1561 compressBound, :499 uncompress, :583 uncompress2 */
 ZB_EXPORT int compress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen);

@@ -71,20 +71,31 @@ def synthetic_mix(n, seed=1):
 
 
 CALGARY_MIX_BYTES = 64 << 20
-CALGARY_MIX_SHA256 = "bfe943ead7312a5efa1338c4b72734ecd5a29c7a65b648837205315bc3063096"
+CALGARY_MIX_SHA256 = "fc0e027bacb9bf3be3c23479b3ea674087602f372086ed3b9c3e180488c1f011"
+
+
+def calgary_extra():
+    """The four non-Silesia sources SURVEY.md 8(d)4 names (lcet10.txt, paper-100k.pdf, fireworks.jpg, gix-blame-readme.bin of the
+    reference's test-data), committed as data/calgary_extra.tar.gz."""
+    if "extra" not in _cache:
+        import tarfile
+        with tarfile.open(os.path.join(ROOT, "data", "calgary_extra.tar.gz")) as tf:
+            _cache["extra"] = [tf.extractfile(nm).read() for nm in ("lcet10.txt", "paper-100k.pdf", "fireworks.jpg", "gix-blame-readme.bin")]
+    return _cache["extra"]
 
 
 def calgary_mix(n=CALGARY_MIX_BYTES):
-    """BASELINE config 4's "64 MiB synthetic Calgary-mix" (SURVEY.md 8d item 4).  The Calgary corpus is not available offline, so the
-    buffer is defined from the committed corpus: 64 KiB slices drawn round-robin from the 12 Silesia members at xorshift64*-chosen
-    offsets (seed 0x9E3779B97F4A7C15), every 16th slice replaced by seeded random bytes and every 32nd by zeros."""
+    """BASELINE config 4's "64 MiB synthetic Calgary-mix" exactly as SURVEY.md 8(d)4 defines it (the Calgary corpus itself is not
+    available offline): 64 KiB slices drawn round-robin from {lcet10.txt, paper-100k.pdf, fireworks.jpg, gix-blame-readme.bin, the 12
+    Silesia members} at xorshift64*-chosen offsets (seed 0x9E3779B97F4A7C15), every 16th slice replaced by seeded random bytes and
+    every 32nd by zeros."""
     key = ("calgary", n)
     if key in _cache:
         return _cache[key]
     SL = 65536
     x = 0x9E3779B97F4A7C15
     mask = (1 << 64) - 1
-    members = [silesia_member(k) for k in range(12)]
+    members = calgary_extra() + [silesia_member(k) for k in range(12)]
     parts = []
     i = 0
     while i * SL < n:
@@ -97,7 +108,7 @@ def calgary_mix(n=CALGARY_MIX_BYTES):
         elif i % 16 == 15:
             parts.append(xorshift_bytes(SL, seed=r))
         else:
-            m = members[i % 12]
+            m = members[i % len(members)]
             off = r % (len(m) - SL)
             parts.append(m[off: off + SL])
         i += 1

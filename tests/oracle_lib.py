@@ -163,3 +163,29 @@ def inflate_stream(data, window_bits=15, in_chunk=1 << 30, out_chunk=1 << 20, fl
     adler = s.adler
     L.zo_inflate_end(ctypes.byref(s))
     return rc, bytes(out), msg, adler
+
+
+class ZoGzHeader(ctypes.Structure):
+    _fields_ = [("text", ctypes.c_int), ("time", ctypes.c_ulong), ("xflags", ctypes.c_int), ("os", ctypes.c_int),
+                ("extra", ctypes.c_char_p), ("extra_len", ctypes.c_uint), ("extra_max", ctypes.c_uint),
+                ("name", ctypes.c_char_p), ("name_max", ctypes.c_uint), ("comment", ctypes.c_char_p), ("comm_max", ctypes.c_uint),
+                ("hcrc", ctypes.c_int), ("done", ctypes.c_int)]
+
+
+def gzip_with_header(data, level=6, text=0, time=0, os=0, extra=None, name=None, comment=None, hcrc=0, mem_level=8, strategy=0):
+    """One-shot gzip stream with a gz_header (deflateSetHeader, zlib-rs/src/deflate.rs:2574-2697) from the oracle."""
+    L = lib()
+    h = ZoGzHeader(text, time, 0, os, extra, len(extra) if extra else 0, 0, name, 0, comment, 0, hcrc, 0)
+    s = ZoStream()
+    assert L.zo_deflate_init(ctypes.byref(s), level, 31, mem_level, strategy) == 0
+    L.zo_deflate_set_header.argtypes = [ctypes.POINTER(ZoStream), ctypes.POINTER(ZoGzHeader)]
+    assert L.zo_deflate_set_header(ctypes.byref(s), ctypes.byref(h)) == 0
+    src = ctypes.create_string_buffer(bytes(data), max(len(data), 1))
+    cap = len(data) + len(data) // 8 + 1024 + (len(extra) if extra else 0) + (len(name) if name else 0) + (len(comment) if comment else 0)
+    out = ctypes.create_string_buffer(cap)
+    s.next_in, s.avail_in = ctypes.addressof(src), len(data)
+    s.next_out, s.avail_out = ctypes.addressof(out), cap
+    assert L.zo_deflate(ctypes.byref(s), 4) == 1
+    n = cap - s.avail_out
+    L.zo_deflate_end(ctypes.byref(s))
+    return out.raw[:n]

@@ -497,3 +497,15 @@ def test_c_client_round_trip(tmp_path):
         r = subprocess.run([os.path.join(root, "tests", "c_client", "_build", "pipe_client"), str(f), str(level)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert ("out=%d " % len(O.compress(d, level)[1])) in r.stdout and ("adler=%08x" % zlib.adler32(d)) in r.stdout
+
+
+@pytest.mark.parametrize("name", ["gzip-0", "gzip-9", "gzip-filtered-9", "gzip-fixed-9", "gzip-huffman-9", "gzip-rle-9"])
+def test_compression_corpus_files_are_reproduced_on_the_gpu(name, eng):
+    """The reference's committed compression corpus as deflate goldens (every strategy): the engine's gzip stream equals the file."""
+    from test_oracle import CORPUS_CASES, corpus_case
+    level, strategy = CORPUS_CASES[name]
+    data, want = corpus_case(name)
+    out, r = eng.deflate(data, level=level, strategy=strategy, window_bits=31)
+    assert out == want and r.exact_parity == 1
+    raw, r = eng.deflate(data, level=level, strategy=strategy, window_bits=-15)
+    assert raw == want[10:-8]

@@ -296,3 +296,47 @@ def test_gzip_with_header_reference_check():
     assert stream[3] == 0x02 | 0x04 | 0x08 | 0x10  # FHCRC | FEXTRA | FNAME | FCOMMENT
     assert extra in stream and name in stream and comment in stream
     assert O.uncompress is not None and O.inflate_stream(stream, 31)[1] == data
+
+
+CORPUS_CASES = {"gzip-0": (0, 0), "gzip-9": (9, 0), "gzip-filtered-9": (9, 1), "gzip-fixed-9": (9, 4), "gzip-huffman-9": (9, 2),
+                "gzip-rle-9": (9, 3)}
+
+
+def corpus_case(name):
+    """(input, whole .gz file) of one file of the reference's compression corpus (test-libz-rs-sys/src/test-data/compression-corpus/,
+    used by inflate.rs:2358-2427 / infback.rs:59-69): 'The fastest WASM zlib.md' gzip-compressed with the named strategy and level."""
+    import zlib
+    b = open(os.path.join(HERE, "golden", "data", "The_fastest_WASM_zlib.md.%s.gz" % name), "rb").read()
+    return zlib.decompress(b, 31), b
+
+
+@pytest.mark.parametrize("name", sorted(CORPUS_CASES))
+def test_compression_corpus_files_are_reproduced(name):
+    """Deflate goldens at every strategy: the oracle's gzip stream of the corpus text equals the reference's committed file byte
+    for byte (header with XFL/OS, deflate data, crc32 + isize) -- two of the six differ from what stock zlib writes."""
+    level, strategy = CORPUS_CASES[name]
+    data, want = corpus_case(name)
+    rc, out = O.compress(data, level, 31, 8, strategy)
+    assert rc == 0 and out == want
+    rc, raw = O.compress(data, level, -15, 8, strategy)
+    assert rc == 0 and raw == want[10:-8]
+
+
+def test_issue_169_call_sequence():
+    """test-libz-rs-sys/src/deflate.rs:2353-2419: level 1, raw, 2048 bytes with Z_NO_FLUSH and 1053 bytes of room, then the last 67
+    bytes with Z_FINISH: every intermediate avail/total value and the final 1242 bytes are literals of the reference's test."""
+    import ctypes, zlib
+    L = O.lib()
+    js = open(os.path.join(HERE, "golden", "data", "issue-169.js"), "rb").read()
+    assert len(js) == 2115
+    s = O.ZoStream()
+    assert L.zo_deflate_init(ctypes.byref(s), 1, -15, 8, 0) == 0
+    src, out = ctypes.create_string_buffer(js, len(js)), ctypes.create_string_buffer(4096)
+    s.next_in, s.next_out, s.avail_in, s.avail_out = ctypes.addressof(src), ctypes.addressof(out), 2048, 1053
+    assert L.zo_deflate(ctypes.byref(s), 0) == 0 and (s.avail_in, s.avail_out, s.total_in, s.total_out) == (0, 1053, 2048, 0)
+    s.avail_in = 67
+    assert L.zo_deflate(ctypes.byref(s), 4) == 0 and (s.avail_in, s.avail_out, s.total_in, s.total_out) == (67, 0, 2048, 1053)
+    s.avail_out = 4096 - s.total_out
+    assert L.zo_deflate(ctypes.byref(s), 4) == 1 and (s.avail_in, s.avail_out, s.total_in, s.total_out) == (0, 2854, 2115, 1242)
+    assert zlib.decompress(out.raw[:1242], -15) == js
+    L.zo_deflate_end(ctypes.byref(s))

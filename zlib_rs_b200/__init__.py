@@ -24,6 +24,8 @@ Z_DEFAULT_STRATEGY, Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED = 0, 1, 2, 3, 4
 ZLIB_VERSION = b"1.3.0-zlib-rs-0.6.7-b200"
 ZB_FLAG_NOT_LAST = 1
 ZB_FLAG_LOW_PARALLEL = 2
+ZB_FLAG_CHECK_ADLER = 4
+ZB_FLAG_CHECK_CRC = 8
 
 
 class ZStream(ctypes.Structure):

@@ -395,12 +395,20 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                     // them over more SMs
                     // few dirty tiles: small pieces on many SMs, few warps each (the walk of a sparse piece is issue-bound per warp)
                     // one wave of CTAs if possible: the per-piece latency, not the throughput, bounds a sparse pass
-                    jb.match_sub = n_dirty > 9 ? kMatchSub : n_dirty > 2 ? 2048 : 512;
-                    uint32_t mthreads = n_dirty > 2 ? 1024 : 256;
-                    if (n_dirty > 9) { // experiment knobs for the dense passes (not part of the interface)
+                    // Pieces: the full first pass runs two CTAs per SM (4 KiB of positions each: the window copy of a CTA is 111 KiB);
+                    // later passes cut the dirty tiles into enough pieces for about four CTAs per SM, because a sparse pass is
+                    // bounded by its slowest piece, not by throughput.
+                    uint32_t mthreads = 1024;
+                    if (iters == 1) jb.match_sub = 4096;
+                    else if (n_dirty <= 2) { jb.match_sub = 512; mthreads = 256; }
+                    else {
+                        const uint64_t per_cta = (uint64_t)n_dirty * kMatchTile / (4 * 148);
+                        jb.match_sub = per_cta >= 8192 ? 8192 : per_cta >= 4096 ? 4096 : per_cta >= 2048 ? 2048 : 1024;
+                    }
+                    {   // experiment knobs for the dense passes (not part of the interface)
                         static const char *e_sub = getenv("ZB_MSUB"), *e_thr = getenv("ZB_MTHREADS");
-                        if (e_sub) jb.match_sub = (uint32_t)atoi(e_sub);
-                        if (e_thr) mthreads = (uint32_t)atoi(e_thr);
+                        if (e_sub && n_dirty > 9) jb.match_sub = (uint32_t)atoi(e_sub);
+                        if (e_thr && n_dirty > 9) mthreads = (uint32_t)atoi(e_thr);
                     }
                     uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     uint32_t n_ptiles = npt, first_ptile = 0;
@@ -640,6 +648,13 @@ int zb_inflate(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, 
 {
     if (!z) return ZB_E_NODEVICE;
     return z->e.inflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, window_bits, res);
+}
+
+int zb_inflate_ex(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev, int window_bits, uint32_t flags,
+                  zb_inflate_result *res)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.inflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, window_bits, res, flags);
 }
 
 int zb_inflate_blocks(zb_engine *z, const void *src, size_t n, uint64_t start_bit, const void *dict, size_t dict_len, void *dst, size_t cap,

@@ -926,7 +926,7 @@ int Engine::inflate_init()
     } while (0)
 
 int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int window_bits,
-                    zb_inflate_result *res)
+                    zb_inflate_result *res, uint32_t flags)
 {
     if (!res || (!src && n) || (!dst && dst_cap)) return ZB_E_PARAM;
     memset(res, 0, sizeof *res);
@@ -1015,12 +1015,14 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     if (his->err == IE_OUTPUT_FULL) status = ZB_E_BUF;
     else if (his->err != IE_OK) { status = ZB_E_DATA; snprintf(res->msg, sizeof res->msg, "%s", inf_msg(his->err)); }
     // check value of what was produced (inflate.rs:1398-1430 verifies it against the trailer)
-    uint32_t check = his->kind == 2 ? 0 : 1;
-    if (his->kind != 0 && his->out_bytes) {
+    // a raw stream has no check value of its own; a caller that frames the stream itself asks for one (ZB_INF_CHECK_*)
+    const uint32_t ck_kind = his->kind ? his->kind : (flags & ZB_INF_CHECK_CRC) ? 2u : (flags & ZB_INF_CHECK_ADLER) ? 1u : 0u;
+    uint32_t check = ck_kind == 2 ? 0 : 1;
+    if (ck_kind != 0 && his->out_bytes && status != ZB_E_BUF) {
         void *d_ck;
         const size_t ck_bytes = ((size_t)his->out_bytes / 16384 + 16) * 8;
         if ((rc = reserve(18 /*S_CK*/, ck_bytes, &d_ck)) != ZB_OK) return rc;
-        if (his->kind == 2) CKI(launch_crc32(d_dst, his->out_bytes, 0, d_ck, ck_bytes, d_check, st));
+        if (ck_kind == 2) CKI(launch_crc32(d_dst, his->out_bytes, 0, d_ck, ck_bytes, d_check, st));
         else CKI(launch_adler32(d_dst, his->out_bytes, 1, d_ck, ck_bytes, d_check, st));
         launches += 2;
         CKI(cudaMemcpyAsync(h_info, d_check, 4, cudaMemcpyDeviceToHost, st));

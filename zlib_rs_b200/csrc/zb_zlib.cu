@@ -543,6 +543,236 @@ int compress(Bytef *dest, uLongf *destLen, const Bytef *source, uLong sourceLen)
 }
 
 // ---------------------------------------------------------------- inflate
+namespace {
+
+int inflate_wbits(IState *s, int windowBits)
+{
+    // inflate::reset_with_config (zlib-rs/src/inflate.rs:2298-2327)
+    int wrap, wb = windowBits;
+    if (wb < 0) { if (wb < -15) return Z_STREAM_ERROR; wrap = 0; wb = -wb; }
+    else { wrap = (wb >> 4) + 5; if (wb < 48) wb &= 15; }
+    if (wb != 0 && (wb < 8 || wb > 15)) return Z_STREAM_ERROR;
+    s->window_bits = windowBits;
+    s->wrap = wrap;
+    s->wbits = wb;
+    return Z_OK;
+}
+
+void inflate_reset_keep(z_streamp strm, IState *s)
+{
+    // inflate::reset_keep (zlib-rs/src/inflate.rs:2338-2370)
+    strm->total_in = strm->total_out = 0;
+    strm->msg = nullptr;
+    if (s->wrap != 0) strm->adler = (uLong)(s->wrap & 1);
+    s->phase = IP_HEAD;
+    s->gzip = -1;
+    s->result = Z_OK;
+    s->msg[0] = 0;
+    s->in.clear(); s->bit_off = 0;
+    s->out.clear(); s->out_pos = 0;
+    s->check = 1; s->total = 0; s->dictid = 0;
+    s->have_dict = false; s->tried_oneshot = false; s->sync_point = false;
+    s->tried_len = 0;
+    s->head = nullptr;
+    s->dmax = 32768;
+}
+
+int inflate_bad(z_streamp strm, IState *s, const char *msg, int rc = Z_DATA_ERROR)
+{
+    snprintf(s->msg, sizeof s->msg, "%s", msg);
+    strm->msg = s->msg;
+    s->phase = IP_BAD;
+    s->result = rc;
+    return rc;
+}
+
+void window_push(IState *s, const uint8_t *p, size_t n)
+{
+    // inflate/window.rs extend(): keep the last 32 KiB
+    if (n >= 32768) { s->window.assign(p + n - 32768, p + n); return; }
+    if (s->window.size() + n > 32768) s->window.erase(s->window.begin(), s->window.begin() + (s->window.size() + n - 32768));
+    s->window.insert(s->window.end(), p, p + n);
+}
+
+// Header bytes (framing, zlib-rs/src/inflate.rs:926-1222).  Returns 1 header complete (bytes removed from s->in), 0 need more input,
+// <0 error (state is IP_BAD / IP_DICT as appropriate).
+int parse_header(z_streamp strm, IState *s)
+{
+    if (s->wrap == 0) { s->gzip = -1; s->phase = IP_BLOCKS; return 1; }
+    const std::vector<uint8_t> &b = s->in;
+    if (b.size() < 2) return 0;
+    const unsigned hold = b[0] | (b[1] << 8);
+    if ((s->wrap & 2) && hold == 0x8b1f) {
+        if (s->wbits == 0) s->wbits = 15;
+        if (b.size() < 10) return 0;
+        const unsigned flags = b[3];
+        if (b[2] != Z_DEFLATED) return inflate_bad(strm, s, "unknown compression method");
+        if (flags & 0xe0) return inflate_bad(strm, s, "unknown header flags set");
+        size_t p = 10, extra_off = 0, extra_len = 0, name_off = 0, name_len = 0, comm_off = 0, comm_len = 0;
+        if (flags & 4) {
+            if (b.size() < p + 2) return 0;
+            extra_len = b[p] | (b[p + 1] << 8);
+            p += 2; extra_off = p;
+            if (b.size() < p + extra_len) return 0;
+            p += extra_len;
+        }
+        if (flags & 8) {
+            name_off = p;
+            while (p < b.size() && b[p]) p++;
+            if (p >= b.size()) return 0;
+            p++; name_len = p - name_off; // with the terminator
+        }
+        if (flags & 16) {
+            comm_off = p;
+            while (p < b.size() && b[p]) p++;
+            if (p >= b.size()) return 0;
+            p++; comm_len = p - comm_off;
+        }
+        if (flags & 2) {
+            if (b.size() < p + 2) return 0;
+            if (s->wrap & 4) { // header crc (the low 16 bits of the crc32 of everything before it), on the crc32 kernel
+                uint32_t c = 0;
+                zb_engine *e = engine();
+                if (!e || zb_crc32(e, 0, b.data(), p, 0, &c, nullptr) != ZB_OK) return inflate_bad(strm, s, kNoDevice, Z_MEM_ERROR);
+                if ((c & 0xffffu) != (unsigned)(b[p] | (b[p + 1] << 8))) return inflate_bad(strm, s, "header crc mismatch");
+            }
+            p += 2;
+        }
+        if (gz_header *h = s->head) {
+            h->text = (int)(flags & 1);
+            h->time = (uLong)b[4] | ((uLong)b[5] << 8) | ((uLong)b[6] << 16) | ((uLong)b[7] << 24);
+            h->xflags = b[8];
+            h->os = b[9];
+            if (flags & 4) {
+                h->extra_len = (uInt)extra_len;
+                if (h->extra) memcpy(h->extra, b.data() + extra_off, extra_len < h->extra_max ? extra_len : h->extra_max);
+            } else h->extra = nullptr;
+            if (flags & 8) { if (h->name) memcpy(h->name, b.data() + name_off, name_len < h->name_max ? name_len : h->name_max); }
+            else h->name = nullptr;
+            if (flags & 16) { if (h->comment) memcpy(h->comment, b.data() + comm_off, comm_len < h->comm_max ? comm_len : h->comm_max); }
+            else h->comment = nullptr;
+            h->hcrc = (int)((flags >> 1) & 1);
+            h->done = 1;
+        }
+        s->gzip = 1;
+        s->check = 0;
+        strm->adler = 0;
+        s->in.erase(s->in.begin(), s->in.begin() + p);
+        s->phase = IP_BLOCKS;
+        return 1;
+    }
+    if (s->head) s->head->done = -1;
+    if (!(s->wrap & 1) || (((hold & 0xff) << 8) + (hold >> 8)) % 31) return inflate_bad(strm, s, "incorrect header check");
+    if ((hold & 0xf) != Z_DEFLATED) return inflate_bad(strm, s, "unknown compression method");
+    const int len = (int)((hold >> 4) & 0xf) + 8;
+    if (s->wbits == 0) s->wbits = len;
+    if (len > 15 || len > s->wbits) return inflate_bad(strm, s, "invalid window size");
+    s->dmax = 1u << len;
+    s->gzip = 0;
+    s->check = 1;
+    if (hold & 0x2000) { // FDICT: the dictionary id follows (inflate.rs Mode::DictId / Mode::Dict)
+        if (b.size() < 6) return 0;
+        s->dictid = ((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5];
+        s->in.erase(s->in.begin(), s->in.begin() + 6);
+        strm->adler = s->dictid;
+        s->phase = IP_DICT;
+        return 1;
+    }
+    strm->adler = 1;
+    s->in.erase(s->in.begin(), s->in.begin() + 2);
+    s->phase = IP_BLOCKS;
+    return 1;
+}
+
+// Trailer bytes (inflate.rs:1398-1430, 1779-1795).  1 done, 0 need more, <0 error.
+int parse_trailer(z_streamp strm, IState *s)
+{
+    size_t p = s->bit_off ? 1 : 0; // the final block's last partial byte
+    const size_t need = s->gzip == 1 ? 8 : s->gzip == 0 ? 4 : 0;
+    if (s->wrap == 0 || s->gzip < 0) { // raw stream: nothing behind the last block
+        s->in.erase(s->in.begin(), s->in.begin() + (p < s->in.size() ? p : s->in.size()));
+        s->bit_off = 0;
+        s->phase = IP_DONE;
+        return 1;
+    }
+    if (s->in.size() < p + need) return 0;
+    const uint8_t *t = s->in.data() + p;
+    if (s->gzip == 0) {
+        const uint32_t v = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+        if ((s->wrap & 4) && v != s->check) return inflate_bad(strm, s, "incorrect data check");
+    } else {
+        const uint32_t v = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t l = t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+        if ((s->wrap & 4) && v != s->check) return inflate_bad(strm, s, "incorrect data check");
+        if ((s->wrap & 4) && l != (uint32_t)s->total) return inflate_bad(strm, s, "incorrect length check");
+    }
+    s->in.erase(s->in.begin(), s->in.begin() + p + need);
+    s->bit_off = 0;
+    s->phase = IP_DONE;
+    return 1;
+}
+
+// Decode what the buffered input allows.  A whole stream that is already there goes through the block-parallel one-shot decoder
+// (once); otherwise the complete blocks are decoded by zb_inflate_blocks and the rest waits for more input.
+int decode_blocks(z_streamp strm, IState *s, bool finishing)
+{
+    zb_engine *e = engine();
+    if (!e) return inflate_bad(strm, s, kNoDevice, Z_MEM_ERROR);
+    const int kind = !(s->wrap & 4) || s->gzip < 0 ? 0 : s->gzip == 1 ? 2 : 1;
+    if (!s->tried_oneshot && s->total == 0 && s->bit_off == 0 && s->window.empty() && (finishing || s->in.size() >= (1u << 16))) {
+        // nothing decoded yet and a lot of input: perhaps the whole stream.  Raw blocks + the check value of the output; the
+        // trailer stays framing.
+        s->tried_oneshot = true;
+        size_t cap = s->in.size() * 4 + 65536;
+        for (;;) {
+            const size_t base = s->out.size();
+            s->out.resize(base + cap);
+            zb_inflate_result r;
+            const int rc = zb_inflate_ex(e, s->in.data(), s->in.size(), 0, s->out.data() + base, cap, 0, -15,
+                                         kind == 2 ? ZB_INF_CHECK_CRC : kind == 1 ? ZB_INF_CHECK_ADLER : 0u, &r);
+            if (rc == ZB_E_BUF) { s->out.resize(base); cap *= 4; continue; }
+            if (rc == ZB_OK) {
+                s->out.resize(base + r.out_bytes);
+                window_push(s, s->out.data() + base, r.out_bytes);
+                s->check = r.check;
+                s->total = r.out_bytes;
+                s->in.erase(s->in.begin(), s->in.begin() + r.in_bytes);
+                s->bit_off = 0;
+                s->phase = IP_TRAILER;
+                return Z_OK;
+            }
+            s->out.resize(base);
+            if (rc != ZB_E_DATA) return inflate_bad(strm, s, zb_last_error(), map_rc(rc));
+            break; // truncated or damaged: the block decoder below finds out which, block by block
+        }
+    }
+    if (!finishing && s->in.size() == s->tried_len) return Z_OK; // nothing new since the last attempt
+    size_t cap = s->in.size() * 8 + 65536;
+    for (;;) {
+        const size_t base = s->out.size();
+        s->out.resize(base + cap);
+        zb_inflate_seg r;
+        const int rc = zb_inflate_blocks(e, s->in.data(), s->in.size(), s->bit_off, s->window.data(), s->window.size(),
+                                         s->out.data() + base, cap, kind, s->check, &r);
+        if (rc == ZB_E_BUF) { s->out.resize(base); cap *= 4; continue; }
+        if (rc != ZB_OK && rc != ZB_E_DATA) { s->out.resize(base); return inflate_bad(strm, s, zb_last_error(), map_rc(rc)); }
+        s->out.resize(base + r.out_bytes);
+        window_push(s, s->out.data() + base, r.out_bytes);
+        s->check = r.check;
+        s->total += r.out_bytes;
+        s->sync_point = r.sync_point != 0;
+        const size_t eat = (size_t)(r.end_bit >> 3);
+        s->in.erase(s->in.begin(), s->in.begin() + eat);
+        s->bit_off = (uint32_t)(r.end_bit & 7);
+        s->tried_len = s->in.size();
+        if (rc == ZB_E_DATA) { inflate_bad(strm, s, r.msg); return Z_OK; } // what the complete blocks produced is delivered first
+        if (r.final_block) s->phase = IP_TRAILER;
+        return Z_OK;
+    }
+}
+
+} // namespace
+
 int inflateInit2_(z_streamp strm, int windowBits, const char *version, int stream_size)
 {
     if (!version_ok(version, stream_size)) return Z_VERSION_ERROR;
@@ -550,72 +780,40 @@ int inflateInit2_(z_streamp strm, int windowBits, const char *version, int strea
     strm->msg = nullptr;
     if (!strm->zalloc) { strm->zalloc = default_alloc; strm->opaque = nullptr; }
     if (!strm->zfree) strm->zfree = default_free;
-    // inflate::reset_with_config (zlib-rs/src/inflate.rs:2298-2327)
-    int wb = windowBits;
-    if (wb < 0) { if (wb < -15) return Z_STREAM_ERROR; wb = -wb; }
-    else if (wb < 48) wb &= 15;
-    if (wb != 0 && (wb < 8 || wb > 15)) return Z_STREAM_ERROR;
+    IState probe;
+    if (inflate_wbits(&probe, windowBits) != Z_OK) return Z_STREAM_ERROR;
     if (!engine()) { strm->msg = kNoDevice; return Z_MEM_ERROR; }
     void *mem = strm->zalloc(strm->opaque, 1, (uInt)sizeof(IState));
     if (!mem) return Z_MEM_ERROR;
     IState *s = new (mem) IState();
     s->magic = kIMagic;
-    s->window_bits = windowBits;
     strm->state = reinterpret_cast<internal_state *>(s);
-    return inflateReset(strm);
+    return inflateReset2(strm, windowBits);
 }
 int inflateInit_(z_streamp strm, const char *version, int stream_size) { return inflateInit2_(strm, MAX_WBITS, version, stream_size); }
 
-int inflateReset(z_streamp strm)
+int inflateResetKeep(z_streamp strm)
 {
     IState *s = istate(strm);
     if (!s) return Z_STREAM_ERROR;
-    strm->total_in = strm->total_out = 0;
-    strm->msg = nullptr;
-    strm->adler = s->window_bits < 0 ? 0 : 1;
-    s->status = 0;
-    s->in.clear(); s->out.clear(); s->out_pos = 0; s->last_attempt = 0; s->consumed = 0;
-    s->result = Z_OK;
+    inflate_reset_keep(strm, s);
+    return Z_OK;
+}
+int inflateReset(z_streamp strm)
+{
+    // inflate::reset (inflate.rs:2329-2336): the window is dropped as well
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    s->window.clear();
+    inflate_reset_keep(strm, s);
     return Z_OK;
 }
 int inflateReset2(z_streamp strm, int windowBits)
 {
     IState *s = istate(strm);
     if (!s) return Z_STREAM_ERROR;
-    s->window_bits = windowBits;
+    if (inflate_wbits(s, windowBits) != Z_OK) return Z_STREAM_ERROR;
     return inflateReset(strm);
-}
-
-// Decode everything collected so far.  Returns 1 when the stream is complete (or definitely bad).
-static int try_decode(z_streamp strm, IState *s, bool must_finish)
-{
-    zb_engine *e = engine();
-    if (!e) { s->status = -1; s->result = Z_MEM_ERROR; strm->msg = kNoDevice; return 1; }
-    size_t cap = s->in.size() * 4 + 65536;
-    for (;;) {
-        s->out.resize(cap);
-        zb_inflate_result r;
-        int rc = zb_inflate(e, s->in.data(), s->in.size(), 0, s->out.data(), cap, 0, s->window_bits == 0 ? 15 : s->window_bits, &r);
-        if (rc == ZB_E_BUF) { cap *= 4; continue; }
-        if (rc == ZB_OK) {
-            s->out.resize(r.out_bytes);
-            s->consumed = r.in_bytes;
-            strm->adler = r.check;
-            s->status = 1;
-            s->result = Z_STREAM_END;
-            return 1;
-        }
-        s->out.clear();
-        if (rc == ZB_E_DATA && strcmp(r.msg, "unexpected end of input") == 0 && !must_finish) return 0; // need more input
-        s->status = -1;
-        if (rc == ZB_E_DATA) {
-            snprintf(s->msg, sizeof s->msg, "%s", r.msg);
-            strm->msg = s->msg;
-            s->result = strcmp(r.msg, "need dictionary") == 0 ? Z_NEED_DICT : Z_DATA_ERROR;
-            if (strcmp(r.msg, "unexpected end of input") == 0) { s->status = 0; s->result = Z_BUF_ERROR; return 0; }
-        } else { strm->msg = zb_last_error(); s->result = map_rc(rc); }
-        return 1;
-    }
 }
 
 int inflate(z_streamp strm, int flush)
@@ -623,37 +821,55 @@ int inflate(z_streamp strm, int flush)
     IState *s = istate(strm);
     if (!s) return Z_STREAM_ERROR;
     if (!strm->next_out || (!strm->next_in && strm->avail_in != 0)) return Z_STREAM_ERROR; // inflate.rs:2376-2379
-    if (s->status == -1) return s->result;
-    if (s->status == 2) return Z_STREAM_END;
+    if (s->phase == IP_BAD && s->out_pos >= s->out.size()) { strm->msg = s->msg; return s->result; }
+    if (s->phase == IP_DICT) return Z_NEED_DICT;
     const size_t in0 = strm->avail_in;
-    size_t produced = 0;
-    if (s->status == 0) {
-        if (strm->avail_in) {
-            s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
-            strm->next_in += strm->avail_in;
-            strm->total_in += strm->avail_in;
-            strm->avail_in = 0;
-        }
-        // The engine decodes whole streams: try when asked to finish, when no new input arrived, or when the
-        // collected input has doubled since the last attempt (keeps total work linear for chunked callers).
-        const bool attempt = flush == Z_FINISH || in0 == 0 || s->in.size() >= 2 * s->last_attempt || s->in.size() <= (1u << 20);
-        if (attempt && !s->in.empty()) {
-            s->last_attempt = s->in.size();
-            try_decode(strm, s, false);
-            if (s->status == -1) return s->result;
-            if (s->status == 1 && s->consumed < s->in.size()) {
-                // bytes after the end of the stream are handed back to the caller
-                const size_t extra = s->in.size() - s->consumed;
-                if (extra <= in0) { strm->next_in -= extra; strm->avail_in += (uInt)extra; strm->total_in -= extra; }
-            }
-        }
+    // take the offered input; whatever lies behind the end of the stream is handed back below
+    if (in0 && s->phase != IP_DONE && s->phase != IP_BAD) {
+        s->in.insert(s->in.end(), strm->next_in, strm->next_in + in0);
+        strm->next_in += in0;
+        strm->total_in += in0;
+        strm->avail_in = 0;
     }
-    if (s->status == 1) {
-        produced = drain(strm, s->out, s->out_pos);
-        if (s->out_pos >= s->out.size() && s->out.empty()) { s->status = 2; return Z_STREAM_END; }
-        return Z_OK;
+    const bool finishing = flush == Z_FINISH;
+    for (int guard = 0; guard < 8; guard++) {
+        if (s->phase == IP_HEAD) {
+            const int rc = parse_header(strm, s);
+            if (rc < 0) break;
+            if (rc == 0) break;
+            if (s->phase == IP_DICT) break;
+            continue;
+        }
+        if (s->phase == IP_BLOCKS) {
+            const int before = s->phase;
+            const size_t in_before = s->in.size(), out_before = s->out.size();
+            decode_blocks(strm, s, finishing);
+            if (s->phase == before && s->in.size() == in_before && s->out.size() == out_before) break; // waiting for input
+            continue;
+        }
+        if (s->phase == IP_TRAILER) {
+            if (parse_trailer(strm, s) <= 0) break;
+            continue;
+        }
+        break;
     }
-    if ((in0 == 0 && produced == 0) || flush == Z_FINISH) return Z_BUF_ERROR;
+    if (s->phase == IP_DONE && !s->in.empty()) {
+        // bytes behind the end of the stream go back to the caller (they arrived with this call)
+        const size_t extra = s->in.size();
+        if (extra <= in0) { strm->next_in -= extra; strm->avail_in += (uInt)extra; strm->total_in -= extra; }
+        s->in.clear();
+    }
+    const size_t produced = drain(strm, s->out, s->out_pos);
+    if (s->phase != IP_DICT && (s->gzip >= 0 || s->wrap == 0)) strm->adler = s->check; // in IP_DICT adler holds the dictionary id
+    // inflate.rs:2441-2449: unused bits of the last byte + 64 behind the last block + 128 on a block boundary (where this decoder
+    // always stops)
+    strm->data_type = (s->bit_off ? 8 - (int)s->bit_off : 0) + (s->phase == IP_TRAILER || s->phase == IP_DONE ? 64 : 0) +
+                      (s->phase == IP_BLOCKS ? 128 : 0);
+    if (s->out_pos < s->out.size()) return Z_OK; // more output is waiting for room
+    if (s->phase == IP_DICT) return Z_NEED_DICT;
+    if (s->phase == IP_BAD) { strm->msg = s->msg; return s->result; }
+    if (s->phase == IP_DONE) return Z_STREAM_END;
+    if ((in0 == 0 && produced == 0) || finishing) return Z_BUF_ERROR; // inflate.rs:2452-2455
     return Z_OK;
 }
 
@@ -667,14 +883,87 @@ int inflateEnd(z_streamp strm)
     strm->state = nullptr;
     return Z_OK;
 }
-int inflateSetDictionary(z_streamp strm, const Bytef *, uInt) { return istate(strm) ? Z_STREAM_ERROR : Z_STREAM_ERROR; }
+
+int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength)
+{
+    // inflate::set_dictionary (zlib-rs/src/inflate.rs:2621-2647)
+    IState *s = istate(strm);
+    if (!s || (!dictionary && dictLength)) return Z_STREAM_ERROR;
+    if (s->wrap != 0 && s->phase != IP_DICT) return Z_STREAM_ERROR;
+    if (s->phase == IP_DICT) {
+        uint32_t id = 1;
+        zb_engine *e = engine();
+        if (!e) return Z_MEM_ERROR;
+        if (dictLength && zb_adler32(e, 1, dictionary, dictLength, 0, &id, nullptr) != ZB_OK) return Z_MEM_ERROR;
+        if (id != s->dictid) return Z_DATA_ERROR;
+    }
+    window_push(s, dictionary, dictLength);
+    s->have_dict = true;
+    if (s->phase == IP_DICT) { s->phase = IP_BLOCKS; s->check = 1; strm->adler = 1; }
+    return Z_OK;
+}
+int inflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength)
+{
+    // inflate::get_dictionary (inflate.rs:2690-2711): the current window, oldest byte first
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (dictionary && !s->window.empty()) memcpy(dictionary, s->window.data(), s->window.size());
+    if (dictLength) *dictLength = (uInt)s->window.size();
+    return Z_OK;
+}
 int inflateGetHeader(z_streamp strm, gz_headerp head)
 {
-    if (!istate(strm)) return Z_STREAM_ERROR;
+    // inflate::get_header (inflate.rs:2662-2685)
+    IState *s = istate(strm);
+    if (!s || !(s->wrap & 2)) return Z_STREAM_ERROR;
+    s->head = head;
     if (head) head->done = 0;
     return Z_OK;
 }
-int inflateSync(z_streamp strm) { return istate(strm) ? Z_DATA_ERROR : Z_STREAM_ERROR; }
+int inflateSync(z_streamp strm)
+{
+    // inflate::sync (inflate.rs:2477-2527): skip to the next 00 00 ff ff (a stored block's LEN/NLEN of a flush marker) and restart
+    // there on a block boundary
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (strm->avail_in == 0 && s->in.empty()) return Z_BUF_ERROR;
+    if (strm->avail_in) {
+        s->in.insert(s->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        strm->next_in += strm->avail_in;
+        strm->total_in += strm->avail_in;
+        strm->avail_in = 0;
+    }
+    size_t p = s->bit_off ? 1 : 0;
+    unsigned got = 0;
+    for (; p < s->in.size() && got < 4; p++) {
+        const uint8_t c = s->in[p];
+        if (c == (got < 2 ? 0 : 0xff)) got++;
+        else if (c) got = 0;
+        else got = 4 - got;
+    }
+    if (got != 4) { s->in.clear(); s->bit_off = 0; return Z_DATA_ERROR; }
+    s->in.erase(s->in.begin(), s->in.begin() + p);
+    s->bit_off = 0;
+    if (s->gzip == -1) s->wrap = 0; else s->wrap &= ~4; // no header yet: raw; otherwise no point in checking the check value now
+    const uLong ti = strm->total_in, to = strm->total_out;
+    const int gz = s->gzip;
+    std::vector<uint8_t> keep;
+    keep.swap(s->in);
+    s->window.clear();
+    inflate_reset_keep(strm, s);
+    keep.swap(s->in);
+    strm->total_in = ti; strm->total_out = to;
+    s->gzip = gz;
+    s->phase = IP_BLOCKS;
+    s->tried_oneshot = true;
+    return Z_OK;
+}
+int inflateSyncPoint(z_streamp strm)
+{
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    return s->sync_point ? 1 : 0; // inflate.rs:2537-2539
+}
 int inflateCopy(z_streamp dest, z_streamp source)
 {
     IState *s = istate(source);
@@ -686,8 +975,85 @@ int inflateCopy(z_streamp dest, z_streamp source)
     dest->state = reinterpret_cast<internal_state *>(d);
     return Z_OK;
 }
-long inflateMark(z_streamp strm) { return istate(strm) ? 0 : -(1L << 16); }
-int inflatePrime(z_streamp strm, int, int) { return istate(strm) ? Z_STREAM_ERROR : Z_STREAM_ERROR; }
+long inflateMark(z_streamp strm)
+{
+    // inflate::mark (inflate.rs:2605-2619): this decoder stops on block boundaries only, where back = -1 and length = 0
+    if (!istate(strm)) return -(1L << 16);
+    return -(1L << 16);
+}
+int inflatePrime(z_streamp strm, int bits, int value)
+{
+    // inflate::prime (inflate.rs:2160-2172).  Supported where it is used (raw streams, on a byte boundary of the input, e.g. to
+    // resume behind a block that ended inside a byte): the bits are put in front of the input that follows.
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (bits == 0) return Z_OK;
+    if (bits < 0) { if (s->bit_off) { s->in.erase(s->in.begin()); s->bit_off = 0; } return Z_OK; }
+    if (bits > 16) return Z_STREAM_ERROR;
+    if (s->wrap != 0 || !s->in.empty() || (s->phase != IP_HEAD && s->phase != IP_BLOCKS)) return Z_STREAM_ERROR;
+    const uint32_t v = (uint32_t)value & ((1u << bits) - 1u);
+    const uint32_t pad = (8u - ((uint32_t)bits & 7u)) & 7u;
+    const uint32_t w = v << pad;
+    for (uint32_t i = 0; i < ((uint32_t)bits + 7u) / 8u; i++) s->in.push_back((uint8_t)(w >> (8 * i)));
+    s->bit_off = pad;
+    s->tried_oneshot = true;
+    return Z_OK;
+}
+int inflateUndermine(z_streamp strm, int subvert)
+{
+    // inflate::undermine (inflate.rs:2588-2593) only clears the "sane" flag, which makes too-far distances read zeros; the kernels
+    // always check distances, which is what a build without that allowance answers
+    if (!istate(strm)) return Z_STREAM_ERROR;
+    return subvert ? Z_DATA_ERROR : Z_OK;
+}
+int inflateValidate(z_streamp strm, int check)
+{
+    IState *s = istate(strm);
+    if (!s) return Z_STREAM_ERROR;
+    if (check && s->wrap != 0) s->wrap |= 4; else s->wrap &= ~4; // inflate.rs:2595-2603
+    return Z_OK;
+}
+unsigned long inflateCodesUsed(z_streamp strm)
+{
+    return istate(strm) ? 0ul : (unsigned long)-1; // the decode tables live on the device and are rebuilt per block
+}
+
+// inflateBack (zlib-rs/src/inflate/infback.rs): raw deflate with caller-supplied input and output functions, on the same block decoder
+int inflateBackInit_(z_streamp strm, int windowBits, unsigned char *window, const char *version, int stream_size)
+{
+    if (!version_ok(version, stream_size)) return Z_VERSION_ERROR;
+    if (!strm || !window || windowBits < 8 || windowBits > 15) return Z_STREAM_ERROR;
+    const int rc = inflateInit2_(strm, -windowBits, version, stream_size);
+    if (rc != Z_OK) return rc;
+    istate(strm)->tried_oneshot = true;
+    return Z_OK;
+}
+int inflateBack(z_streamp strm, in_func in, void *in_desc, out_func out, void *out_desc)
+{
+    IState *s = istate(strm);
+    if (!s || !in || !out) return Z_STREAM_ERROR;
+    uint8_t obuf[32768];
+    for (;;) {
+        if (strm->avail_in == 0) {
+            const unsigned char *p = nullptr;
+            const unsigned got = in(in_desc, &p);
+            if (got == 0) { strm->next_in = nullptr; return Z_BUF_ERROR; }
+            strm->next_in = p;
+            strm->avail_in = got;
+        }
+        int rc;
+        do {
+            strm->next_out = obuf;
+            strm->avail_out = sizeof obuf;
+            rc = inflate(strm, Z_NO_FLUSH);
+            const unsigned have = (unsigned)(sizeof obuf - strm->avail_out);
+            if (have && out(out_desc, obuf, have)) return Z_BUF_ERROR;
+        } while (strm->avail_out == 0 && (rc == Z_OK || rc == Z_BUF_ERROR));
+        if (rc == Z_STREAM_END) return Z_STREAM_END;
+        if (rc != Z_OK && rc != Z_BUF_ERROR) return rc;
+    }
+}
+int inflateBackEnd(z_streamp strm) { return inflateEnd(strm); }
 
 int uncompress2(Bytef *dest, uLongf *destLen, const Bytef *source, uLong *sourceLen)
 {
