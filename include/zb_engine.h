@@ -72,6 +72,12 @@ ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_
                                                     sets the symbols per block (zlib-rs/src/deflate.rs:321, deflate/sym_buf.rs:23) */
 ZB_API int zb_deflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                   int level, int strategy, int window_bits, uint32_t flags, zb_deflate_result *res);
+/* deflate with a preset dictionary (deflateSetDictionary, zlib-rs/src/deflate.rs:498-564): raw streams only (window_bits < 0; the
+ * caller writes the zlib header with FDICT and the dictionary id); `dict` is a host pointer (or a device pointer when
+ * src_on_device).  Byte-identical to the reference at levels 0 and 3..9 and for every strategy; levels 1 and 2 use the level-3
+ * kernel set (valid stream, exact_parity = 0). */
+ZB_API int zb_deflate_dict(zb_engine *e, const void *dict, size_t dict_len, const void *src, size_t src_len, int src_on_device, void *dst,
+                           size_t dst_cap, int dst_on_device, int level, int strategy, int window_bits, uint32_t flags, zb_deflate_result *res);
 ZB_API size_t zb_deflate_bound(size_t src_len);
 
 typedef struct zb_inflate_result {

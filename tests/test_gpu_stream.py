@@ -337,3 +337,73 @@ def test_inflate_back_and_misc_exports():
     assert lib.inflatePrime(ctypes.byref(zp2.s), 3, second[0] & 7) == Z_OK
     shifted = bytes(((second[i] >> 3) | ((second[i + 1] << 5) & 0xff)) if i + 1 < len(second) else (second[i] >> 3) for i in range(len(second)))
     assert zp2.feed(shifted) in (Z_STREAM_END, Z_OK, Z_BUF_ERROR) and bytes(zp2.out) == d[30000:60000]
+
+
+def deflate_with_dict(data, zdict, level=6, wbits=15, strategy=0, mem_level=8):
+    """deflateInit2 + deflateSetDictionary + deflate(Z_FINISH) through the ABI.  Returns (stream, dictid as left in strm.adler)."""
+    lib = L()
+    lib.deflateSetDictionary.argtypes = [ctypes.POINTER(Z.ZStream), ctypes.c_void_p, ctypes.c_uint]
+    s = Z.ZStream()
+    assert lib.deflateInit2_(ctypes.byref(s), level, 8, wbits, mem_level, strategy, Z.ZLIB_VERSION, ctypes.sizeof(Z.ZStream)) == Z_OK
+    db = ctypes.create_string_buffer(bytes(zdict), max(len(zdict), 1))
+    assert lib.deflateSetDictionary(ctypes.byref(s), ctypes.addressof(db), len(zdict)) == Z_OK
+    did = s.adler
+    src = ctypes.create_string_buffer(bytes(data), max(len(data), 1))
+    cap = len(data) + len(data) // 8 + 1024
+    dst = ctypes.create_string_buffer(cap)
+    s.next_in, s.avail_in, s.next_out, s.avail_out = ctypes.addressof(src), len(data), ctypes.addressof(dst), cap
+    assert lib.deflate(ctypes.byref(s), Z_FINISH) == Z_STREAM_END
+    out = dst.raw[: s.total_out]
+    assert lib.deflateEnd(ctypes.byref(s)) == Z_OK
+    return out, did
+
+
+@pytest.mark.parametrize("level", [0, 3, 4, 5, 6, 7, 8, 9])
+def test_deflate_with_preset_dictionary_bit_exact(level):
+    """deflate::set_dictionary (zlib-rs/src/deflate.rs:498-564): the stream (FDICT header, dictionary id, data parsed against the
+    dictionary, adler32 of the input) equals the oracle's for every dictionary length class (short, one window, more than one
+    window, more than the window buffer) and for inputs on the serial and on the parallel path."""
+    m = silesia_member(3)
+    x = silesia_member(9)
+    for dl, n in ((5, 14), (1000, 3000), (32768, 200000), (40000, 120000), (70000, 300000), (2, 5000), (3, 70000)):
+        for src in (m, x):
+            dic, data = src[:dl], src[dl: dl + n]
+            rc, want, did = O.compress_dict(data, dic, level)
+            assert rc == 0
+            got, gid = deflate_with_dict(data, dic, level)
+            assert gid == did == zlib.adler32(dic)
+            assert got == want, (level, dl, n, len(got), len(want))
+            assert zlib.decompressobj(zdict=dic).decompress(got) == data
+
+
+def test_deflate_dictionary_reference_case_strategies_and_ghost_entry():
+    # the reference's own check (test-libz-rs-sys/src/deflate.rs:862-900): "hello" / "hello, hello!\0"
+    rc, want, did = O.compress_dict(b"hello, hello!\0", b"hello", 6)
+    got, gid = deflate_with_dict(b"hello, hello!\0", b"hello", 6)
+    assert got == want and gid == did
+    d = synthetic_mix(150000, seed=21)
+    for strategy in (1, 2, 3, 4):
+        for level in (6, 9):
+            rc, want, did = O.compress_dict(d[3000:], d[:3000], level, 15, 8, strategy)
+            got, _ = deflate_with_dict(d[3000:], d[:3000], level, 15, strategy)
+            assert got == want, (strategy, level)
+    # raw stream: no header, no check value
+    rc, want, did = O.compress_dict(d[1000:90000], d[:1000], 6, -15)
+    got, _ = deflate_with_dict(d[1000:90000], d[:1000], 6, -15)
+    assert got == want
+    # the last dictionary string is first hashed with a zero behind it (deflate.rs:535-545): an input that continues with a
+    # non-zero byte and soon repeats "<last three dictionary bytes> 0" walks through that stale table entry
+    dic = bytes(range(50, 250)) * 4 + b"abc"
+    for filler in (40, 300, 5000):
+        data = b"Xyz" + bytes((i * 7 + 3) % 251 + 1 for i in range(filler)) + b"abc\0abc\0abcX" + d[:60000]
+        for level in (4, 6, 8):
+            rc, want, did = O.compress_dict(data, dic, level)
+            got, _ = deflate_with_dict(data, dic, level)
+            assert got == want, (filler, level)
+    # gzip streams take no dictionary; a zlib stream only before the first deflate() call
+    lib = L()
+    s = Z.ZStream()
+    assert lib.deflateInit2_(ctypes.byref(s), 6, 8, 31, 8, 0, Z.ZLIB_VERSION, ctypes.sizeof(Z.ZStream)) == Z_OK
+    db = ctypes.create_string_buffer(b"dict", 4)
+    assert lib.deflateSetDictionary(ctypes.byref(s), ctypes.addressof(db), 4) == Z_STREAM_ERROR
+    lib.deflateEnd(ctypes.byref(s))

@@ -51,13 +51,15 @@ __global__ void k_rle(JobBufs);
 __global__ void k_emit_slow(JobBufs);
 __global__ void k_tail_slow(JobBufs);
 __global__ void k_serial_low(JobBufs);
+__global__ void k_links_dict_ghost(JobBufs, uint32_t *);
+__global__ void k_links_dict_ghost_apply(JobBufs, const uint32_t *);
 
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64;
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
-constexpr uint32_t kChainSmemBytes = 320 * kPathHead * 8;
+constexpr uint32_t kChainSmemBytes = kChainChunkTiles * kPathHead * 8;
 constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2 + 35824 + 16; // head + prev tables of one stream + the input ring (level 2)
 constexpr uint32_t kSerialSmemQuick = 65536 * 2 + 65536 + 16;         // head + 64 KiB input ring (level 1)
 
@@ -169,9 +171,19 @@ size_t deflate_bound(size_t n)
     return n + ((n + 7) >> 3) + ((n + 63) >> 6) + 5 + 18 + 64;
 }
 
-int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int level, int strategy,
-                    int window_bits, uint32_t flags, zb_deflate_result *res)
+int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_t dst_cap, bool dst_dev, int level, int strategy,
+                    int window_bits, uint32_t flags, zb_deflate_result *res, const void *dict, size_t dict_len)
 {
+    // A preset dictionary (deflate::set_dictionary, deflate.rs:498-564) is the input's prefix in the window: the kernels work on
+    // dictionary ++ input in absolute coordinates and start parsing at `dstart`.  A dictionary that would fill the window
+    // (>= 2 * w_size) is cut to its last w_size bytes (:517-531).
+    size_t dstart = 0;
+    if (dict_len) {
+        if (!dict || window_bits >= 0) { snprintf(g_err, sizeof g_err, "a dictionary needs a raw stream (the caller frames FDICT / DICTID)"); return ZB_E_PARAM; }
+        if (dict_len >= 2 * (size_t)kWSize) { dict = static_cast<const uint8_t *>(dict) + (dict_len - kWSize); dict_len = kWSize; }
+        dstart = dict_len;
+    }
+    const size_t n = n_in + dstart;
     int mem_level = (int)((flags >> 8) & 15u);
     if (mem_level == 0) mem_level = 8;
     if (mem_level > 9) return ZB_E_PARAM;
@@ -198,7 +210,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     const uint32_t nmt = N / kMatchTile + 1, npt = N / kPathTile + 1;
     // levels 1 and 2 (deflate_quick / deflate_fast) run the reference's serial parser on one warp (zb_serial.h) unless the caller
     // asks for the parallel level-3 kernel set (valid stream, better ratio, not byte-identical)
-    const bool low_parallel = (flags & ZB_FLAG_LOW_PARALLEL) != 0;
+    const bool low_parallel = (flags & ZB_FLAG_LOW_PARALLEL) != 0 || dstart != 0; // the one-warp parsers of levels 1/2 take no dictionary
     const bool serial_low = (level == 1 || level == 2) && strategy != 2 && strategy != 3 && !low_parallel;
     // deflate_quick writes one static block: its pieces are an encoding detail, not sym_buf flushes
     const uint32_t block_syms = (serial_low && level == 1) ? kBlockSyms : (1u << (mem_level + 6)) - 1u;
@@ -211,10 +223,11 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     if ((rc = reserve(slot, bytes, &p)) != ZB_OK) return rc;            \
     jb.field = static_cast<type>(p);
     uint8_t *d_in;
-    if (src_dev) d_in = const_cast<uint8_t *>(static_cast<const uint8_t *>(src));
+    if (src_dev && !dstart) d_in = const_cast<uint8_t *>(static_cast<const uint8_t *>(src));
     else { if ((rc = reserve(S_IN, npad + 16, &p)) != ZB_OK) return rc; d_in = static_cast<uint8_t *>(p); }
     jb.in = d_in;
     jb.N = N;
+    jb.start = (uint32_t)dstart;
     jb.nmt = nmt;
     jb.tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
     jb.block_syms = block_syms;
@@ -280,7 +293,7 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     // slides it and every distance fits: N <= w_size - MIN_LOOKAHEAD (deflate.rs:1423, 1787); windowBits 8 is 9 (deflate.rs:308-312).
     const int wb_eff = wb == 8 ? 9 : wb;
     const bool small_ok = wb_eff < 15 && (uint64_t)N + kMinLookahead <= (1ull << wb_eff);
-    bool exact = wb_eff == 15 || small_ok;
+    bool exact = (wb_eff == 15 || small_ok) && (dstart == 0 || wb_eff == 15); // dictionaries: the 32 KiB window only
     jb.cinfo = small_ok ? (uint32_t)(wb_eff - 8) : 7u;
     jb.wsize = kWSize;
     // A small window that the input does leave: levels 3..6 run the exact serial simulator over the whole input when it fits
@@ -311,9 +324,10 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
 
     CK(cudaEventRecord(ev0, st));
     if (profile) { for (int i = 0; i < kPhases; i++) { phase_ms[i] = 0; phase_launches[i] = 0; } }
-    if (!src_dev) {
+    if (!src_dev || dstart) {
         pbegin();
-        if (n) CK(cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, st));
+        if (dstart) CK(cudaMemcpyAsync(d_in, dict, dstart, src_dev ? cudaMemcpyDefault : cudaMemcpyHostToDevice, st));
+        if (n_in) CK(cudaMemcpyAsync(d_in + dstart, src, n_in, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(d_in + n, 0, kPad, st));
         pend(9, 0);
     }
@@ -321,21 +335,21 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
     CK(cudaMemsetAsync(d_out, 0, out_cap, st));
     // checksum of the input (deflate.rs:1705-1713 computes it while filling the window)
     pbegin();
-    if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in, n, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
-    else if (wrap == 2 || (wrap == 0 && (flags & ZB_FLAG_CHECK_CRC))) { CK(launch_crc32(d_in, n, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in + dstart, n_in, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
+    else if (wrap == 2 || (wrap == 0 && (flags & ZB_FLAG_CHECK_CRC))) { CK(launch_crc32(d_in + dstart, n_in, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
     else CK(cudaMemsetAsync(d_check, 0, 4, st));
     pend(8, 2);
 
     uint32_t iters = 0;
     if (level == 0) {
-        const uint32_t nb = N == 0 ? 1 : (N + 65534) / 65535;
+        const uint32_t nb = n_in == 0 ? 1 : (uint32_t)((n_in + 65534) / 65535);
         k_stored<<<nb, 256, 0, st>>>(jb);
         launches++;
         k_finish<<<1, 32, 0, st>>>(jb, d_check);
         launches++;
     } else {
         if (jb.huffman_only) {
-            k_literal_syms<<<N / 256 + 1, 256, 0, st>>>(jb);
+            k_literal_syms<<<(uint32_t)(n_in / 256 + 1), 256, 0, st>>>(jb);
             launches++;
         } else if (jb.serial_mode) {
             iters = 1;
@@ -361,11 +375,18 @@ int Engine::deflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 k_links2_std<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
                 k_links_fix_std<<<N / 256 + 1, 256, 0, st>>>(jb);
                 launches += 2;
+                if (dstart >= 3 && n_in) {
+                    uint32_t *d_first = reinterpret_cast<uint32_t *>(d_check) + 2;
+                    CK(cudaMemsetAsync(d_first, 0xff, 4, st));
+                    k_links_dict_ghost<<<(kMaxDist + 255) / 256, 256, 0, st>>>(jb, d_first);
+                    k_links_dict_ghost_apply<<<1, 32, 0, st>>>(jb, d_first);
+                    launches += 2;
+                }
             }
             if (!jb.slow_mode) CK(cudaMemcpyAsync(jb.Lr, jb.L, npad * 2, cudaMemcpyDeviceToDevice, st));
             pend(0, 1);
             if (jb.slow_mode) {
-                if (N > 0) {
+                if (n_in > 0) {
                     iters = 1;
                     pbegin();
                     if (jb.slow_mode == 2) k_rle<<<(N + 255) / 256, 256, 0, st>>>(jb);
@@ -632,6 +653,13 @@ int zb_deflate(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, 
 {
     if (!z) return ZB_E_NODEVICE;
     return z->e.deflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, level, strategy, window_bits, 0, res);
+}
+
+int zb_deflate_dict(zb_engine *z, const void *dict, size_t dict_len, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev,
+                    int level, int strategy, int window_bits, uint32_t flags, zb_deflate_result *res)
+{
+    if (!z) return ZB_E_NODEVICE;
+    return z->e.deflate(src, n, src_dev != 0, dst, cap, dst_dev != 0, level, strategy, window_bits, flags, res, dict, dict_len);
 }
 
 int zb_deflate_ex(zb_engine *z, const void *src, size_t n, int src_dev, void *dst, size_t cap, int dst_dev, int level, int strategy,

@@ -456,8 +456,8 @@ constexpr uint32_t kMaxBlocks = 1u << 16;
 constexpr uint32_t kHashSize = 1u << 18;
 enum { PS_OK = 0, PS_FALLBACK = 1 };
 
-struct InfCand { uint64_t start_bit, end_bit; uint32_t out_len, valid, bfinal, pad; };
-struct InfBlock { uint64_t start_bit, out_off; uint32_t out_len, type, src_byte, pad; };
+struct InfCand { uint64_t start_bit, end_bit; uint32_t out_len, valid, bfinal, nsyms; }; // nsyms: symbols kept in the arena (0: none)
+struct InfBlock { uint64_t start_bit, out_off; uint32_t out_len, type, src_byte, cand; }; // cand: candidate index of a dynamic block
 struct InfPar {
     uint32_t ncand, nblocks, status, kind;
     uint64_t first_bit, total_out, end_bit;
@@ -646,7 +646,9 @@ __device__ __forceinline__ int dec_symbol(const DecShared &S, BitRd &br, uint32_
 constexpr uint32_t kMaxBlockOut = 256u << 20;
 
 // 2. measure every candidate (one decoding lane per candidate, no output)
-__global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand)
+// The symbols are kept (one 32-bit word each: a literal, or length << 16 | distance) in the candidate's slot of the arena, so that
+// k_inf_decode does not decode the Huffman codes a second time; a block with more symbols than a slot is decoded again there.
+__global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand, uint32_t *arena, uint32_t slot_syms)
 {
     __shared__ DecShared S;
     const uint32_t k = blockIdx.x;
@@ -654,7 +656,8 @@ __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n,
     BitRd br;
     uint32_t lenbits, distbits, bf = 0;
     int rc = dec_setup(S, src, n, cand[k].start_bit, br, lenbits, distbits, &bf);
-    uint32_t o = 0;
+    uint32_t o = 0, ns = 0;
+    uint32_t *slot = arena ? arena + (size_t)k * slot_syms : nullptr;
     if (rc == 0) {
         const uint32_t lm = (1u << lenbits) - 1, dm = (1u << distbits) - 1;
         const uint64_t nbits = n * 8;
@@ -663,11 +666,15 @@ __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n,
             const int t = dec_symbol(S, br, lm, dm, v, d);
             if (t == 0) {
                 // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
+                if (ns < slot_syms) slot[ns] = v;
+                ns++;
                 o++;
                 if ((o & 63u) == 0 && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; break; }
                 continue;
             }
             if (t == 1) {
+                if (ns < slot_syms) slot[ns] = (v << 16) | d;
+                ns++;
                 o += v;
                 if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; break; }
                 continue;
@@ -681,6 +688,7 @@ __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n,
     cand[k].out_len = o;
     cand[k].bfinal = bf;
     cand[k].valid = rc == 0;
+    cand[k].nsyms = (rc == 0 && slot && ns <= slot_syms) ? ns : 0u;
 }
 
 // 3. follow the chain of blocks from the first one
@@ -712,6 +720,7 @@ __global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const I
             const uint32_t f = cand_lookup(htab, cand, pos);
             if (f == 0xffffffffu || !cand[f].valid) { par->status = PS_FALLBACK; return; }
             b.out_len = cand[f].out_len;
+            b.cand = f;
             pos = cand[f].end_bit;
         } else { par->status = PS_FALLBACK; return; } // fixed-code blocks / invalid type: serial decoder
         out += b.out_len;
@@ -750,7 +759,8 @@ struct DecodeShared {
 __device__ __forceinline__ void nb_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void nb_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t n, InfPar *par, const InfBlock *blocks, uint16_t *tmp)
+__global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t n, InfPar *par, const InfBlock *blocks, uint16_t *tmp,
+                                                    const InfCand *cand, const uint32_t *arena, uint32_t slot_syms)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeShared &S = *reinterpret_cast<DecodeShared *>(smem_raw);
@@ -764,6 +774,24 @@ __global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t 
         return;
     }
     constexpr uint32_t kFull = 1, kEmpty = 5; // named barriers 1..4 / 5..8
+    const uint32_t kept = (arena && b.type == 2) ? cand[b.cand].nsyms : 0u;
+    if (warp == 0 && kept) {
+        // ---- the symbols are already there (k_inf_scan): the warp only feeds them to the replaying warp, 32 per batch
+        const uint32_t *slot = arena + (size_t)b.cand * slot_syms;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t q = it & 3;
+            if (it >= 4) nb_sync(kEmpty + q);
+            const uint32_t base = it * 32;
+            const uint32_t cnt = kept - base < 32 ? kept - base : 32;
+            if (lane < cnt) S.d.q[q][lane] = slot[base + lane];
+            const bool fin = base + cnt >= kept;
+            if (lane == 0) { S.d.qn[q] = cnt; S.d.qfin[q] = fin; S.d.err = 0; }
+            __syncwarp();
+            nb_arrive(kFull + q);
+            if (fin) break;
+        }
+        return;
+    }
     if (warp == 0) {
         // ---- decoding warp
         BitRd br;
@@ -973,7 +1001,12 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
         CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
         CKI(cudaStreamSynchronize(st));
         if (hpar.status == PS_OK && hpar.ncand > 0 && hpar.ncand <= kMaxCand) {
-            k_inf_scan<<<hpar.ncand, 32, 0, st>>>(d_src, n, dpar, dcand);
+            // symbol arena: one slot per candidate (a deflate block of zlib-family encoders has at most 32767 symbols + end of block)
+            constexpr uint32_t kSlotSyms = 40960;
+            uint32_t *darena = nullptr;
+            if ((size_t)hpar.ncand * kSlotSyms * 4 <= ((size_t)2 << 30) && reserve(36 /* inflate symbol arena */, (size_t)hpar.ncand * kSlotSyms * 4, &p) == ZB_OK)
+                darena = static_cast<uint32_t *>(p);
+            k_inf_scan<<<hpar.ncand, 32, 0, st>>>(d_src, n, dpar, dcand, darena, darena ? kSlotSyms : 0u);
             k_inf_chain<<<1, 32, 0, st>>>(d_src, n, dpar, dcand, dhtab, dblk);
             launches += 2;
             CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
@@ -983,7 +1016,7 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 if ((rc = reserve(4 /*S_M*/, (hpar.total_out + 64) * 2, &p)) != ZB_OK) return rc;
                 dtmp = static_cast<uint16_t *>(p);
                 CKI(cudaFuncSetAttribute(k_inf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
-                k_inf_decode<<<hpar.nblocks, 64, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp);
+                k_inf_decode<<<hpar.nblocks, 64, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp, dcand, darena, darena ? kSlotSyms : 0u);
                 const uint64_t quads = (hpar.total_out + 1023) / 1024;
                 k_inf_resolve<<<(unsigned)(quads < 148 * 16 ? (quads ? quads : 1) : 148 * 16), 256, 0, st>>>(dpar, dblk, dtmp, d_dst);
                 launches += 2;

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
         for (uint32_t i = tid; i < (span + 31) / 32; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
     }
     __syncthreads();
+#ifdef ZB_SKIP_DENSE
     for (uint32_t round = 0; round < 24; round++) {
         int ch = 0;
         for (uint32_t i = tid; i < span; i += 1024) {
@@ -215,6 +216,29 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
         }
         if (!__syncthreads_or(ch)) break;
     }
+#else
+    // pointer jumping over the holes only: every thread owns two words of the hole bitmap and visits their set bits
+    const uint32_t nwd = (span + 31) / 32;
+    for (uint32_t round = 0; round < 24; round++) {
+        int ch = 0;
+        for (uint32_t wi = tid; wi < nwd; wi += 1024) {
+            uint32_t bits = sh[wi];
+            while (bits) {
+                const uint32_t i = wi * 32 + (__ffs(bits) - 1);
+                bits &= bits - 1;
+                if (i >= span) break;
+                const uint32_t d = sL[i];
+                if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
+                const uint32_t t = i - d;
+                if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
+                const uint32_t d2 = sL[t];
+                sL[i] = (uint16_t)((d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2);
+                ch = 1;
+            }
+        }
+        if (!__syncthreads_or(ch)) break;
+    }
+#endif
     for (uint32_t i = ts - ws + tid; i < span; i += 1024) {
         uint32_t d = sL[i];
         if (!((sh[i >> 5] >> (i & 31)) & 1u) && d != 0 && d <= i) {
@@ -504,6 +528,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_next;
+    __shared__ __align__(8) unsigned long long s_mbar; // completion barrier of the window's bulk copy
     const uint32_t sub = jb.match_sub;
     const uint32_t ts = (jb.match_list ? jb.match_list[blockIdx.x] : blockIdx.x) * sub;
     if (ts >= jb.N) return;
@@ -567,15 +592,33 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             }
         }
     }
-    if (tid == 0) s_next = ts;
+    if (tid == 0) {
+        s_next = ts;
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // make the initialised barrier visible to the async proxy
+    }
     const long long t_0 = clock64();
     __syncthreads();
     {
-        // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes
-        const uint32_t n16 = (te + 512 - ws + 15) / 16;
-        const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
-        uint4 *dst = reinterpret_cast<uint4 *>(sdata);
-        for (uint32_t i = tid; i < n16 && i < data_bytes / 16; i += nthr) dst[i] = src[i];
+        // data: [ws, te + 512) rounded to 16 bytes; the input allocation is padded with kPad zero bytes.  The window is one
+        // contiguous range: a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) brings it in while the threads stage
+        // the links, which need a transform on the way.
+        uint32_t n16 = (te + 512 - ws + 15) / 16;
+        if (n16 > data_bytes / 16) n16 = data_bytes / 16;
+        const bool bulk = (reinterpret_cast<uintptr_t>(jb.in) & 15u) == 0; // a caller's device buffer may be unaligned
+        if (bulk) {
+            if (tid == 0) {
+                const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar), dsts = (uint32_t)__cvta_generic_to_shared(sdata);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n16 * 16u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dsts), "l"(jb.in + ws), "r"(n16 * 16u), "r"(mb) : "memory");
+            }
+        } else {
+            const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ws);
+            uint4 *dst = reinterpret_cast<uint4 *>(sdata);
+            for (uint32_t i = tid; i < n16; i += nthr) dst[i] = src[i];
+        }
         // chain links with the holes already bridged (k_skip): a walk never lands on a hole
         const uint32_t nl = (te - ws + 7) / 8; // 8 links per uint4
         const uint4 *ls = reinterpret_cast<const uint4 *>(jb.Lr + ws);
@@ -585,6 +628,14 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             uint4 v = ls[i];
             v.x |= __vcmpeq2(v.x, 0u); v.y |= __vcmpeq2(v.y, 0u); v.z |= __vcmpeq2(v.z, 0u); v.w |= __vcmpeq2(v.w, 0u);
             ld[i] = v;
+        }
+        if (bulk) { // phase 0 of the barrier completes when all bytes have landed
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(mb) : "memory");
+            }
         }
     }
     __syncthreads();
@@ -749,7 +800,7 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
 // the first kPathHead positions, whose (exit, count) pairs k_path_tiles also wrote to a compact table:
 // the CTA stages that table in shared memory chunk by chunk, so the serial walk only sees shared-memory
 // latency.
-constexpr uint32_t kChainChunk = 320;
+constexpr uint32_t kChainChunk = kChainChunkTiles;
 __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles, uint32_t first_tile)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -758,7 +809,7 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
     __shared__ uint32_t c_entry[kChainChunk], c_base[kChainChunk];
     // tiles before first_tile kept their nxt: the walk resumes from the state saved at that tile's boundary
     if (threadIdx.x == 0) {
-        if (first_tile == 0) { s_e = 0; s_base = 0; s_done = jb.tail_start == 0; s_tail = 0; }
+        if (first_tile == 0) { s_e = jb.start; s_base = 0; s_done = jb.tail_start == 0; s_tail = jb.start; }
         else { const uint4 v = jb.chain_state[first_tile]; s_e = v.x; s_base = v.y; s_done = v.z; s_tail = v.w; }
     }
     for (uint32_t t = threadIdx.x; t < first_tile; t += blockDim.x) jb.mark_needed[t] = 0;
@@ -916,30 +967,44 @@ __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
 // holes := holes_new; report change and the match tiles whose window saw it
 __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, uint32_t nmtiles)
 {
+    // dirty hash buckets of this CTA's 8192 positions are collected in shared memory first: in the first iteration every hole is a
+    // change (hundreds of thousands of bits), and global atomics on the 8 KiB bucket map would serialise
+    __shared__ uint32_t sb[2048];
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwords) return;
-    const uint32_t a = jb.holes[w], b = jb.holes_new[w];
-    jb.hdiff[w] = b & ~a;                  // became holes
-    jb.hdiff[jb.hdiff_words + w] = a & ~b; // became inserted positions
-    if (a != b) {
-        jb.hcoarse[w >> 5] = 1;
-        const uint32_t t = (w * 32) / kMatchTile;
-        jb.info->holes_changed = 1u; // iteration control: some word changed (plain store, every writer stores the same value)
-        jb.tile_dirty[t] = 1;
-        if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
-        jb.holes[w] = b;
-        uint32_t diff = a ^ b;
-        while (diff) {
-            const uint32_t y = w * 32 + (__ffs(diff) - 1);
-            diff &= diff - 1;
-            if (y + 4 <= jb.N) {
-                const uint8_t *q = jb.in + y;
-                const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
-                atomicOr(&jb.bucket_map[h >> 5], 1u << (h & 31));
+    uint32_t a = 0, b = 0;
+    if (w < nwords) { a = jb.holes[w]; b = jb.holes_new[w]; }
+    const bool changed = a != b;
+    if (!__syncthreads_or(changed)) {
+        if (w < nwords) { jb.hdiff[w] = 0; jb.hdiff[jb.hdiff_words + w] = 0; jb.holes_new[w] = 0; }
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) sb[i] = 0;
+    __syncthreads();
+    if (w < nwords) {
+        jb.hdiff[w] = b & ~a;                  // became holes
+        jb.hdiff[jb.hdiff_words + w] = a & ~b; // became inserted positions
+        if (changed) {
+            jb.hcoarse[w >> 5] = 1;
+            const uint32_t t = (w * 32) / kMatchTile;
+            jb.info->holes_changed = 1u; // iteration control: some word changed (plain store, every writer stores the same value)
+            jb.tile_dirty[t] = 1;
+            if (t + 1 < nmtiles) jb.tile_dirty[t + 1] = 1;
+            jb.holes[w] = b;
+            uint32_t diff = a ^ b;
+            while (diff) {
+                const uint32_t y = w * 32 + (__ffs(diff) - 1);
+                diff &= diff - 1;
+                if (y + 4 <= jb.N) {
+                    const uint8_t *q = jb.in + y;
+                    const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+                    atomicOr(&sb[h >> 5], 1u << (h & 31));
+                }
             }
         }
+        jb.holes_new[w] = 0;
     }
-    jb.holes_new[w] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) if (sb[i]) atomicOr(&jb.bucket_map[i], sb[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -968,7 +1033,7 @@ __global__ void __launch_bounds__(32) k_tail(JobBufs jb)
     __shared__ uint32_t ins[1024];
     if (threadIdx.x != 0) return;
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
-    const uint32_t p0 = jb.info->tail_entry;
+    const uint32_t p0 = max(jb.info->tail_entry, jb.start); // without a path (short input) the tail starts at the first input byte
     const uint32_t n_mid = jb.info->n_mid_syms;
     uint32_t k = 0;
     Sym *syms = jb.syms + n_mid;
@@ -1019,7 +1084,7 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
         bd.sym_begin = begin;
         bd.sym_count = count;
         bd.last = last && !jb.not_last;
-        const uint32_t start = begin == 0 ? 0 : sym_end(jb.syms[begin - 1]);
+        const uint32_t start = begin == 0 ? jb.start : sym_end(jb.syms[begin - 1]);
         const uint32_t end = last ? jb.N : sym_end(jb.syms[begin + count - 1]);
         bd.in_start = start;
         bd.in_len = end - start;
@@ -1252,7 +1317,7 @@ __global__ void k_finish(JobBufs jb, const uint32_t *check)
         jb.out[p + 3] = (uint8_t)a;
     } else if (jb.wrap == 2) { // crc32 + isize, little endian (deflate.rs:2773-2785)
         for (int i = 0; i < 4; i++) jb.out[p + i] = (uint8_t)(a >> (8 * i));
-        for (int i = 0; i < 4; i++) jb.out[p + 4 + i] = (uint8_t)(jb.N >> (8 * i));
+        for (int i = 0; i < 4; i++) jb.out[p + 4 + i] = (uint8_t)((jb.N - jb.start) >> (8 * i));
     }
     jb.info->adler = a;
 }
@@ -1261,24 +1326,25 @@ __global__ void k_finish(JobBufs jb, const uint32_t *check)
 __global__ void __launch_bounds__(256) k_literal_syms(JobBufs jb)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = jb.N - jb.start;
     if (p == 0) {
-        jb.info->n_mid_syms = jb.N;
-        jb.info->n_syms = jb.N;
-        jb.info->n_blocks = jb.N / jb.block_syms + 1;
+        jb.info->n_mid_syms = n;
+        jb.info->n_syms = n;
+        jb.info->n_blocks = n / jb.block_syms + 1;
         // deflate_huff refills only when lookahead == 0: the base moves when strstart reaches 2w + k*w; the last fill_window call
-        // (strstart == N) still slides when strstart >= w + max_dist (deflate.rs:1787)
+        // (strstart == N) still slides when strstart >= w_size + max_dist (deflate.rs:1787)
         const uint32_t w = jb.wsize, q = jb.N ? jb.N - 1 : 0;
         uint32_t B = q < 2 * w ? 0 : w * (1 + (q - 2 * w) / w);
         if (jb.N - B >= 2 * w - kMinLookahead) B += w;
         jb.info->final_base = B;
     }
-    if (p < jb.N) jb.syms[p] = Sym{0, jb.in[p], p};
+    if (p < n) jb.syms[p] = Sym{0, jb.in[jb.start + p], jb.start + p};
 }
 
 // level 0 (deflate/algorithm/stored.rs, one-shot with ample output): stored blocks of 65535 bytes.
 __global__ void __launch_bounds__(256) k_stored(JobBufs jb)
 {
-    const uint32_t N = jb.N;
+    const uint32_t N = jb.N - jb.start; // a dictionary does not enter stored blocks
     const uint32_t nb = N == 0 ? 1 : (N + 65534) / 65535;
     const uint32_t b = blockIdx.x;
     if (b >= nb) return;
@@ -1307,7 +1373,33 @@ __global__ void __launch_bounds__(256) k_stored(JobBufs jb)
             }
         }
     }
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) o[5 + i] = jb.in[start + i];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) o[5 + i] = jb.in[jb.start + start + i];
+}
+
+// deflate::set_dictionary (deflate.rs:535-545) inserts the dictionary's strings while the window holds nothing behind it: the last
+// one it can insert, start - 3, is hashed with a zero in place of the first input byte (standard 4-byte hash only).  The first
+// fill_window with input re-inserts that position under its true hash (deflate.rs:1829-1838) and overwrites its prev link, but its
+// entry as the head of the "zero" bucket K0 stays: the first later position of bucket K0 links to it.  One thread per candidate
+// position finds that position; the thread that holds it patches its link.
+__global__ void __launch_bounds__(256) k_links_dict_ghost(JobBufs jb, uint32_t *first)
+{
+    const uint32_t s = jb.start;
+    if (s < 3 || s >= jb.N) return;
+    const uint8_t *d = jb.in;
+    const uint32_t g = s - 3;
+    const uint32_t k0 = hash_u32((uint32_t)d[g] | ((uint32_t)d[g + 1] << 8) | ((uint32_t)d[g + 2] << 16));
+    const uint32_t kt = hash_u32((uint32_t)d[g] | ((uint32_t)d[g + 1] << 8) | ((uint32_t)d[g + 2] << 16) | ((uint32_t)d[g + 3] << 24));
+    if (k0 == kt) return;
+    const uint32_t x = g + 1 + blockIdx.x * blockDim.x + threadIdx.x; // candidates g+1 .. g+kMaxDist
+    if (x > g + kMaxDist || x + 4 > jb.N) return;
+    const uint32_t kx = hash_u32((uint32_t)d[x] | ((uint32_t)d[x + 1] << 8) | ((uint32_t)d[x + 2] << 16) | ((uint32_t)d[x + 3] << 24));
+    if (kx == k0) atomicMin(first, x);
+}
+__global__ void k_links_dict_ghost_apply(JobBufs jb, const uint32_t *first)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t x = *first;
+    if (x != 0xffffffffu) jb.L[x] = (uint16_t)(x - (jb.start - 3)); // before Lr is copied from L
 }
 
 } // namespace zb

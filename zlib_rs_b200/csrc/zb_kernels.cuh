@@ -15,7 +15,11 @@ constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA (126 KiB of
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
 constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
 constexpr uint32_t kLongPerSub = 8;     // a 1 KiB sub-tile holds at most 1024/257+1 long-match nodes
-constexpr uint32_t kPathHead = 64;      // leading positions of a path tile mirrored in the compact head table
+#ifndef ZB_PATH_HEAD
+#define ZB_PATH_HEAD 64
+#endif
+constexpr uint32_t kPathHead = ZB_PATH_HEAD; // leading positions of a path tile mirrored in the compact head table
+constexpr uint32_t kChainChunkTiles = ZB_PATH_HEAD > 64 ? 96 : 320; // tiles per staged chunk of that table in k_path_chain
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
 constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
 constexpr uint32_t kSymsPerThread = 16;
@@ -42,7 +46,8 @@ struct JobInfo {              // device-resident result / control block of one d
 // One deflate job's device buffers (see DESIGN.md "HBM layout").
 struct JobBufs {
     const uint8_t *in;    // N + kPad bytes, zero padded
-    uint32_t N;
+    uint32_t N;           // bytes in `in`: a preset dictionary (its last <= 32 KiB... see `start`) followed by the input
+    uint32_t start;       // first input position: the parser starts here; [0, start) is the dictionary (deflate.rs:498-564)
     uint32_t tail_start;
     uint16_t *L;          // N + kPad
     uint16_t *SK;         // N + kPad: reach of the chain walk of M[x]: x - (lowest position examined), 0xffff = to the end of the window

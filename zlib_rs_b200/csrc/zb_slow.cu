@@ -316,7 +316,7 @@ __global__ void k_tail_slow(JobBufs jb)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t n = jb.info->n_mid_syms;
-    if (jb.N > 0) n += emit_step(jb, jb.info->tail_entry, jb.syms + n);
+    if (jb.N > jb.start) n += emit_step(jb, jb.info->tail_entry, jb.syms + n);
     jb.info->n_syms = n;
     jb.info->final_base = base_at(jb.N, jb.N);
     uint32_t nb = n / jb.block_syms + 1;

@@ -70,6 +70,8 @@ struct DState {
     std::vector<uint8_t> in, out;
     size_t out_pos;
     gz_header *gzhead;
+    std::vector<uint8_t> dict; // preset dictionary of the next one-shot stream (deflateSetDictionary)
+    uint32_t dictid;
     int bits_used;    // deflateUsed: bits used in the last byte written (8 after a byte-aligned end)
 };
 
@@ -232,6 +234,7 @@ int deflateResetKeep(z_streamp strm)
     d->check = d->wrap == 2 ? 0 : 1;
     d->check_len = 0;
     d->in.clear(); d->out.clear(); d->out_pos = 0;
+    d->dict.clear(); d->dictid = 0;
     d->bits_used = 0;
     return Z_OK;
 }
@@ -274,6 +277,35 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     const size_t base = d->out.size();
     const size_t cap = zb_deflate_bound(n) + 64;
     int rc;
+    if (!d->dict.empty() && !d->header_done) {
+        // preset dictionary (deflate.rs:498-564, 1572-1601, 2556-2572): zlib header with FDICT and the dictionary's adler32, then the
+        // raw data of dictionary ++ input parsed from the first input byte, then the adler32 of the input
+        if (d->wrap == 1) {
+            const unsigned lf = (d->strategy >= Z_HUFFMAN_ONLY || d->level < 2) ? 0 : d->level < 6 ? 1 : d->level == 6 ? 2 : 3;
+            unsigned h = ((8u + (7u << 4)) << 8) | (lf << 6) | 0x20u;
+            h += 31 - (h % 31);
+            d->out.push_back((uint8_t)(h >> 8)); d->out.push_back((uint8_t)h);
+            for (int i = 3; i >= 0; i--) d->out.push_back((uint8_t)(d->dictid >> (8 * i)));
+        }
+        d->header_done = true;
+        const size_t b1 = d->out.size();
+        d->out.resize(b1 + cap);
+        int wb = d->window_bits < 0 ? -d->window_bits : d->window_bits;
+        rc = zb_deflate_dict(e, d->dict.data(), d->dict.size(), d->in.data(), n, 0, d->out.data() + b1, cap, 0, d->level == 0 && !final ? 1 : d->level,
+                             d->strategy, -wb, (final ? 0 : ZB_FLAG_NOT_LAST) | ZB_FLAG_CHECK_ADLER | ZB_FLAG_MEMLEVEL(d->mem_level), &r);
+        if (rc != ZB_OK) { d->out.resize(base); d->header_done = false; strm->msg = zb_last_error(); return map_rc(rc); }
+        d->out.resize(b1 + r.out_bytes);
+        d->bits_used = (int)r.bits_used;
+        d->check = d->wrap == 1 ? adler_combine(1, r.check, n) : 0;
+        d->check_len = n;
+        strm->adler = d->check;
+        if (strm->data_type == Z_UNKNOWN) strm->data_type = r.data_type;
+        d->dict.clear();
+        d->in.clear();
+        if (final) { if (d->wrap == 1) for (int i = 3; i >= 0; i--) d->out.push_back((uint8_t)(d->check >> (8 * i))); }
+        else d->any_segment = true;
+        return Z_OK;
+    }
     if (final && !d->any_segment && d->wrap == 2 && d->gzhead) {
         // one-shot gzip stream with a caller-supplied header: the engine writes the raw deflate data and returns the crc32 of the
         // input; header and trailer (crc32, isize; deflate.rs:2773-2785) are framing
@@ -422,17 +454,35 @@ int deflateParams(z_streamp strm, int level, int strategy)
     return Z_OK;
 }
 
-int deflateSetDictionary(z_streamp strm, const Bytef *, uInt)
+int deflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dictLength)
 {
+    // deflate::set_dictionary (zlib-rs/src/deflate.rs:498-564): not for gzip streams, for zlib streams only before the first
+    // deflate() call, never with input pending
+    DState *d = dstate(strm);
+    if (!d || (!dictionary && dictLength)) return Z_STREAM_ERROR;
+    if (d->wrap == 2 || (d->wrap == 1 && d->status != 1) || !d->in.empty() || d->any_segment) return Z_STREAM_ERROR;
+    if (d->wrap == 1) {
+        uint32_t id = 1;
+        zb_engine *e = engine();
+        if (!e) { strm->msg = kNoDevice; return Z_MEM_ERROR; }
+        if (dictLength && zb_adler32(e, (uint32_t)strm->adler, dictionary, dictLength, 0, &id, nullptr) != ZB_OK) return Z_MEM_ERROR;
+        d->dictid = id;
+        strm->adler = id;
+    }
+    d->dict.assign(dictionary, dictionary + dictLength);
+    return Z_OK;
+}
+int deflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength)
+{
+    // deflate::get_dictionary (deflate.rs:3292-3307): the last min(strstart + lookahead, w_size) bytes of the window -- here the
+    // dictionary followed by the input taken so far
     DState *d = dstate(strm);
     if (!d) return Z_STREAM_ERROR;
-    strm->msg = "preset dictionaries are not implemented by the B200 engine";
-    return Z_STREAM_ERROR;
-}
-int deflateGetDictionary(z_streamp strm, Bytef *, uInt *len)
-{
-    if (!dstate(strm)) return Z_STREAM_ERROR;
-    if (len) *len = 0;
+    std::vector<uint8_t> w(d->dict);
+    w.insert(w.end(), d->in.begin(), d->in.end());
+    const size_t len = w.size() < 32768 ? w.size() : 32768;
+    if (dictionary && len) memcpy(dictionary, w.data() + (w.size() - len), len);
+    if (dictLength) *dictLength = (uInt)len;
     return Z_OK;
 }
 int deflatePrime(z_streamp strm, int, int) { return dstate(strm) ? Z_BUF_ERROR : Z_STREAM_ERROR; }
@@ -480,7 +530,7 @@ uLong deflateBound(z_streamp strm, uLong sourceLen)
     if (!d) return (uLong)(comp_len + 6);
     size_t wrap_len = 6;
     if (d->wrap == 0) wrap_len = 0;
-    else if (d->wrap == 1) wrap_len = 6; // (+4 once a dictionary is set: strstart != 0)
+    else if (d->wrap == 1) wrap_len = d->dict.empty() ? 6 : 10; // + DICTID once a dictionary is set (strstart != 0)
     else if (d->wrap == 2) {
         wrap_len = 18;
         if (const gz_header *g = d->gzhead) {
