@@ -45,7 +45,7 @@ typedef struct zb_deflate_result {
     int32_t exact_parity;  /* 1: bytes equal zlib-rs' deflate(Z_FINISH) at this level/strategy/memLevel; 0: valid stream only */
     float gpu_ms;          /* device time of the call (CUDA events), copies included when buffers are on the host */
     uint32_t bits_used;    /* bits used in the last byte of the deflate data, 1..8 (deflateUsed, zlib-rs/src/deflate.rs:129) */
-    uint32_t reserved;
+    uint32_t carry;        /* END_PARTIAL / END_BLOCK: value of the partial last byte (its low bits_used bits), not part of the output */
 } zb_deflate_result;
 
 /* One engine = one CUDA device + stream + grow-only device buffers.  Not thread safe; create one per thread. */
@@ -68,6 +68,11 @@ ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_
                                    deflate_quick / deflate_fast (valid stream, smaller, not byte-identical; exact_parity = 0) */
 #define ZB_FLAG_CHECK_ADLER 4u /* raw stream (window_bits < 0), but also return the adler32 of the input in res->check: */
 #define ZB_FLAG_CHECK_CRC 8u   /* ... or its crc32 -- for callers that write the zlib / gzip framing themselves (gz_header, FDICT) */
+#define ZB_FLAG_END_PARTIAL 16u /* with NOT_LAST: end like Z_PARTIAL_FLUSH (empty static block, 10 bits, zlib-rs/src/deflate.rs:2726-2732) ... */
+#define ZB_FLAG_END_BLOCK 32u   /* ... or like Z_BLOCK (nothing): the segment ends inside a byte, whole bytes are returned and the rest
+                                   comes back in res->bits_used / res->carry for the next segment's ZB_FLAG_PRIME */
+#define ZB_FLAG_PRIME(bits, val) ((((uint32_t)(bits) & 7u) << 12) | (((uint32_t)(val) & 0xffu) << 16)) /* deflatePrime: the raw stream
+                                   starts with `bits` (< 8) bits of `val` (the partial last byte of the previous segment) */
 #define ZB_FLAG_MEMLEVEL(m) ((uint32_t)(m) << 8) /* deflateInit2's memLevel 1..9 (0 = default 8): lit_bufsize = 1 << (memLevel + 6)
                                                     sets the symbols per block (zlib-rs/src/deflate.rs:321, deflate/sym_buf.rs:23) */
 ZB_API int zb_deflate_ex(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,

@@ -41,7 +41,7 @@ class DeflateResult(ctypes.Structure):
     _fields_ = [("out_bytes", ctypes.c_uint64), ("check", ctypes.c_uint32), ("data_type", ctypes.c_int32),
                 ("iterations", ctypes.c_uint32), ("n_symbols", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32),
                 ("gpu_launches", ctypes.c_uint32), ("exact_parity", ctypes.c_int32), ("gpu_ms", ctypes.c_float),
-                ("bits_used", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("bits_used", ctypes.c_uint32), ("carry", ctypes.c_uint32)]
 
 
 class InflateResult(ctypes.Structure):

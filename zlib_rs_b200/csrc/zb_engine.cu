@@ -285,6 +285,9 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     jb.hdr_len = wrap == 1 ? 2 : wrap == 2 ? 10 : 0;
     jb.huffman_only = strategy == 2 && level != 0;
     jb.not_last = (flags & ZB_FLAG_NOT_LAST) ? 1 : 0;
+    jb.end_mode = (flags & ZB_FLAG_END_PARTIAL) ? 1u : (flags & ZB_FLAG_END_BLOCK) ? 2u : 0u;
+    jb.prime_bits = (flags >> 12) & 7u;
+    if ((jb.end_mode && !jb.not_last) || (jb.prime_bits && wrap != 0)) { snprintf(g_err, sizeof g_err, "END_* needs NOT_LAST, PRIME a raw stream"); return ZB_E_PARAM; }
     if (jb.not_last && (level == 0 || wrap != 0)) { snprintf(g_err, sizeof g_err, "NOT_LAST needs raw deflate and level > 0"); return ZB_E_PARAM; }
     jb.xfl = level == 9 ? 2 : (strategy >= 2 || level < 2) ? 4 : 0;
     // levels 3..9 and Z_RLE follow the reference parser exactly; levels 1 and 2 run the level-3 kernel set
@@ -333,6 +336,10 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     }
     CK(cudaMemsetAsync(d_info, 0, sizeof(JobInfo), st));
     CK(cudaMemsetAsync(d_out, 0, out_cap, st));
+    if (jb.prime_bits) { // the bit packing ORs into the zeroed output: the prime bits are simply there first
+        h_prime = (uint8_t)((flags >> 16) & ((1u << jb.prime_bits) - 1u));
+        CK(cudaMemcpyAsync(d_out, &h_prime, 1, cudaMemcpyHostToDevice, st));
+    }
     // checksum of the input (deflate.rs:1705-1713 computes it while filling the window)
     pbegin();
     if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in + dstart, n_in, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
@@ -579,6 +586,11 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     res->exact_parity = exact ? 1 : 0;
     res->gpu_ms = ms;
     res->bits_used = (uint32_t)(h_info->total_bits & 7u) ? (uint32_t)(h_info->total_bits & 7u) : 8u;
+    if (jb.not_last && jb.end_mode && (h_info->total_bits & 7u)) {
+        uint8_t last = 0;
+        CK(cudaMemcpy(&last, d_out + out_bytes, 1, cudaMemcpyDeviceToHost));
+        res->carry = last & ((1u << (h_info->total_bits & 7u)) - 1u);
+    }
     return ZB_OK;
 }
 

@@ -25,6 +25,7 @@ struct Engine {
     uint32_t *d_check = nullptr;
     void *d_inf_state = nullptr, *h_inf_state = nullptr; // inflate result block
     uint32_t launches = 0;
+    uint8_t h_prime = 0; // staging byte of ZB_FLAG_PRIME (must outlive the async copy)
     // optional per-phase device timing (zb_engine_set_profile): 0 links, 1 match, 2 nxt, 3 path, 4 emit+holes,
     // 5 tail, 6 blocks(hist+trees+scan), 7 encode, 8 checksum, 9 h2d, 10 d2h
     static constexpr int kPhases = 12;

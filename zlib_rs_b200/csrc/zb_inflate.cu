@@ -651,39 +651,47 @@ constexpr uint32_t kMaxBlockOut = 256u << 20;
 __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand, uint32_t *arena, uint32_t slot_syms)
 {
     __shared__ DecShared S;
-    const uint32_t k = blockIdx.x;
-    if (k >= par->ncand || k >= kMaxCand || threadIdx.x != 0) return;
+    const uint32_t k = blockIdx.x, lane = threadIdx.x;
+    if (k >= par->ncand || k >= kMaxCand) return;
     BitRd br;
-    uint32_t lenbits, distbits, bf = 0;
-    int rc = dec_setup(S, src, n, cand[k].start_bit, br, lenbits, distbits, &bf);
+    uint32_t lenbits = 0, distbits = 0, bf = 0;
+    int rc = 0;
+    if (lane == 0) rc = dec_setup(S, src, n, cand[k].start_bit, br, lenbits, distbits, &bf);
     uint32_t o = 0, ns = 0;
     uint32_t *slot = arena ? arena + (size_t)k * slot_syms : nullptr;
-    if (rc == 0) {
-        const uint32_t lm = (1u << lenbits) - 1, dm = (1u << distbits) - 1;
-        const uint64_t nbits = n * 8;
-        for (;;) {
-            uint32_t v, d;
-            const int t = dec_symbol(S, br, lm, dm, v, d);
-            if (t == 0) {
-                // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
-                if (ns < slot_syms) slot[ns] = v;
-                ns++;
-                o++;
-                if ((o & 63u) == 0 && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; break; }
-                continue;
+    const uint32_t lm = (1u << lenbits) - 1, dm = (1u << distbits) - 1;
+    const uint64_t nbits = n * 8;
+    // lane 0 decodes 32 symbols at a time into shared memory; the warp then stores them with one coalesced write (single-lane
+    // 4-byte stores made this kernel three times slower)
+    for (uint32_t done = __shfl_sync(0xffffffffu, (uint32_t)(rc != 0), 0); !done;) {
+        uint32_t cnt = 0;
+        if (lane == 0) {
+            while (cnt < 32) {
+                uint32_t v, d;
+                const int t = dec_symbol(S, br, lm, dm, v, d);
+                if (t == 0) { S.q[0][cnt++] = v; o++; continue; }
+                if (t == 1) {
+                    S.q[0][cnt++] = (v << 16) | d;
+                    o += v;
+                    if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; done = 1; break; }
+                    continue;
+                }
+                if (t < 0) rc = -t;
+                done = 1;
+                break;
             }
-            if (t == 1) {
-                if (ns < slot_syms) slot[ns] = (v << 16) | d;
-                ns++;
-                o += v;
-                if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; break; }
-                continue;
-            }
-            if (t < 0) rc = -t;
-            break;
+            // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
+            if (!done && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; done = 1; }
         }
-        if (rc == 0 && br.consumed() > nbits) rc = 8;
+        __syncwarp();
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (slot && lane < cnt && ns + lane < slot_syms) slot[ns + lane] = S.q[0][lane];
+        ns += cnt;
+        __syncwarp();
     }
+    if (lane != 0) return;
+    if (rc == 0 && br.consumed() > nbits) rc = 8;
     cand[k].end_bit = br.consumed();
     cand[k].out_len = o;
     cand[k].bfinal = bf;

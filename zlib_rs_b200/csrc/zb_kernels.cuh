@@ -95,7 +95,10 @@ struct JobBufs {
     uint4 *chain_state;       // k_path_chain: (entry, symbol base, done, tail entry) at every tile boundary
     uint32_t *bucket_map;     // 65536 bits: hash buckets in which a hole changed in the last iteration
     uint32_t use_bucket_map;  // k_match recomputes only positions of those buckets (later iterations)
-    uint32_t not_last;        // segment mode: no BFINAL, an empty stored block (00 00 ff ff) is appended
+    uint32_t not_last;        // segment mode: no BFINAL; what follows the last block is end_mode
+    uint32_t end_mode;        // not_last: 0 Z_SYNC_FLUSH marker (empty stored block, byte aligned), 1 Z_PARTIAL_FLUSH (empty static block,
+                              // 10 bits, deflate.rs:2726-2732), 2 Z_BLOCK (nothing): 1 and 2 end inside a byte, whole bytes are returned
+    uint32_t prime_bits;      // bits of the previous segment's last partial byte that this stream starts with (deflatePrime)
     uint32_t block_syms;      // symbols per deflate block: lit_bufsize - 1 = (1 << (memLevel + 6)) - 1 (deflate.rs:321, sym_buf.rs:23)
     uint32_t serial_mode;     // 1: deflate_quick (level 1), 2: deflate_fast (level 2) -- k_serial_low, zb_serial.h
     uint32_t *block_base;     // serial levels: window base in force when block b was flushed

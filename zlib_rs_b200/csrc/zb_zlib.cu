@@ -72,6 +72,8 @@ struct DState {
     gz_header *gzhead;
     std::vector<uint8_t> dict; // preset dictionary of the next one-shot stream (deflateSetDictionary)
     uint32_t dictid;
+    std::vector<uint8_t> hist; // segment mode: the last 32 KiB of input already compressed (the next segment's window)
+    uint32_t carry_bits, carry_val; // bits of a partial last byte not written yet (Z_PARTIAL_FLUSH / Z_BLOCK / deflatePrime)
     int bits_used;    // deflateUsed: bits used in the last byte written (8 after a byte-aligned end)
 };
 
@@ -235,6 +237,7 @@ int deflateResetKeep(z_streamp strm)
     d->check_len = 0;
     d->in.clear(); d->out.clear(); d->out_pos = 0;
     d->dict.clear(); d->dictid = 0;
+    d->hist.clear(); d->carry_bits = d->carry_val = 0;
     d->bits_used = 0;
     return Z_OK;
 }
@@ -268,7 +271,7 @@ static int gzip_header_bytes(const DState *d, std::vector<uint8_t> &h)
     return Z_OK;
 }
 
-static int run_segment(z_streamp strm, DState *d, bool final)
+static int run_segment(z_streamp strm, DState *d, bool final, int flush)
 {
     zb_deflate_result r;
     zb_engine *e = engine();
@@ -300,6 +303,11 @@ static int run_segment(z_streamp strm, DState *d, bool final)
         d->check_len = n;
         strm->adler = d->check;
         if (strm->data_type == Z_UNKNOWN) strm->data_type = r.data_type;
+        if (!final) {
+            d->hist = d->dict;
+            d->hist.insert(d->hist.end(), d->in.begin(), d->in.end());
+            if (d->hist.size() > 32768) d->hist.erase(d->hist.begin(), d->hist.begin() + (d->hist.size() - 32768));
+        }
         d->dict.clear();
         d->in.clear();
         if (final) { if (d->wrap == 1) for (int i = 3; i >= 0; i--) d->out.push_back((uint8_t)(d->check >> (8 * i))); }
@@ -359,11 +367,23 @@ static int run_segment(z_streamp strm, DState *d, bool final)
     const size_t b2 = d->out.size();
     d->out.resize(b2 + cap);
     const int lvl = d->level == 0 ? 1 : d->level; // stored segments need level > 0 framing
-    rc = zb_deflate_ex(e, d->in.data(), n, 0, d->out.data() + b2, cap, 0, lvl, d->strategy, -15,
-                       (final ? 0 : ZB_FLAG_NOT_LAST) | ZB_FLAG_MEMLEVEL(d->mem_level), &r);
+    // Z_PARTIAL_FLUSH ends with an empty static block, Z_BLOCK with nothing (deflate.rs:2726-2752): both stop inside a byte, the
+    // unwritten bits start the next segment.  Z_SYNC_FLUSH / Z_FULL_FLUSH end with the byte-aligned empty stored block.  The
+    // previous input stays the window of the next segment (not after Z_FULL_FLUSH, which forgets it, :2739-2751).
+    const uint32_t endf = final ? 0u : flush == Z_PARTIAL_FLUSH ? ZB_FLAG_END_PARTIAL : flush == Z_BLOCK ? ZB_FLAG_END_BLOCK : 0u;
+    const uint32_t fl = (final ? 0 : ZB_FLAG_NOT_LAST) | endf | ZB_FLAG_PRIME(d->carry_bits, d->carry_val) | ZB_FLAG_MEMLEVEL(d->mem_level);
+    rc = zb_deflate_dict(e, d->hist.empty() ? nullptr : d->hist.data(), d->hist.size(), d->in.data(), n, 0, d->out.data() + b2, cap, 0, lvl,
+                         d->strategy, -15, fl, &r);
     if (rc != ZB_OK) { d->out.resize(b2); strm->msg = zb_last_error(); return map_rc(rc); }
     d->out.resize(b2 + r.out_bytes);
     d->bits_used = (int)r.bits_used;
+    d->carry_bits = endf && r.bits_used != 8 ? r.bits_used : 0;
+    d->carry_val = d->carry_bits ? r.carry : 0;
+    if (flush == Z_FULL_FLUSH) d->hist.clear();
+    else {
+        d->hist.insert(d->hist.end(), d->in.begin(), d->in.end());
+        if (d->hist.size() > 32768) d->hist.erase(d->hist.begin(), d->hist.begin() + (d->hist.size() - 32768));
+    }
     // running check value over all consumed input (segment checks chained with the combine algebra)
     uint32_t seg = 0;
     if (d->wrap == 1) { zb_adler32(e, 1, d->in.data(), n, 0, &seg, nullptr); d->check = adler_combine(d->check, seg, n); }
@@ -415,7 +435,7 @@ int deflate(z_streamp strm, int flush)
     if (d->status != 3) {
         const bool final = flush == Z_FINISH;
         if (final || !d->in.empty() || !d->header_done) {
-            int rc = run_segment(strm, d, final);
+            int rc = run_segment(strm, d, final, flush);
             if (rc != Z_OK) return rc;
         }
         if (final) d->status = 3;
@@ -485,7 +505,25 @@ int deflateGetDictionary(z_streamp strm, Bytef *dictionary, uInt *dictLength)
     if (dictLength) *dictLength = (uInt)len;
     return Z_OK;
 }
-int deflatePrime(z_streamp strm, int, int) { return dstate(strm) ? Z_BUF_ERROR : Z_STREAM_ERROR; }
+int deflatePrime(z_streamp strm, int bits, int value)
+{
+    // deflate::prime (zlib-rs/src/deflate.rs:566-604): the bits go into the bit buffer in front of whatever is written next; whole
+    // bytes leave at once, the rest waits with the carry bits of the segment writer.  Raw streams and byte-aligned positions of
+    // wrapped ones (the engine writes its own wrapper in one piece).
+    DState *d = dstate(strm);
+    if (!d) return Z_STREAM_ERROR;
+    if (bits < 0 || bits > 32) return Z_BUF_ERROR;
+    if (bits == 0) return Z_OK;
+    if (d->wrap != 0 && !d->header_done) { strm->msg = "deflatePrime before the stream header is not implemented by the B200 engine"; return Z_STREAM_ERROR; }
+    uint64_t buf = (uint64_t)d->carry_val | (((uint64_t)(uint32_t)value & ((bits == 32 ? 0ull : (1ull << bits)) - 1ull)) << d->carry_bits);
+    uint32_t nb = d->carry_bits + (uint32_t)bits;
+    while (nb >= 8) { d->out.push_back((uint8_t)buf); buf >>= 8; nb -= 8; }
+    d->carry_bits = nb;
+    d->carry_val = (uint32_t)buf;
+    d->header_done = true; // a primed stream is built from raw segments
+    d->any_segment = true;
+    return Z_OK;
+}
 int deflatePending(z_streamp strm, unsigned *pending, int *bits)
 {
     DState *d = dstate(strm);
