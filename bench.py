@@ -325,12 +325,20 @@ def main():
         m = prof["match"]
         full_ms = prof.get("match_first", {"ms": m["ms"] / max(m["launches"], 1)})["ms"]
         achieved = N / (full_ms * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes_read+write of one full k_match launch from the committed `ncu --set full` capture -- only if that capture
+        # was made from THIS build of the kernels (sha256 of zb_kernels.cu recorded beside the number), else null
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "k_match_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            import hashlib
+            tj = json.load(open(tp))
+            src_sha = hashlib.sha256(open(os.path.join(ROOT, "zlib_rs_b200", "csrc", "zb_kernels.cu"), "rb").read()).hexdigest()
+            if tj.get("kernels_sha256") == src_sha:
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("capture")
+            else:
+                traffic_note = "profiles/k_match_traffic.json was captured from another build of zb_kernels.cu"
         roof = {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": N, "launch_ms": full_ms,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": N, "launch_ms": full_ms,
                 "phases_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "iterations": int(res.iterations)}
 
     # One stream cut into `world` contiguous ranges (BASELINE config 4): every rank compresses its range as a raw

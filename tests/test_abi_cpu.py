@@ -128,3 +128,24 @@ def test_bench_reference_arm_contract():
     assert line["metric"] == "deflate_level6_raw_input_throughput_silesia_small_tar" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_reference_zpipe_compiles_and_links_unchanged():
+    """The reference's own C client (libz-rs-sys-cdylib/zpipe.c) builds against include/zlib.h and links with -lz_b200 without a
+    source change.  The binary lands in tests/c_client/_build/ (ignored by git, shipped to the GPU box), where
+    tests/test_gpu_stream.py runs it.  Skipped where the reference tree is absent (the GPU box)."""
+    import subprocess
+    src = "/root/reference/libz-rs-sys-cdylib/zpipe.c"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present")
+    root = ROOT
+    outdir = os.path.join(ROOT, "tests", "c_client", "_build")
+    os.makedirs(outdir, exist_ok=True)
+    exe = os.path.join(outdir, "zpipe_ref")
+    r = subprocess.run(["gcc", "-O2", "-I" + os.path.join(root, "include"), src, "-L" + os.path.join(root, "zlib_rs_b200"), "-lz_b200",
+                        "-Wl,-rpath," + os.path.join(root, "zlib_rs_b200"), "-Wl,-rpath,$ORIGIN/../../../zlib_rs_b200", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for f in ("deflateInit_", "deflate", "deflateEnd", "inflateInit_", "inflate", "inflateEnd"):
+        assert (" " + f + "\n") in syms or (" " + f + "@") in syms or f in syms

@@ -359,13 +359,12 @@ FLUSH_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["flush"]
 @pytest.mark.parametrize("v", FLUSH_KATS, ids=[v["name"] for v in FLUSH_KATS])
 def test_reference_flush_vectors(v):
     """zlib-rs/src/deflate.rs:4073-4147 (test_flush): one deflate() call with a flush value on a fresh gzip stream.  Z_SYNC_FLUSH and
-    Z_FULL_FLUSH close the block and append the empty stored block: the reference's bytes.  Z_PARTIAL_FLUSH / Z_BLOCK leave the
-    stream inside a byte in the reference; the shim ends every flushed segment with the sync marker instead (valid, different)."""
+    Z_FULL_FLUSH close the block and append the empty stored block, Z_PARTIAL_FLUSH appends the empty static block and Z_BLOCK nothing
+    (both leave the stream inside a byte; the unwritten bits start the next segment): the reference's bytes in all four cases."""
     d = bytes.fromhex(v["input_hex"])
     z = Z.Deflate(v["level"], window_bits=v["window_bits"], mem_level=v["mem_level"], strategy=v["strategy"])
     out = z.deflate(d, v["flush"])
-    if v["flush"] in (Z.Z_SYNC_FLUSH, Z.Z_FULL_FLUSH):
-        assert out == bytes.fromhex(v["expected_hex"])
+    assert out == bytes.fromhex(v["expected_hex"])  # round 2: Z_PARTIAL_FLUSH and Z_BLOCK end inside a byte like the reference
     rest = z.deflate(b"", Z.Z_FINISH)
     assert zlib.decompress(out + rest, 31) == d
 

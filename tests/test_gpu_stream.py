@@ -407,3 +407,54 @@ def test_deflate_dictionary_reference_case_strategies_and_ghost_entry():
     db = ctypes.create_string_buffer(b"dict", 4)
     assert lib.deflateSetDictionary(ctypes.byref(s), ctypes.addressof(db), 4) == Z_STREAM_ERROR
     lib.deflateEnd(ctypes.byref(s))
+
+
+def test_mixed_flush_sequence_and_deflate_prime():
+    """Segments that end inside a byte (Z_PARTIAL_FLUSH, Z_BLOCK) hand their last bits to the next segment; the previous input is the
+    next segment's window (not after Z_FULL_FLUSH).  The stitched stream is what stock zlib inflates; deflatePrime puts bits in front
+    of a raw stream (zlib-rs/src/deflate.rs:566-604)."""
+    d = silesia_member(3)[:400000]
+    flushes = [Z.Z_PARTIAL_FLUSH, Z.Z_BLOCK, Z.Z_SYNC_FLUSH, Z.Z_BLOCK, Z.Z_PARTIAL_FLUSH, Z.Z_FULL_FLUSH, Z.Z_BLOCK, Z.Z_NO_FLUSH]
+    for wbits in (15, -15, 31):
+        z = Z.Deflate(6, window_bits=wbits)
+        out = bytearray()
+        step = len(d) // len(flushes)
+        for i, f in enumerate(flushes):
+            out += z.deflate(d[i * step:(i + 1) * step], f)
+        out += z.deflate(d[len(flushes) * step:], Z.Z_FINISH)
+        assert zlib.decompress(bytes(out), wbits) == d
+        if wbits == 15:
+            one = zlib.compress(d, 6)
+            assert len(out) < len(one) * 1.02  # the window survives the flushes: hardly any ratio is lost
+    # deflatePrime: 5 bits in front of a raw stream; dropping them again gives a stream that inflates
+    lib = L()
+    lib.deflatePrime.argtypes = [ctypes.POINTER(Z.ZStream), ctypes.c_int, ctypes.c_int]
+    s = Z.ZStream()
+    assert lib.deflateInit2_(ctypes.byref(s), 6, 8, -15, 8, 0, Z.ZLIB_VERSION, ctypes.sizeof(Z.ZStream)) == Z_OK
+    assert lib.deflatePrime(ctypes.byref(s), 5, 0b10110) == Z_OK
+    data = d[:50000]
+    src = ctypes.create_string_buffer(data, len(data))
+    dst = ctypes.create_string_buffer(len(data))
+    s.next_in, s.avail_in, s.next_out, s.avail_out = ctypes.addressof(src), len(data), ctypes.addressof(dst), len(data)
+    assert lib.deflate(ctypes.byref(s), Z_FINISH) == Z_STREAM_END
+    out = dst.raw[: s.total_out]
+    lib.deflateEnd(ctypes.byref(s))
+    assert out[0] & 31 == 0b10110
+    bits = int.from_bytes(out, "little") >> 5
+    assert zlib.decompress(bits.to_bytes(len(out), "little"), -15) == data
+
+
+def test_reference_zpipe_binary_round_trip(tmp_path):
+    """The reference's zpipe.c, built unchanged against this library by tests/test_abi_cpu.py (in the build container), compresses and
+    decompresses a file of several MiB through 16 KiB deflate()/inflate() calls."""
+    import subprocess
+    exe = os.path.join(HERE, "c_client", "_build", "zpipe_ref")
+    if not os.path.exists(exe):
+        pytest.skip("zpipe_ref was not built (reference tree absent at build time)")
+    d = silesia_tar()[: 5 << 20]
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(os.path.dirname(HERE), "zlib_rs_b200"))
+    z = subprocess.run([exe], input=d, capture_output=True, timeout=600, env=env)
+    assert z.returncode == 0, z.stderr[-500:]
+    assert zlib.decompress(z.stdout) == d and z.stdout == O.compress(d, 6)[1]  # Z_DEFAULT_COMPRESSION through deflate(Z_FINISH) at EOF
+    u = subprocess.run([exe, "-d"], input=z.stdout, capture_output=True, timeout=600, env=env)
+    assert u.returncode == 0 and u.stdout == d

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "zb_engine_internal.h"
 #include "zb_inflate_core.h"
 
@@ -456,7 +458,7 @@ constexpr uint32_t kMaxBlocks = 1u << 16;
 constexpr uint32_t kHashSize = 1u << 18;
 enum { PS_OK = 0, PS_FALLBACK = 1 };
 
-struct InfCand { uint64_t start_bit, end_bit; uint32_t out_len, valid, bfinal, nsyms; }; // nsyms: symbols kept in the arena (0: none)
+struct InfCand { uint64_t start_bit, end_bit; uint32_t out_len, valid, bfinal, nsyms; uint32_t dbg_kcyc, dbg_mode; }; // nsyms: symbols kept in the arena (0: none)
 struct InfBlock { uint64_t start_bit, out_off; uint32_t out_len, type, src_byte, cand; }; // cand: candidate index of a dynamic block
 struct InfPar {
     uint32_t ncand, nblocks, status, kind;
@@ -645,58 +647,200 @@ __device__ __forceinline__ int dec_symbol(const DecShared &S, BitRd &br, uint32_
 
 constexpr uint32_t kMaxBlockOut = 256u << 20;
 
-// 2. measure every candidate (one decoding lane per candidate, no output)
-// The symbols are kept (one 32-bit word each: a literal, or length << 16 | distance) in the candidate's slot of the arena, so that
-// k_inf_decode does not decode the Huffman codes a second time; a block with more symbols than a slot is decoded again there.
+// 2. measure every candidate and keep its symbols.  Huffman decoding of one block is serial in principle, but it resynchronises:
+// a decoder started at a wrong bit usually falls into step with the true symbol boundaries within a few symbols, and a deflate
+// symbol boundary is all the state there is inside a block.  So the 32 lanes of the warp split the block's bit range (up to the
+// next candidate's start -- the guess of where it ends):
+//   pass 1  every lane decodes its sub-range from a guessed start (lane 0 from the true first symbol) and notes where it left it;
+//   pass 2+ lane j starts where lane j-1 left and decodes again, now keeping the symbols; the pass repeats for the lanes whose start
+//           moved, until start(j) == exit(j-1) everywhere: by induction from lane 0 these are the true symbol boundaries.
+// One pass after the speculative one is the rule; the worst case (never resynchronising) degenerates to the serial order, not to a
+// wrong answer.  The symbols (one 32-bit word each: a literal, or length << 16 | distance) are compacted into the candidate's slot
+// of the arena, so that k_inf_decode does not decode Huffman codes a second time.  Blocks that do not fit the per-lane staging, or
+// that run past the guessed end, are decoded by lane 0 alone as before.
+constexpr uint32_t kScanLaneCap = 4096;   // staged symbols per lane and pass
+constexpr uint32_t kScanMinBits = 8192;   // shorter blocks are not worth splitting
+constexpr uint32_t kScanWarmBits = 2048;  // a lane starts this far in front of its range
+
+struct LaneRun { uint64_t exit_bit; uint32_t nsym, nout; int rc; uint32_t eob; };
+
+// decode from the reader's position until `stop_bit` is reached (symbol boundary >= stop_bit), the end of the block, or an error
+__device__ __forceinline__ LaneRun scan_run(const DecShared &S, BitRd &br, uint32_t lm, uint32_t dm, uint64_t stop_bit, uint64_t nbits,
+                                            uint32_t *keep, uint32_t cap)
+{
+    LaneRun r{0, 0, 0, 0, 0};
+    while (br.consumed() < stop_bit) {
+        uint32_t v, d;
+        const int t = dec_symbol(S, br, lm, dm, v, d);
+        if (t == 0) { if (keep && r.nsym < cap) keep[r.nsym] = v; r.nsym++; r.nout++; }
+        else if (t == 1) { if (keep && r.nsym < cap) keep[r.nsym] = (v << 16) | d; r.nsym++; r.nout += v; }
+        else { if (t == 2) r.eob = 1; else r.rc = -t; break; }
+        if (br.consumed() > nbits || r.nout > kMaxBlockOut) { r.rc = 7; break; }
+    }
+    r.exit_bit = br.consumed();
+    return r;
+}
+
 __global__ void __launch_bounds__(32) k_inf_scan(const uint8_t *src, uint64_t n, InfPar *par, InfCand *cand, uint32_t *arena, uint32_t slot_syms)
 {
     __shared__ DecShared S;
+    __shared__ uint64_t s_exit[33];
+    __shared__ uint32_t s_cnt[32], s_out[32], s_flag[32];
     const uint32_t k = blockIdx.x, lane = threadIdx.x;
-    if (k >= par->ncand || k >= kMaxCand) return;
+    const uint32_t ncand = min(par->ncand, kMaxCand);
+    if (k >= ncand) return;
+    const uint64_t nbits = n * 8, start_bit = cand[k].start_bit;
+    const long long t_begin = clock64();
+    uint32_t dbg_mode = 0; // 1 split decode, 2 serial decode, 3 unresolved; + 16 * passes of the last split attempt
+    // Where the block probably ends: the nearest candidate behind this one -- or the one after that, when a false candidate sits
+    // inside a true block.  A candidate that runs past both without an end-of-block code is left unresolved: it is a false
+    // candidate decoding garbage (they never reach the chain, and must not be the long pole of the kernel), or a block k_inf_chain
+    // hands to the serial decoder.
+    uint64_t lim[2] = {nbits, nbits};
+    for (uint32_t i = lane; i < ncand; i += 32) {
+        const uint64_t b = cand[i].start_bit;
+        if (b > start_bit) { if (b < lim[0]) { lim[1] = lim[0]; lim[0] = b; } else if (b < lim[1]) lim[1] = b; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const uint64_t a0 = __shfl_xor_sync(0xffffffffu, lim[0], o), a1 = __shfl_xor_sync(0xffffffffu, lim[1], o);
+        // merge two sorted pairs, keep the two smallest
+        const uint64_t m0 = min(lim[0], a0), m1 = min(max(lim[0], a0), min(lim[1], a1));
+        lim[0] = m0; lim[1] = m1;
+    }
     BitRd br;
     uint32_t lenbits = 0, distbits = 0, bf = 0;
-    int rc = 0;
-    if (lane == 0) rc = dec_setup(S, src, n, cand[k].start_bit, br, lenbits, distbits, &bf);
-    uint32_t o = 0, ns = 0;
-    uint32_t *slot = arena ? arena + (size_t)k * slot_syms : nullptr;
-    const uint32_t lm = (1u << lenbits) - 1, dm = (1u << distbits) - 1;
-    const uint64_t nbits = n * 8;
-    // lane 0 decodes 32 symbols at a time into shared memory; the warp then stores them with one coalesced write (single-lane
-    // 4-byte stores made this kernel three times slower)
-    for (uint32_t done = __shfl_sync(0xffffffffu, (uint32_t)(rc != 0), 0); !done;) {
-        uint32_t cnt = 0;
-        if (lane == 0) {
-            while (cnt < 32) {
-                uint32_t v, d;
-                const int t = dec_symbol(S, br, lm, dm, v, d);
-                if (t == 0) { S.q[0][cnt++] = v; o++; continue; }
-                if (t == 1) {
-                    S.q[0][cnt++] = (v << 16) | d;
-                    o += v;
-                    if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; done = 1; break; }
-                    continue;
+    int rc0 = 0;
+    uint64_t body = 0;
+    if (lane == 0) { rc0 = dec_setup(S, src, n, start_bit, br, lenbits, distbits, &bf); body = br.consumed(); }
+    __syncwarp();
+    rc0 = __shfl_sync(0xffffffffu, rc0, 0);
+    body = __shfl_sync(0xffffffffu, body, 0);
+    const uint32_t lm = (1u << __shfl_sync(0xffffffffu, lenbits, 0)) - 1, dm = (1u << __shfl_sync(0xffffffffu, distbits, 0)) - 1;
+    uint32_t *slot = arena ? arena + (size_t)k * (slot_syms + 32u * kScanLaneCap) : nullptr;
+    uint32_t *stage = slot ? slot + slot_syms + (size_t)lane * kScanLaneCap : nullptr;
+    uint64_t end_bit = body;
+    uint32_t total_out = 0, total_syms = 0, kept = 0;
+    int rc = rc0;
+    bool done = rc0 != 0;
+    for (uint32_t attempt = 0; attempt < 2 && !done; attempt++) {
+        const uint64_t limit = lim[attempt];
+        if (attempt == 1 && lim[1] == lim[0]) break;
+        if (slot && limit > body + kScanMinBits) {
+            // ---- split decode
+            const uint64_t chunk = (limit - body + 31) / 32;
+            const uint64_t my_b0 = body + lane * chunk, my_b1 = lane == 31 ? limit : body + (lane + 1) * chunk;
+            // pass 1: a lane warms up in front of its range, so that it has usually fallen into step by the time it enters it
+            uint64_t my_start = my_b0;
+            if (lane > 0) {
+                const uint64_t warm = my_b0 - body < kScanWarmBits ? my_b0 - body : kScanWarmBits;
+                br.init(src, n, my_b0 - warm);
+                const LaneRun w = scan_run(S, br, lm, dm, my_b0, nbits, nullptr, 0);
+                if (w.rc || w.eob) br.init(src, n, my_b0);
+                my_start = br.consumed();
+            } else br.init(src, n, body);
+            LaneRun run = my_start >= my_b1 ? LaneRun{my_start, 0, 0, 0, 0} : scan_run(S, br, lm, dm, my_b1, nbits, stage, kScanLaneCap);
+            bool ok = false;
+            uint32_t npass = 0;
+            for (uint32_t pass = 0; pass < 34 && !ok; pass++) {
+                npass++;
+                s_exit[lane + 1] = run.exit_bit;
+                s_flag[lane] = run.eob | (run.rc ? 2u : 0u);
+                __syncwarp();
+                // where the true chain says this lane starts: the exit of the lane before, unless that one ended the block
+                const uint64_t want = lane == 0 ? body : s_exit[lane];
+                const bool prev_stop = lane > 0 && s_flag[lane - 1] != 0;
+                const bool redo = lane > 0 && !prev_stop && want != my_start;
+                __syncwarp();
+                if (redo) {
+                    my_start = want;
+                    br.init(src, n, my_start);
+                    run = want >= my_b1 ? LaneRun{want, 0, 0, 0, 0} : scan_run(S, br, lm, dm, my_b1, nbits, stage, kScanLaneCap);
                 }
-                if (t < 0) rc = -t;
-                done = 1;
-                break;
+                ok = !__any_sync(0xffffffffu, redo);
             }
-            // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
-            if (!done && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; done = 1; }
+            // the chain: lanes 0..L where L is the first lane that ended the block (end-of-block code or error)
+            s_exit[lane + 1] = run.exit_bit;
+            s_flag[lane] = run.eob | (run.rc ? 2u : 0u);
+            s_cnt[lane] = run.nsym;
+            s_out[lane] = run.nout;
+            __syncwarp();
+            uint32_t last = 32;
+            for (uint32_t j = 0; j < 32; j++) if (s_flag[j]) { last = j; break; }
+            const bool over = __any_sync(0xffffffffu, lane <= last && run.nsym > kScanLaneCap);
+            dbg_mode = 1 + 16 * npass;
+            if (ok && last < 32) {
+                total_syms = total_out = 0;
+                for (uint32_t j = 0; j <= last; j++) { total_syms += s_cnt[j]; total_out += s_out[j]; }
+                end_bit = s_exit[last + 1];
+                rc = (s_flag[last] & 2u) ? __shfl_sync(0xffffffffu, run.rc, last) : 0;
+                if (rc == 0 && end_bit > nbits) rc = 8;
+                // compaction: the lanes' staged symbols become one sequence (coalesced copies, lane region after lane region)
+                kept = 0;
+                if (rc == 0 && !over && total_syms <= slot_syms) {
+                    uint32_t off = 0;
+                    for (uint32_t j = 0; j <= last; j++) {
+                        const uint32_t *sj = slot + slot_syms + (size_t)j * kScanLaneCap;
+                        for (uint32_t i = lane; i < s_cnt[j]; i += 32) slot[off + i] = sj[i];
+                        off += s_cnt[j];
+                    }
+                    kept = total_syms;
+                }
+                done = true;
+            }
+            __syncwarp();
+        } else {
+            // ---- serial decode by lane 0 (short blocks, no arena), up to the limit of this attempt
+            if (lane == 0) br.init(src, n, body);
+            uint32_t o = 0, ns = 0, ended = 0;
+            for (uint32_t fin = 0; !fin;) {
+                uint32_t cnt = 0;
+                if (lane == 0) {
+                    while (cnt < 32) {
+                        if (br.consumed() >= limit) { fin = 1; break; } // ran into the next block: not this attempt
+                        uint32_t v, d;
+                        const int t = dec_symbol(S, br, lm, dm, v, d);
+                        if (t == 0) { S.q[0][cnt++] = v; o++; continue; }
+                        if (t == 1) {
+                            S.q[0][cnt++] = (v << 16) | d;
+                            o += v;
+                            if (o > kMaxBlockOut || br.consumed() > nbits) { rc = 7; fin = 1; ended = 1; break; }
+                            continue;
+                        }
+                        if (t < 0) rc = -t;
+                        fin = 1; ended = 1;
+                        break;
+                    }
+                    // beyond the input the bit reader yields zeros: a block whose all-zero code word is a literal would never end
+                    if (!fin && (o > kMaxBlockOut || br.consumed() > nbits)) { rc = 7; fin = 1; ended = 1; }
+                }
+                __syncwarp();
+                cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                fin = __shfl_sync(0xffffffffu, fin, 0);
+                if (slot && lane < cnt && ns + lane < slot_syms) slot[ns + lane] = S.q[0][lane];
+                ns += cnt;
+                __syncwarp();
+            }
+            dbg_mode = 2;
+            if (__shfl_sync(0xffffffffu, ended, 0)) {
+                rc = __shfl_sync(0xffffffffu, rc, 0);
+                if (lane == 0) { end_bit = br.consumed(); if (rc == 0 && end_bit > nbits) rc = 8; }
+                end_bit = __shfl_sync(0xffffffffu, end_bit, 0);
+                rc = __shfl_sync(0xffffffffu, rc, 0);
+                total_out = __shfl_sync(0xffffffffu, o, 0);
+                kept = (rc == 0 && slot && ns <= slot_syms) ? ns : 0u;
+                done = true;
+            } else rc = 0;
         }
-        __syncwarp();
-        cnt = __shfl_sync(0xffffffffu, cnt, 0);
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (slot && lane < cnt && ns + lane < slot_syms) slot[ns + lane] = S.q[0][lane];
-        ns += cnt;
-        __syncwarp();
     }
+    if (!done) { rc = 9; dbg_mode = 3 | (dbg_mode & ~3u); } // unresolved: not a block that ends at one of the next two candidates
     if (lane != 0) return;
-    if (rc == 0 && br.consumed() > nbits) rc = 8;
-    cand[k].end_bit = br.consumed();
-    cand[k].out_len = o;
+    cand[k].end_bit = end_bit;
+    cand[k].out_len = total_out;
     cand[k].bfinal = bf;
     cand[k].valid = rc == 0;
-    cand[k].nsyms = (rc == 0 && slot && ns <= slot_syms) ? ns : 0u;
+    cand[k].nsyms = rc == 0 ? kept : 0u;
+    cand[k].dbg_kcyc = (uint32_t)((clock64() - t_begin) >> 10);
+    cand[k].dbg_mode = dbg_mode;
 }
 
 // 3. follow the chain of blocks from the first one
@@ -785,7 +929,7 @@ __global__ void __launch_bounds__(64) k_inf_decode(const uint8_t *src, uint64_t 
     const uint32_t kept = (arena && b.type == 2) ? cand[b.cand].nsyms : 0u;
     if (warp == 0 && kept) {
         // ---- the symbols are already there (k_inf_scan): the warp only feeds them to the replaying warp, 32 per batch
-        const uint32_t *slot = arena + (size_t)b.cand * slot_syms;
+        const uint32_t *slot = arena + (size_t)b.cand * (slot_syms + 32u * kScanLaneCap);
         for (uint32_t it = 0;; it++) {
             const uint32_t q = it & 3;
             if (it >= 4) nb_sync(kEmpty + q);
@@ -1012,9 +1156,22 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
             // symbol arena: one slot per candidate (a deflate block of zlib-family encoders has at most 32767 symbols + end of block)
             constexpr uint32_t kSlotSyms = 40960;
             uint32_t *darena = nullptr;
-            if ((size_t)hpar.ncand * kSlotSyms * 4 <= ((size_t)2 << 30) && reserve(36 /* inflate symbol arena */, (size_t)hpar.ncand * kSlotSyms * 4, &p) == ZB_OK)
+            const size_t slot_words = (size_t)kSlotSyms + 32u * kScanLaneCap; // the compacted symbols + the lanes' staging areas
+            if ((size_t)hpar.ncand * slot_words * 4 <= ((size_t)2 << 30) && reserve(36 /* inflate symbol arena */, (size_t)hpar.ncand * slot_words * 4, &p) == ZB_OK)
                 darena = static_cast<uint32_t *>(p);
             k_inf_scan<<<hpar.ncand, 32, 0, st>>>(d_src, n, dpar, dcand, darena, darena ? kSlotSyms : 0u);
+            if (getenv("ZB_DEBUG")) {
+                std::vector<InfCand> hc(hpar.ncand);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(hc.data(), dcand, sizeof(InfCand) * hpar.ncand, cudaMemcpyDeviceToHost);
+                std::sort(hc.begin(), hc.end(), [](const InfCand &a, const InfCand &b) { return a.dbg_kcyc > b.dbg_kcyc; });
+                unsigned long long modes[4] = {0, 0, 0, 0};
+                for (auto &c : hc) modes[c.dbg_mode & 3]++;
+                fprintf(stderr, "scan: %u candidates, split ok %llu, serial short %llu, serial after failed split %llu\n", hpar.ncand, modes[1], modes[2], modes[3]);
+                for (size_t i = 0; i < hc.size() && i < 8; i++)
+                    fprintf(stderr, "  cand start %llu end %llu kcyc %u mode 0x%x valid %u out %u nsyms %u\n", (unsigned long long)hc[i].start_bit,
+                            (unsigned long long)hc[i].end_bit, hc[i].dbg_kcyc, hc[i].dbg_mode, hc[i].valid, hc[i].out_len, hc[i].nsyms);
+            }
             k_inf_chain<<<1, 32, 0, st>>>(d_src, n, dpar, dcand, dhtab, dblk);
             launches += 2;
             CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));

@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t qld_u32u(uint32_t a) // unaligned
 
 constexpr uint32_t kSlowSafe = 1024; // nodes this close to the end of the input take the generic slow_step()
 constexpr uint32_t kSlowBatch = 8;
-constexpr uint32_t kSlowBurst = 4;
+constexpr uint32_t kSlowBurst = 8;
 enum { SS_IDLE = 0, SS_START = 1, SS_WALK = 2, SS_PEND = 3, SS_DONE = 4 };
 
 // The lanes of a warp run the macro steps of different fresh loop-tops.  A lane is IDLE (needs a node), at the
@@ -133,32 +133,41 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
         cur -= d;
     };
 
+    // One pass of the loop: a burst of walk steps for the walking lanes (a tight loop: the link, the byte at index `best` as the
+    // only filter, a handful of integer instructions per candidate; a lane leaves it at its first event and the event is re-derived
+    // from registers), then -- each only when enough lanes wait for it -- the starts of new searches, the full compares, the refill.
+    // The search semantics are those of the round-1 kernel; the schedule is the one measured on k_match (zb_kernels.cu).
+    uint32_t fadj = 0; // dadj + best - mo: the filter byte of candidate chain position `cur` sits at fadj + cur
     for (;;) {
+        if (state == SS_WALK) {
+            if (chain > kSlowBurst) {
+                uint32_t fb, d;
+                bool more = false;
+#pragma unroll
+                for (uint32_t k = 0; k < kSlowBurst; k++) {
+                    fb = qld_u8(fadj + cur);
+                    d = qld_u16(ladj + 2 * cur);
+                    if (fb == xb) break;
+                    chain--;
+                    if (d == 0 || d >= cur - limit) break; // the chain ends or leaves the window
+                    cur -= d;
+                    if (k + 1 == kSlowBurst) more = true;
+                }
+                if (!more) {
+                    if (fb == xb) { cand = cur - mo; state = SS_PEND; }
+                    else finish_search(best, mstart, true);
+                }
+            } else {
+                if (cur >= q) finish_search(best, mstart, true);
+                else if (qld_u8(fadj + cur) == xb) { cand = cur - mo; state = SS_PEND; }
+                else next_in_chain();
+            }
+        }
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == SS_IDLE);
         const uint32_t m_start = __ballot_sync(0xffffffffu, state == SS_START);
         const uint32_t m_walk = __ballot_sync(0xffffffffu, state == SS_WALK);
         const uint32_t m_pend = __ballot_sync(0xffffffffu, state == SS_PEND);
         if ((m_idle | m_start | m_walk | m_pend) == 0) break;
-        if (m_idle && (__popc(m_idle) >= (int)kSlowBatch || (m_start | m_walk | m_pend) == 0)) {
-            uint32_t base = 0;
-            const uint32_t leader = __ffs(m_idle) - 1;
-            if (lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (state == SS_IDLE) {
-                const uint32_t x = base + __popc(m_idle & ((1u << lane) - 1u));
-                if (x >= te) state = SS_DONE;
-                else if (x + kSlowSafe > N) {
-                    p = x;
-                    const SlowStep s = slow_step(acc, x, N, sp);
-                    write_node(s.next, s.nlit, s.len, s.dist);
-                } else {
-                    p = q = x; l = 0; ms = 0;
-                    B = base_at(x, N);
-                    state = SS_START;
-                }
-            }
-            continue;
-        }
         // START/PEND lanes do not wait for the walkers when few lanes are busy at all
         const uint32_t thr = min(kSlowBatch, max(1u, (uint32_t)__popc(m_start | m_walk | m_pend) / 4u));
         if (m_start && (__popc(m_start) >= (int)thr || m_walk == 0)) {
@@ -189,15 +198,14 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                         limit = limit_base + mo;
                         ended = cur <= limit;
                     }
-                    if (ended) finish_search(best, mstart, true);
+                    if (ended || cur >= q) finish_search(best, mstart, true);
                     else {
                         xb = qld_u8(dadj + q + best);
-                        xw0 = qld_u32u(dadj + q);
+                        fadj = dadj + best - mo;
                         state = SS_WALK;
                     }
                 }
             }
-            continue;
         }
         if (m_pend && (__popc(m_pend) >= (int)thr || m_walk == 0)) {
             if (state == SS_PEND) {
@@ -248,22 +256,25 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                         } else next_in_chain();
                     }
                 } else next_in_chain();
+                if (state == SS_WALK) { fadj = dadj + best - mo; if (cur >= q) finish_search(best, mstart, true); }
             }
-            continue;
         }
-#pragma unroll
-        for (uint32_t burst = 0; burst < kSlowBurst; burst++) {
-            if (state == SS_WALK) {
-                if (cur >= q) finish_search(best, mstart, true);
-                else {
-                    const uint32_t c = cur - mo;
-                    bool pass = qld_u8(dadj + c + best) == xb;
-                    if (pass) {
-                        const uint32_t dw = qld_u32u(dadj + c) ^ xw0;
-                        pass = (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
-                    }
-                    if (pass) { cand = c; state = SS_PEND; }
-                    else next_in_chain();
+        if (m_idle && (__popc(m_idle) >= (int)kSlowBatch || (m_start | m_walk | m_pend) == 0)) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(m_idle) - 1;
+            if (lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (state == SS_IDLE) {
+                const uint32_t x = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (x >= te) state = SS_DONE;
+                else if (x + kSlowSafe > N) {
+                    p = x;
+                    const SlowStep s = slow_step(acc, x, N, sp);
+                    write_node(s.next, s.nlit, s.len, s.dist);
+                } else {
+                    p = q = x; l = 0; ms = 0;
+                    B = base_at(x, N);
+                    state = SS_START;
                 }
             }
         }
