@@ -411,8 +411,12 @@ def main():
             other = {}
             best = min(eng.inflate(gz, N)[2].gpu_ms for _ in range(3))
             rc, got, r3 = eng.inflate(gz, N)
+            peak_i = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+            alg = len(gz) + N  # compressed bytes in + raw bytes out
             other["inflate_silesia_small_tar_gz"] = {"ms": best, "out_GBps": N / best / 1e6, "bit_exact": bool(rc == 0 and got == tar),
-                                                     "gpu_launches": int(r3.gpu_launches), "note": "config 3; host buffers, copies inside the timed region"}
+                                                     "gpu_launches": int(r3.gpu_launches), "note": "config 3; host buffers, copies inside the timed region",
+                                                     "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / best / 1e6, "peak": peak_i, "unit": "GB/s",
+                                                                  "frac": alg / best / 1e6 / peak_i, "note": "whole call incl. H2D/D2H; the kernels are latency-bound (DESIGN.md 2c)"}}
             o9, r9 = eng.deflate(ins[0].data_ptr(), n=N, level=9, src_on_device=True, dst=out_t.data_ptr(), dst_cap=cap, dst_on_device=True)
             o9, r9 = eng.deflate(ins[1].data_ptr(), n=N, level=9, src_on_device=True, dst=out_t.data_ptr(), dst_cap=cap, dst_on_device=True)
             out9 = bytes(out_t[: int(r9.out_bytes)].cpu().numpy().tobytes())

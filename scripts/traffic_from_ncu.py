@@ -13,7 +13,7 @@ def val(name):
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 out = {"kernel": "k_match (first, full launch)", "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
        "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"),
-       "duration_ms_under_ncu": val("gpu__time_duration.sum") / 1e6 if "gpu__time_duration.sum" in H else None,
+       "duration_under_ncu": V[H.index("gpu__time_duration.sum")] + " " + U[H.index("gpu__time_duration.sum")],
        "inst_executed": val("smsp__inst_executed.sum"), "threads_per_inst": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
        "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
        "kernels_sha256": hashlib.sha256(open(os.path.join(ROOT, "zlib_rs_b200", "csrc", "zb_kernels.cu"), "rb").read()).hexdigest(),

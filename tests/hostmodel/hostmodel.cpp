@@ -126,6 +126,88 @@ extern "C" int hm_parse_parallel(const uint8_t *data, uint32_t N, int level, Sym
     return 0;
 }
 
+
+// The parallel formulation with a window smaller than 32 KiB (windowBits 9..14): same phases as hm_parse_parallel, links capped at the
+// window's match range, the window schedule of DynWin everywhere.
+struct HostAccW {
+    const uint8_t *data; uint32_t N; const uint16_t *L; const uint32_t *holes; const uint32_t *M; uint32_t w;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 2 * w) return 0; y -= w; }
+        return data[y];
+    }
+    uint32_t link(uint32_t y) const { return y + 4 <= N ? L[y] : 0; }
+    bool inserted(uint32_t y) const { return !((holes[y >> 5] >> (y & 31)) & 1u); }
+    Match mlook(uint32_t x) const { uint32_t v = M[x]; return Match{v >> 16, x - (v & 0xffff)}; }
+};
+
+extern "C" int hm_parse_parallel_w(const uint8_t *data, uint32_t N, int level, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms,
+                                   uint32_t *iters_out)
+{
+    const DynWin wn{1u << wbits};
+    LevelParams lp = level_params(level);
+    std::vector<uint16_t> L(N + 8, 0);
+    {
+        std::vector<int64_t> head(65536, -1);
+        for (uint32_t x = 0; x + 4 <= N; x++) {
+            uint32_t v = data[x] | (data[x + 1] << 8) | (data[x + 2] << 16) | ((uint32_t)data[x + 3] << 24);
+            uint32_t h = hash_u32(v);
+            if (head[h] >= 0 && x - head[h] <= wn.maxdist()) L[x] = (uint16_t)(x - head[h]);
+            head[h] = x;
+        }
+    }
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), newholes((N >> 5) + 2, 0);
+    std::vector<uint32_t> M(N + 1024, 0), nxt(N + 1, 0);
+    HostAccW a{data, N, L.data(), holes.data(), M.data(), wn.w};
+    uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    uint32_t iters = 0;
+    std::vector<uint32_t> path;
+    uint32_t tail_entry = 0;
+    for (;;) {
+        iters++;
+        for (uint32_t x = 0; x < N; x++) {
+            Match m = (x + kMSafe <= N) ? lm_walk(a, x, 0xffffffffu, lp, wn) : Match{0, 0};
+            M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+        }
+        for (uint32_t p = 0; p < tail_start; p++) {
+            uint32_t ns;
+            nxt[p] = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns, wn);
+        }
+        path.clear();
+        uint32_t p = 0;
+        while (p < tail_start) {
+            if (nxt[p] >= tail_start) break;
+            path.push_back(p);
+            p = nxt[p];
+        }
+        tail_entry = p;
+        std::fill(newholes.begin(), newholes.end(), 0);
+        for (uint32_t q : path) {
+            uint32_t ns;
+            macro_step(a, q, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy)
+                    for (uint32_t y = s.pos + 1; y + 1 < s.pos + s.lc + 3; y++) newholes[y >> 5] |= 1u << (y & 31);
+            }, &ns, wn);
+        }
+        if (newholes == holes) break;
+        holes = newholes;
+        a.holes = holes.data();
+        if (iters > N / 257u + 64u) return -1;
+    }
+    uint32_t n = 0;
+    for (uint32_t q : path) {
+        uint32_t ns;
+        macro_step(a, q, lp, tail_start, [&](Sym s) { if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc}; n++; }, &ns, wn);
+    }
+    std::vector<uint32_t> ins(64 + (N - tail_entry) / 32 + 2, 0);
+    serial_medium(a, N, tail_entry, ins.data(), (uint32_t)ins.size(), lp, [&](Sym s, uint32_t) {
+        if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc};
+        n++;
+    }, wn);
+    *nsyms = n;
+    *iters_out = iters;
+    return 0;
+}
+
 // Oracle trace (reference parser's tallied symbols)
 struct TraceCtx { SymOut *out; uint32_t cap, n; };
 static void trace_cb(void *ctx, uint64_t pos, unsigned dist, unsigned lc_or_len)

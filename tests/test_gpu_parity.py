@@ -508,3 +508,20 @@ def test_compression_corpus_files_are_reproduced_on_the_gpu(name, eng):
     assert out == want and r.exact_parity == 1
     raw, r = eng.deflate(data, level=level, strategy=strategy, window_bits=-15)
     assert raw == want[10:-8]
+
+
+def test_small_windows_parallel_path_levels_3_to_6(eng):
+    """windowBits 9..14 at levels 3..6 beyond the serial simulator's range (round 2): the parallel kernels take the window size as a
+    parameter; 300 KB inputs slide a 512-byte window a thousand times."""
+    srcs = [synthetic_mix(300000, 9), silesia_member(9)[:300000], silesia_member(1)[:300000], silesia_member(3)[:200000]]
+    for wb in (9, 10, 11, 12, 13, 14):
+        for i, src in enumerate(srcs):
+            for level in ((3, 6) if (wb + i) % 2 else (4, 5)):
+                out, res = eng.deflate(src, level=level, window_bits=wb)
+                assert res.exact_parity == 1 and out == O.compress(src, level, wb)[1], (wb, i, level)
+    d = srcs[1][:100000]
+    assert eng.deflate(d, level=6, window_bits=-12)[0] == O.compress(d, 6, -12)[1]
+    assert eng.deflate(d, level=6, window_bits=28, mem_level=4)[0] == O.compress(d, 6, 28, 4)[1]
+    for level in (7, 9):  # not built: the lazy levels keep the 32 KiB engine for sliding small windows (valid stream, CINFO 7)
+        out, res = eng.deflate(d, level=level, window_bits=12)
+        assert res.exact_parity == 0 and zlib.decompress(out) == d

@@ -187,3 +187,19 @@ def test_fuzz_smoke():
     spec.loader.exec_module(m)
     cases, bad = m.run(60, 7, max_cases=150)
     assert cases == 150 and bad == 0
+
+
+def test_parallel_formulation_with_small_windows():
+    """windowBits 9..14 at levels 3..6 on inputs that slide the window many times: the phases of the GPU pipeline (links capped at
+    the window's match range, M for every position, macro steps with the DynWin window schedule, path, hole fixed point, serial
+    tail) give every symbol the oracle's deflate_medium tallies."""
+    cases = [("xml", silesia_member(9)[:120000]), ("mix", synthetic_mix(150000, 5)), ("nci", silesia_member(1)[:90000])]
+    for name, data in cases:
+        n = len(data)
+        for wbits, level in ((9, 6), (10, 4), (12, 3), (12, 6), (14, 5), (14, 6)):
+            a = np.zeros((n + 16) * 2, dtype=np.uint32)
+            b = np.zeros((n + 16) * 2, dtype=np.uint32)
+            na, nb, it = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+            assert H().hm_parse_parallel_w(data, n, level, wbits, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na), ctypes.byref(it)) == 0
+            assert H().hm_oracle_trace_w(data, n, level, wbits, 8, b.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(nb)) == 0
+            assert na.value == nb.value and (a[: na.value * 2] == b[: nb.value * 2]).all(), (name, wbits, level)

@@ -70,7 +70,7 @@ struct FullWin {
     ZB_HD uint32_t t0() const { return kT0; }
 };
 struct DynWin {
-    uint32_t w;
+    uint32_t w; // a power of two, 512 .. 32768 (windowBits 9 .. 15)
     ZB_HD uint32_t wsize() const { return w; }
     ZB_HD uint32_t maxdist() const { return w - kMinLookahead; }
     ZB_HD uint32_t t0() const { return 2 * w - kMinLookahead; }
@@ -206,8 +206,8 @@ struct Sym {
 // `stop` = first position handled by the tail: a chain that reaches a loop-top >= stop ends there
 // (the tail re-simulates from the last canonical node, so nothing is lost).
 // ---------------------------------------------------------------------------------------------
-template <class MA, class E>
-ZB_HD uint32_t macro_step(const MA &a, uint32_t p, const LevelParams &lp, uint32_t stop, E &&emit, uint32_t *nsym_out)
+template <class MA, class E, class WN = FullWin>
+ZB_HD uint32_t macro_step(const MA &a, uint32_t p, const LevelParams &lp, uint32_t stop, E &&emit, uint32_t *nsym_out, const WN wn = WN())
 {
     uint32_t nsym = 0;
     Match m = a.mlook(p);
@@ -216,18 +216,18 @@ ZB_HD uint32_t macro_step(const MA &a, uint32_t p, const LevelParams &lp, uint32
     if (m.len >= 4) { cur.len = m.len; cur.ms = m.start; } else { cur.len = 1; cur.ms = 0; }
     for (;;) {
         // loop-top at cur.ss with `cur` decided.  Look ahead (medium.rs:103-153).
-        uint32_t B = wbase(cur.ss);
+        uint32_t B = wbase_w(wn, cur.ss);
         PMatch next;
         next.len = 0;
         bool committed = false;
         uint32_t ns = cur.ss + cur.len;
-        if (!lp.early_exit && (ns - B) < kT0) {
+        if (!lp.early_exit && (ns - B) < wn.t0()) {
             Match nm = a.mlook(ns);
             next.ss = next.org = ns;
             if (nm.len >= 4) {
                 next.len = nm.len;
                 next.ms = nm.start;
-                committed = fizzle(a, B, cur, next);
+                committed = fizzle(a, B, cur, next, wn);
             } else {
                 next.len = 1;
                 next.ms = 0;

@@ -308,6 +308,15 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
         jb.tail_start = 0;
         exact = true;
     }
+    // ... and larger inputs run the parallel kernels with the window size as a parameter (round 2: the window schedule, the match
+    // range of the links and of the walks, fizzle_matches and the stale bytes behind the input all take it from jb.wsize; the host
+    // model checks the formulation against the oracle for windowBits 9..14, tests/test_hostmodel.py)
+    const bool par_win = wb_eff < 15 && !small_ok && !serial_win && level >= 3 && level <= 6 && strategy != 2 && strategy != 3 && dstart == 0;
+    if (par_win) {
+        jb.wsize = 1u << wb_eff;
+        jb.cinfo = (uint32_t)(wb_eff - 8);
+        exact = true;
+    }
     // level 0 does not depend on the window at all (stored.rs copies straight from the input); Z_HUFFMAN_ONLY only through the
     // stored-block rule (window base at flush time, k_block_hist); levels 1 and 2 emulate the window literally (zb_serial.h)
     if (wb_eff < 15 && (level == 0 || (strategy == 2 && level != 0) || serial_low)) {

@@ -463,7 +463,7 @@ struct InfBlock { uint64_t start_bit, out_off; uint32_t out_len, type, src_byte,
 struct InfPar {
     uint32_t ncand, nblocks, status, kind;
     uint64_t first_bit, total_out, end_bit;
-    uint32_t trailer_check, trailer_len, decode_err, pad;
+    uint32_t trailer_check, trailer_len, decode_err, all_kept; // all_kept: every dynamic block of the chain has its symbols in the arena
 };
 
 // stream header (inflate.rs:926-1010 Head .. :1222 HCrc): zlib 2 bytes, gzip 10 + optional fields
@@ -850,7 +850,7 @@ __global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const I
     if (par->status != PS_OK) return;
     BitSrc s{src, n};
     uint64_t pos = par->first_bit, out = 0;
-    uint32_t nb = 0;
+    uint32_t nb = 0, all_kept = 1;
     for (;;) {
         if (pos + 3 > n * 8 || nb >= kMaxBlocks) { par->status = PS_FALLBACK; return; }
         const uint32_t w = s.peek32(pos);
@@ -873,6 +873,7 @@ __global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const I
             if (f == 0xffffffffu || !cand[f].valid) { par->status = PS_FALLBACK; return; }
             b.out_len = cand[f].out_len;
             b.cand = f;
+            if (cand[f].nsyms == 0 && cand[f].out_len != 0) all_kept = 0;
             pos = cand[f].end_bit;
         } else { par->status = PS_FALLBACK; return; } // fixed-code blocks / invalid type: serial decoder
         out += b.out_len;
@@ -881,6 +882,7 @@ __global__ void k_inf_chain(const uint8_t *src, uint64_t n, InfPar *par, const I
     }
     par->nblocks = nb;
     par->total_out = out;
+    par->all_kept = all_kept;
     // trailer (inflate.rs:1398-1430, 1779-1795)
     const uint64_t tb = (pos + 7) >> 3;
     par->end_bit = tb * 8;
@@ -1065,6 +1067,130 @@ __global__ void __launch_bounds__(256) k_inf_resolve(InfPar *par, const InfBlock
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Output-tile replay (round 2).  With every block's symbols in the arena, the sequential part of inflate -- the LZ77 copies -- no
+// longer has to follow the block structure: k_inf_cum turns the symbol lengths of a block into output offsets, and k_inf_tiles
+// gives every 8 KiB tile of the OUTPUT its own warp, which finds the first symbol of its tile by binary search (block, then
+// symbol) and replays until the tile is full.  A copy whose source lies in front of the tile leaves a 16-bit marker (its distance
+// back from the tile start), exactly as the block-wise replay did for sources in front of the block; k_inf_tile_resolve chases
+// the markers with plain arithmetic (the tile of a position is position / 8192 -- no search).  8 warps per SM instead of the 2
+// the block-wise replay could keep busy.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTileOut = 8192;
+
+__global__ void __launch_bounds__(256) k_inf_cum(InfPar *par, const InfBlock *blocks, const InfCand *cand, const uint32_t *arena,
+                                                 uint32_t *cum, uint32_t slot_syms)
+{
+    __shared__ uint32_t s_part[256];
+    const uint32_t k = blockIdx.x, tid = threadIdx.x;
+    if (k >= par->nblocks) return;
+    const InfBlock b = blocks[k];
+    if (b.type != 2) return;
+    const uint32_t ns = cand[b.cand].nsyms;
+    const uint32_t *slot = arena + (size_t)b.cand * (slot_syms + 32u * kScanLaneCap);
+    uint32_t *c = cum + (size_t)b.cand * slot_syms;
+    const uint32_t per = (ns + 255) / 256, beg = tid * per, end = min(beg + per, ns);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; i++) { const uint32_t e = slot[i]; sum += (e >> 16) ? (e >> 16) : 1u; }
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < 256; i++) { const uint32_t t = s_part[i]; s_part[i] = run; run += t; }
+        if (run != b.out_len) atomicOr(&par->decode_err, 4u);
+    }
+    __syncthreads();
+    uint32_t run = s_part[tid];
+    for (uint32_t i = beg; i < end; i++) { const uint32_t e = slot[i]; c[i] = run; run += (e >> 16) ? (e >> 16) : 1u; }
+}
+
+__global__ void __launch_bounds__(32) k_inf_tiles(const uint8_t *src, InfPar *par, const InfBlock *blocks, const InfCand *cand,
+                                                  const uint32_t *arena, const uint32_t *cum, uint32_t slot_syms, uint16_t *tmp)
+{
+    __shared__ uint16_t tile[kTileOut];
+    __shared__ uint32_t sm_e[32], sm_c[32];
+    const uint32_t lane = threadIdx.x, nb = par->nblocks;
+    const uint64_t total = par->total_out, T0 = (uint64_t)blockIdx.x * kTileOut;
+    if (T0 >= total) return;
+    const uint64_t T1 = min(T0 + kTileOut, total);
+    // the block that holds T0: the last one whose out_off <= T0
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (blocks[mid].out_off <= T0) lo = mid; else hi = mid; }
+    uint32_t bi = lo;
+    uint64_t pos = T0;
+    bool bad = false;
+    while (pos < T1 && bi < nb) {
+        const InfBlock b = blocks[bi];
+        const uint64_t bend = b.out_off + b.out_len;
+        if (pos >= bend) { bi++; continue; }
+        const uint64_t upto = min(bend, T1);
+        if (b.type == 0) {
+            for (uint64_t i = pos + lane; i < upto; i += 32) tile[i - T0] = src[b.src_byte + (i - b.out_off)];
+            __syncwarp();
+            pos = upto;
+            continue;
+        }
+        const uint32_t ns = cand[b.cand].nsyms;
+        const uint32_t *slot = arena + (size_t)b.cand * (slot_syms + 32u * kScanLaneCap);
+        const uint32_t *c = cum + (size_t)b.cand * slot_syms;
+        const uint32_t rel = (uint32_t)(pos - b.out_off), rel_end = (uint32_t)(upto - b.out_off);
+        // the symbol that produces byte `rel`: the last one that starts at or before it
+        uint32_t slo = 0, shi = ns;
+        while (shi - slo > 1) { const uint32_t mid = (slo + shi) >> 1; if (c[mid] <= rel) slo = mid; else shi = mid; }
+        for (uint32_t s0 = slo; s0 < ns; s0 += 32) {
+            const uint32_t cnt = min(32u, ns - s0);
+            const uint32_t e = lane < cnt ? slot[s0 + lane] : 0u;
+            const uint32_t cs = lane < cnt ? c[s0 + lane] : 0xffffffffu;
+            if (__shfl_sync(0xffffffffu, cs, 0) >= rel_end) break; // this batch starts behind the tile (or the block's part of it)
+            sm_e[lane] = e;
+            sm_c[lane] = cs;
+            const uint32_t len = e >> 16;
+            // literals first: a literal is final wherever it is, and the copies of this batch only read in front of themselves
+            if (lane < cnt && len == 0 && cs >= rel && cs < rel_end) tile[b.out_off + cs - T0] = (uint16_t)e;
+            __syncwarp();
+            const uint32_t mm = __ballot_sync(0xffffffffu, lane < cnt && len != 0 && cs < rel_end && cs + len > rel);
+            for (uint32_t m = mm; m; m &= m - 1) {
+                const uint32_t i = __ffs(m) - 1;
+                const uint32_t ee = sm_e[i], L = ee >> 16, D = ee & 0xffffu;
+                const uint64_t G = b.out_off + sm_c[i]; // where the copy starts in the output
+                if ((uint64_t)D > G) bad = true;         // "invalid distance too far back"
+                for (uint32_t j = lane; j < L; j += 32) {
+                    const uint64_t g = G + j;
+                    if (g < pos || g >= upto) continue;
+                    const uint64_t sg = G + (D < L ? j % D : j) - D;
+                    tile[g - T0] = sg >= T0 ? tile[sg - T0] : (uint16_t)(0x8000u | (uint32_t)(T0 - sg - 1));
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+        pos = upto;
+    }
+    for (uint32_t i = lane; i < (uint32_t)(T1 - T0); i += 32) tmp[T0 + i] = tile[i];
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&par->decode_err, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_inf_tile_resolve(InfPar *par, const uint16_t *__restrict__ tmp, uint8_t *out)
+{
+    const uint64_t total = par->total_out;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4; i0 < total; i0 += (uint64_t)gridDim.x * 1024) {
+        uint32_t packed = 0;
+        for (uint32_t k = 0; k < 4 && i0 + k < total; k++) {
+            uint64_t i = i0 + k;
+            uint16_t v = tmp[i];
+            while (v & 0x8000u) {
+                const uint64_t t0 = i & ~(uint64_t)(kTileOut - 1), back = (uint64_t)(v & 0x7fffu) + 1;
+                if (back > t0) { atomicOr(&par->decode_err, 2u); v = 0; break; }
+                i = t0 - back;
+                v = tmp[i];
+            }
+            packed |= (uint32_t)(v & 0xffu) << (8 * k);
+        }
+        if (i0 + 4 <= total && ((reinterpret_cast<uintptr_t>(out) + i0) & 3) == 0) *reinterpret_cast<uint32_t *>(out + i0) = packed;
+        else for (uint32_t k = 0; k < 4 && i0 + k < total; k++) out[i0 + k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
 static const char *inf_msg(uint32_t e)
 {
     switch (e) {
@@ -1180,11 +1306,24 @@ int Engine::inflate(const void *src, size_t n, bool src_dev, void *dst, size_t d
                 uint16_t *dtmp;
                 if ((rc = reserve(4 /*S_M*/, (hpar.total_out + 64) * 2, &p)) != ZB_OK) return rc;
                 dtmp = static_cast<uint16_t *>(p);
-                CKI(cudaFuncSetAttribute(k_inf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
-                k_inf_decode<<<hpar.nblocks, 64, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp, dcand, darena, darena ? kSlotSyms : 0u);
                 const uint64_t quads = (hpar.total_out + 1023) / 1024;
-                k_inf_resolve<<<(unsigned)(quads < 148 * 16 ? (quads ? quads : 1) : 148 * 16), 256, 0, st>>>(dpar, dblk, dtmp, d_dst);
-                launches += 2;
+                const unsigned rgrid = (unsigned)(quads < 148 * 16 ? (quads ? quads : 1) : 148 * 16);
+                uint32_t *dcum = nullptr;
+                if (darena && hpar.all_kept && !getenv("ZB_INFLATE_BLOCKWISE") &&
+                    reserve(37 /* inflate cumulative offsets */, (size_t)hpar.ncand * kSlotSyms * 4, &p) == ZB_OK)
+                    dcum = static_cast<uint32_t *>(p);
+                if (dcum) {
+                    // every block's symbols are in the arena: replay by 8 KiB output tiles
+                    k_inf_cum<<<hpar.nblocks, 256, 0, st>>>(dpar, dblk, dcand, darena, dcum, kSlotSyms);
+                    k_inf_tiles<<<(unsigned)((hpar.total_out + kTileOut - 1) / kTileOut), 32, 0, st>>>(d_src, dpar, dblk, dcand, darena, dcum, kSlotSyms, dtmp);
+                    k_inf_tile_resolve<<<rgrid, 256, 0, st>>>(dpar, dtmp, d_dst);
+                    launches += 3;
+                } else {
+                    CKI(cudaFuncSetAttribute(k_inf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
+                    k_inf_decode<<<hpar.nblocks, 64, sizeof(DecodeShared), st>>>(d_src, n, dpar, dblk, dtmp, dcand, darena, darena ? kSlotSyms : 0u);
+                    k_inf_resolve<<<rgrid, 256, 0, st>>>(dpar, dblk, dtmp, d_dst);
+                    launches += 2;
+                }
                 CKI(cudaMemcpyAsync(&hpar, dpar, sizeof(InfPar), cudaMemcpyDeviceToHost, st));
                 CKI(cudaStreamSynchronize(st));
                 CKI(cudaGetLastError());

@@ -33,12 +33,13 @@ struct GAcc { // global memory, absolute coordinates
     const uint16_t *L;
     const uint32_t *holes;
     const uint32_t *M;
+    uint32_t w = kWSize; // window size (windowBits 9..15)
     __device__ __forceinline__ uint32_t byte(uint32_t y) const
     {
         // bytes beyond the input are what the reference's window buffer still holds there
         while (y >= N) {
-            if (y < 2 * kWSize) return 0;
-            y -= kWSize;
+            if (y < 2 * w) return 0;
+            y -= w;
         }
         return data[y];
     }
@@ -106,7 +107,7 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     uint8_t *sd = smem + kKeys * 2 + kLinkTile * 2;                      // kLinkTile + 16 bytes of data
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : kMaxDist;
+    const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
     const uint32_t ts = blockIdx.x * kLinkTile;
     const uint32_t te = min(ts + kLinkTile, N);
     const uint32_t tv = N >= need ? min(te, N - need + 1) : ts; // positions with enough bytes to hash
@@ -155,7 +156,7 @@ __device__ __forceinline__ void links_fix_body(const JobBufs &jb)
     constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
     const uint32_t x = blockIdx.x * 256 + threadIdx.x;
     if (x >= jb.N || jb.L[x] != kFirstFlag) return;
-    const uint32_t tile = x / kLinkTile, cap = kRoll ? kLinkCapSlow : kMaxDist;
+    const uint32_t tile = x / kLinkTile, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
     uint32_t d = 0;
     if (tile > 0) {
         const uint8_t *q = jb.in + x;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
     const uint32_t te = min(ts + kMatchTile, jb.N);
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t span = te - ws, tid = threadIdx.x;
+    const uint32_t md = jb.wsize - kMinLookahead; // the window's match range (kMaxDist for 32 KiB)
     {
         const uint4 *ls = reinterpret_cast<const uint4 *>(jb.L + ws);
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
             const uint32_t t = i - d;
             if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
             const uint32_t d2 = sL[t];
-            sL[i] = (uint16_t)((d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2);
+            sL[i] = (uint16_t)((d2 == 0 || d + d2 > md) ? 0u : d + d2);
             ch = 1;
         }
         if (!__syncthreads_or(ch)) break;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
             const uint32_t t = i - d;
             if ((sh[t >> 5] >> (t & 31)) & 1u) {
                 const uint32_t d2 = sL[t];
-                d = (d2 == 0 || d + d2 > kMaxDist) ? 0u : d + d2;
+                d = (d2 == 0 || d + d2 > md) ? 0u : d + d2;
             }
         }
         jb.Lr[ws + i] = (uint16_t)d;
@@ -311,6 +313,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(sdata);
     const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(sL);
     const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
+    const uint32_t md = jb.wsize - kMinLookahead; // the window's match range (kMaxDist for 32 KiB)
     const uint32_t lane = threadIdx.x & 31;
     uint32_t *const Mout = jb.M + ws;
     uint16_t *const RDout = jb.SK + ws;
@@ -457,7 +460,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                             //  * the nearest candidate now sits exactly at the window limit (only a first candidate may, medium.rs:76).
                             const uint32_t rdo = RDout[xr];
                             const bool on_budget = rdo != 0xffffu && (rdo & 0x8000u);
-                            const uint32_t lo = rdo == 0xffffu ? (xr > kMaxDist ? xr - kMaxDist : 0u) : xr - (rdo & 0x7fffu);
+                            const uint32_t lo = rdo == 0xffffu ? (xr > md ? xr - md : 0u) : xr - (rdo & 0x7fffu);
                             bool redo = DiffMaps::any(dm.del, dm.pdel, lo, xr);
                             if (!redo) {
                                 if (on_budget) redo = DiffMaps::any(dm.add, dm.padd, lo, xr);
@@ -466,7 +469,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                                     if (m) { const uint32_t h2 = xr - (m & 0xffffu); redo = (dm.add[h2 >> 5] >> (h2 & 31)) & 1u; }
                                 }
                             }
-                            if (!redo) redo = sld_u16(lbase + 2 * xr) == kMaxDist;
+                            if (!redo) redo = sld_u16(lbase + 2 * xr) == md;
                             skip = !redo;
                         }
                     }
@@ -474,7 +477,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                         // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
                         // absolute position 0 is never a candidate
                         const uint32_t d0 = sld_u16(lbase + 2 * xr);
-                        lowr = xr > kMaxDist ? xr - kMaxDist : 0;
+                        lowr = xr > md ? xr - md : 0;
                         if (ws == 0 && lowr == 0) lowr = 1;
                         if (xr < lowr + d0) { // no candidate in the window
                             if (filt && Mout[xr] != 0) jb.mchg[(ws + xr) >> 6] = 1;
@@ -482,7 +485,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                         }
                         else {
                             cr = xr - d0;
-                            if (lowr + kMaxDist == xr) lowr++; // after the first candidate the limit tightens by one
+                            if (lowr + md == xr) lowr++; // after the first candidate the limit tightens by one
                             best = 2; chain = budget; res = 0;
                             fbase = dbase + 2;
                             xb = sld_u8(fbase + xr);
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
             if ((jb.bucket_map[h >> 5] >> (h & 31)) & 1u) {
                 const uint32_t rd = jb.SK[x];
-                const uint32_t lo = rd == 0xffffu ? (x > kMaxDist ? x - kMaxDist : 0u) : x - (rd & 0x7fffu);
+                const uint32_t lo = rd == 0xffffu ? (x > jb.wsize - kMinLookahead ? x - (jb.wsize - kMinLookahead) : 0u) : x - (rd & 0x7fffu);
                 for (uint32_t b = lo >> 10; b <= (x >> 10); b++) hit |= jb.hcoarse[b];
             }
         }
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
             if (!((sbm[h >> 5] >> (h & 31)) & 1u)) continue;
         }
         if (x + kMSafe <= N) {
-            Match m = lm_walk(a, x, 0xffffffffu, lp);
+            Match m = jb.wsize == kWSize ? lm_walk(a, x, 0xffffffffu, lp) : lm_walk(a, x, 0xffffffffu, lp, DynWin{jb.wsize});
             if (m.len) v = (m.len << 16) | (x - m.start);
         }
         if (jb.use_bucket_map && jb.M[x] != v) jb.mchg[x >> 6] = 1;
@@ -688,13 +691,16 @@ __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
         for (uint32_t b = b0; b <= b1; b++) chg = chg || jb.mchg[b];
         if (!chg) return;
     }
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
     const uint32_t long_len = 16 * jb.lp.lazy;
     uint32_t ns = 0;
     bool is_long = false;
-    const uint32_t np = macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+    auto see = [&](const Sym &s) {
         if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
-    }, &ns);
+    };
+    // the 32 KiB window is compiled in; smaller windows (windowBits 9..14) take the same step with the window as a parameter
+    const uint32_t np = jb.wsize == kWSize ? macro_step(a, p, jb.lp, jb.tail_start, see, &ns)
+                                           : macro_step(a, p, jb.lp, jb.tail_start, see, &ns, DynWin{jb.wsize});
     const uint32_t delta = np - p;
     if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
     jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
@@ -912,11 +918,11 @@ __global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
     const uint32_t list = t / kLongPerSub, slot = t % kLongPerSub;
     if (list >= nlists || slot >= jb.long_cnt[list]) return;
     const uint32_t p = jb.long_list[(size_t)list * kLongPerSub + slot];
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
     uint32_t ns = 0;
     const uint32_t long_len = 16 * jb.lp.lazy;
     uint32_t *hn = jb.holes_new;
-    macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) {
+    auto mark = [&](const Sym &s) {
         if (s.dist && (uint32_t)s.lc + 3u > long_len) {
             // interior positions pos+1 .. pos+len-2 are never inserted (medium.rs:251-261)
             uint32_t y0 = s.pos + 1, y1 = s.pos + s.lc + 3u - 1; // [y0, y1)
@@ -928,7 +934,9 @@ __global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
                 y0 += n;
             }
         }
-    }, &ns);
+    };
+    if (jb.wsize == kWSize) macro_step(a, p, jb.lp, jb.tail_start, mark, &ns);
+    else macro_step(a, p, jb.lp, jb.tail_start, mark, &ns, DynWin{jb.wsize});
 }
 
 __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
@@ -937,10 +945,12 @@ __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
     if (p >= jb.tail_start) return;
     const uint32_t idx = jb.symidx[p];
     if (!idx) return;
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
     uint32_t k = jb.tile_symbase[p / kPathTile] + idx - 1, ns = 0;
     Sym *syms = jb.syms;
-    macro_step(a, p, jb.lp, jb.tail_start, [&](const Sym &s) { syms[k++] = s; }, &ns);
+    auto put = [&](const Sym &s) { syms[k++] = s; };
+    if (jb.wsize == kWSize) macro_step(a, p, jb.lp, jb.tail_start, put, &ns);
+    else macro_step(a, p, jb.lp, jb.tail_start, put, &ns, DynWin{jb.wsize});
 }
 
 // holes := holes_new; report change and the match tiles whose window saw it
@@ -1011,7 +1021,7 @@ __global__ void __launch_bounds__(32) k_tail(JobBufs jb)
 {
     __shared__ uint32_t ins[1024];
     if (threadIdx.x != 0) return;
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M};
+    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
     const uint32_t p0 = max(jb.info->tail_entry, jb.start); // without a path (short input) the tail starts at the first input byte
     const uint32_t n_mid = jb.info->n_mid_syms;
     uint32_t k = 0;
@@ -1080,7 +1090,7 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
                 Bf = base_at(jb.syms[li].pos, jb.N);     // Z_RLE tallies a symbol at its own loop-top
             } else if (jb.slow_mode) {
                 Bf = base_at(jb.syms[li].pos + 1, jb.N); // the symbol is tallied at the loop-top behind its first byte (slow.rs:84-136)
-            } else Bf = li < n_mid ? wbase(jb.syms[li].pos) : jb.sym_base[li - n_mid];
+            } else Bf = li < n_mid ? wbase_w(DynWin{jb.wsize}, jb.syms[li].pos) : jb.sym_base[li - n_mid];
         }
         bd.have_window = start >= Bf;
     }

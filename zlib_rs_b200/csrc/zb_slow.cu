@@ -45,7 +45,10 @@ __device__ __forceinline__ uint32_t qld_u32u(uint32_t a) // unaligned
 
 constexpr uint32_t kSlowSafe = 1024; // nodes this close to the end of the input take the generic slow_step()
 constexpr uint32_t kSlowBatch = 8;
-constexpr uint32_t kSlowBurst = 8;
+#ifndef ZB_SLOW_BURST
+#define ZB_SLOW_BURST 8
+#endif
+constexpr uint32_t kSlowBurst = ZB_SLOW_BURST;
 enum { SS_IDLE = 0, SS_START = 1, SS_WALK = 2, SS_PEND = 3, SS_DONE = 4 };
 
 // The lanes of a warp run the macro steps of different fresh loop-tops.  A lane is IDLE (needs a node), at the
@@ -137,7 +140,154 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
     // only filter, a handful of integer instructions per candidate; a lane leaves it at its first event and the event is re-derived
     // from registers), then -- each only when enough lanes wait for it -- the starts of new searches, the full compares, the refill.
     // The search semantics are those of the round-1 kernel; the schedule is the one measured on k_match (zb_kernels.cu).
+    if (sp.slow) {
+        // Level 9 (rolling hash, longest_match_slow): the round-1 schedule -- one phase per pass, START and PEND before the walk, the
+        // walk step with the byte filter and the 3/4-byte pre-check.  The round-2 schedule below was measured slower here (133 vs
+        // 160..176 ms for the corpus: the re-rooting loops of START / PEND dominate and do not mix well with the unrolled burst),
+        // and faster at levels 7 / 8 (11.3 -> 7.3 ms, 29.5 -> 19.3 ms).
+        constexpr uint32_t kBurst9 = 4;
+    for (;;) {
+        const uint32_t m_idle = __ballot_sync(0xffffffffu, state == SS_IDLE);
+        const uint32_t m_start = __ballot_sync(0xffffffffu, state == SS_START);
+        const uint32_t m_walk = __ballot_sync(0xffffffffu, state == SS_WALK);
+        const uint32_t m_pend = __ballot_sync(0xffffffffu, state == SS_PEND);
+        if ((m_idle | m_start | m_walk | m_pend) == 0) break;
+        if (m_idle && (__popc(m_idle) >= (int)kSlowBatch || (m_start | m_walk | m_pend) == 0)) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(m_idle) - 1;
+            if (lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (state == SS_IDLE) {
+                const uint32_t x = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (x >= te) state = SS_DONE;
+                else if (x + kSlowSafe > N) {
+                    p = x;
+                    const SlowStep s = slow_step(acc, x, N, sp);
+                    write_node(s.next, s.nlit, s.len, s.dist);
+                } else {
+                    p = q = x; l = 0; ms = 0;
+                    B = base_at(x, N);
+                    state = SS_START;
+                }
+            }
+            continue;
+        }
+        // START/PEND lanes do not wait for the walkers when few lanes are busy at all
+        const uint32_t thr = min(kSlowBatch, max(1u, (uint32_t)__popc(m_start | m_walk | m_pend) / 4u));
+        if (m_start && (__popc(m_start) >= (int)thr || m_walk == 0)) {
+            if (state == SS_START) {
+                // slow.rs:56-82 preconditions (lookahead >= 262 here)
+                bool search = l < sp.lazy;
+                uint32_t hh = 0;
+                if (search) {
+                    const uint32_t d = qld_u16(ladj + 2 * q);
+                    hh = q - d;
+                    search = d != 0 && d <= kMaxDist && hh > B;
+                }
+                if (!search) finish_search(2, ms, false);
+                else {
+                    best = l ? l : 2;
+                    mstart = ms;
+                    chain = best >= sp.good ? sp.chain >> 2 : sp.chain;
+                    limit_base = (q - B > kMaxDist) ? q - kMaxDist : B;
+                    limit = limit_base;
+                    mo = 0;
+                    cur = hh;
+                    bool ended = false;
+                    if (sp.slow && best >= 3) {
+                        for (uint32_t i = 0; i + 3 <= best; i++) {
+                            const uint32_t pos = head_at(q + i + 1);
+                            if (pos < cur) { mo = i + 1; cur = pos; }
+                        }
+                        limit = limit_base + mo;
+                        ended = cur <= limit;
+                    }
+                    if (ended) finish_search(best, mstart, true);
+                    else {
+                        xb = qld_u8(dadj + q + best);
+                        xw0 = qld_u32u(dadj + q);
+                        state = SS_WALK;
+                    }
+                }
+            }
+            continue;
+        }
+        if (m_pend && (__popc(m_pend) >= (int)thr || m_walk == 0)) {
+            if (state == SS_PEND) {
+                uint32_t clen = 0, len;
+                const uint32_t pa = dadj + q, pb = dadj + cand;
+                for (;;) {
+                    const uint32_t d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
+                    const uint32_t d1 = qld_u32u(pa + clen + 4) ^ qld_u32u(pb + clen + 4);
+                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                    break;
+                }
+                if (len > kMaxMatch) len = kMaxMatch;
+                state = SS_WALK;
+                if (len > best) {
+                    mstart = cand;
+                    best = len;
+                    if (best >= sp.nice) finish_search(best, mstart, true);
+                    else {
+                        xb = qld_u8(dadj + q + best);
+                        if (sp.slow && len > 3 && mstart + len < q) {
+                            // longest_match.rs:281-333
+                            cur = cand;
+                            mo = 0;
+                            uint32_t next_pos = cur;
+                            bool ended = false;
+                            for (uint32_t i = 0; i + 3 <= len; i++) {
+                                const uint32_t y = cur + i;
+                                const uint32_t d = qld_u16(ladj + 2 * y);
+                                const uint32_t pos = (d && y - d > B) ? y - d : B;
+                                if (pos < next_pos) {
+                                    if (pos <= limit_base + i) { ended = true; break; }
+                                    next_pos = pos;
+                                    mo = i;
+                                }
+                            }
+                            if (!ended) {
+                                cur = next_pos;
+                                const uint32_t pos = head_at(q + len - 4);
+                                if (pos < cur) {
+                                    mo = len - 4;
+                                    if (pos <= limit_base + mo) ended = true;
+                                    else cur = pos;
+                                }
+                            }
+                            if (ended) finish_search(best, mstart, true);
+                            else limit = limit_base + mo;
+                        } else next_in_chain();
+                    }
+                } else next_in_chain();
+            }
+            continue;
+        }
+#pragma unroll
+        for (uint32_t burst = 0; burst < kBurst9; burst++) {
+            if (state == SS_WALK) {
+                if (cur >= q) finish_search(best, mstart, true);
+                else {
+                    const uint32_t c = cur - mo;
+                    bool pass = qld_u8(dadj + c + best) == xb;
+                    if (pass) {
+                        const uint32_t dw = qld_u32u(dadj + c) ^ xw0;
+                        pass = (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+                    }
+                    if (pass) { cand = c; state = SS_PEND; }
+                    else next_in_chain();
+                }
+            }
+        }
+    }
+        return;
+    }
     uint32_t fadj = 0; // dadj + best - mo: the filter byte of candidate chain position `cur` sits at fadj + cur
+    auto first_ok = [&](uint32_t c) -> bool {
+        const uint32_t dw = qld_u32u(dadj + c) ^ xw0;
+        return (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+    };
     for (;;) {
         if (state == SS_WALK) {
             if (chain > kSlowBurst) {
@@ -201,6 +351,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                     if (ended || cur >= q) finish_search(best, mstart, true);
                     else {
                         xb = qld_u8(dadj + q + best);
+                        xw0 = qld_u32u(dadj + q);
                         fadj = dadj + best - mo;
                         state = SS_WALK;
                     }
