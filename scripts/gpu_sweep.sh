@@ -3,5 +3,7 @@
 mkdir -p gpurun_out
 for so in zlib_rs_b200/variants/libz_b200_*.so; do
   name=$(basename $so .so); name=${name#libz_b200_}
+  mt=""; [[ $name =~ _mt([0-9]+) ]] && mt=${BASH_REMATCH[1]}   # a variant named *_mt768 runs its dense passes with 768 threads per CTA
+  if [ -n "$mt" ]; then export ZB_MTHREADS=$mt; else unset ZB_MTHREADS; fi
   echo "== $name $(ZB_LIB_PATH=$PWD/$so timeout 120 python scripts/variant_probe.py ${2:-6} 2>&1 | tail -1)"
 done 2>&1 | tee gpurun_out/sweep_${1:-s}.log

@@ -159,6 +159,8 @@ struct PMatch {
     uint32_t org;  // orgstart
 };
 
+ZB_HD uint32_t min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
 // fizzle_matches (medium.rs:264-331).  B = window base in force.  Returns true when committed.
 template <class A, class WN = FullWin>
 ZB_HD bool fizzle(const A &a, uint32_t B, PMatch &current, PMatch &next, const WN wn = WN())
@@ -170,18 +172,28 @@ ZB_HD bool fizzle(const A &a, uint32_t B, PMatch &current, PMatch &next, const W
     uint32_t nsw = next.ss - B;
     uint32_t limit = B + (nsw > wn.maxdist() ? nsw - wn.maxdist() : 0);
     PMatch c = current, n = next;
+    // The reference's loop (medium.rs:299-318) moves the next match one byte to the left while
+    //   n.ms > B, window[n.ms-1] == window[n.ss-1], c.len >= 1, n.ss > limit, n.len < 256, n.ms - B > 1
+    // all hold.  All but the byte test are counters: the loop runs min(K, equal bytes to the left) times with
+    uint32_t K = c.len;
+    K = min_u32(K, n.ss > limit ? n.ss - limit : 0u);
+    K = min_u32(K, n.len < 256u ? 256u - n.len : 0u);
+    K = min_u32(K, n.ms > B + 1u ? n.ms - B - 1u : 0u);
     uint32_t changed = 0;
-    for (;;) {
-        // `m.next() == orig.next()` over reversed window[..n.ms] / window[..n.ss] (medium.rs:299-303)
-        if (n.ms <= B) break;
-        if (a.byte(n.ms - 1) != a.byte(n.ss - 1)) break;
-        if (c.len < 1) break;
-        if (n.ss <= limit) break;
-        if (n.len >= 256) break;
-        if (n.ms - B <= 1) break;
-        n.ss--; n.ms--; n.len++; c.len--;
-        changed++;
+    while (changed < K) { // eight bytes per round: the sixteen loads are independent of each other
+        const uint32_t m = K - changed < 8u ? K - changed : 8u;
+        uint32_t diff = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t j = 0; j < 8u; j++)
+            if (j < m && a.byte(n.ms - 1u - changed - j) != a.byte(n.ss - 1u - changed - j)) diff |= 1u << j;
+        uint32_t e = 0;
+        while (e < m && !((diff >> e) & 1u)) e++;
+        changed += e;
+        if (e < m) break;
     }
+    n.ss -= changed; n.ms -= changed; n.len += changed; c.len -= changed;
     if (changed == 0) return false;
     if (c.len <= 1 && n.len != 2) {
         n.org++;

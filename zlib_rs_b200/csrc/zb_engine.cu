@@ -30,7 +30,9 @@ __global__ void k_skip(JobBufs);
 __global__ void k_nxt(JobBufs);
 __global__ void k_path_tiles(JobBufs);
 __global__ void k_path_chain(JobBufs, uint32_t, uint32_t);
-__global__ void k_path_mark(JobBufs);
+__global__ void k_path_groups(JobBufs, uint32_t, uint32_t, uint4 *, uint32_t *);
+__global__ void k_path_chain2(JobBufs, uint32_t, uint32_t, const uint4 *, uint32_t *, uint32_t *);
+__global__ void k_path_mark(JobBufs, const uint32_t *, const uint32_t *);
 __global__ void k_emit(JobBufs);
 __global__ void k_holes(JobBufs, uint32_t);
 __global__ void k_holes_cmp(JobBufs, uint32_t, uint32_t);
@@ -56,10 +58,11 @@ __global__ void k_links_dict_ghost_apply(JobBufs, const uint32_t *);
 
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
-constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64;
+constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64 + 2048;
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = kChainChunkTiles * kPathHead * 8;
+constexpr uint32_t kChain2MaxSmem = 200 * 1024; // two-level chain: group heads + transfer functions of the groups
 constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2 + 35824 + 16; // head + prev tables of one stream + the input ring (level 2)
 constexpr uint32_t kSerialSmemQuick = 65536 * 2 + 65536 + 16;         // head + 64 KiB input ring (level 1)
 
@@ -81,7 +84,7 @@ int Engine::init(int dev)
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(upload_tables());
-    CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
+    CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes + (ZB_MATCH_CTX ? ZB_CTX * 16 * 1024 : 0)));
     CK(cudaFuncSetAttribute(k_skip, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkipSmemBytes));
     CK(cudaFuncSetAttribute(k_links2_std, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
     CK(cudaFuncSetAttribute(k_links2_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinks2SmemBytes));
@@ -89,6 +92,8 @@ int Engine::init(int dev)
     CK(cudaFuncSetAttribute(k_path_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, kPathSmemBytes));
     CK(cudaFuncSetAttribute(k_path_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes));
+    CK(cudaFuncSetAttribute(k_path_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2MaxSmem));
+    CK(cudaFuncSetAttribute(k_path_chain2, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2MaxSmem));
     CK(cudaFuncSetAttribute(k_serial_low, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerialSmemBytes));
     CK(cudaMallocHost(&h_info, sizeof(JobInfo)));
     CK(cudaMalloc(&d_info, sizeof(JobInfo)));
@@ -160,7 +165,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_MCHG, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_MCHG, S_GFN, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -251,10 +256,31 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     RES(S_TDIRTY, (size_t)nmt + 16, tile_dirty, uint8_t *)
     RES(S_SYMS, ((size_t)N + 64) * sizeof(Sym), syms, Sym *)
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
-    RES(S_BMAP, 8192, bucket_map, uint32_t *)
+    RES(S_BMAP, (size_t)nmt * 8192, bucket_map, uint32_t *) // one 65536-bit map per 32 KiB tile
     RES(S_LR, npad * 2, Lr, uint16_t *)
     RES(S_LLAST, (size_t)nmt * 65536 * 2, link_last, uint16_t *)
     RES(S_CSTATE, (size_t)(npt + 1) * 16, chain_state, uint4 *)
+    // two-level path chain: groups of ~sqrt(tiles) path tiles (k_path_groups / k_path_chain2)
+    uint32_t chainG = 16;
+    while ((uint64_t)chainG * chainG < npt) chainG += 8;
+    const uint32_t chain_groups = (npt + chainG - 1) / chainG;
+    const uint32_t chain2_smem = chainG * kPathHead * 8 + chain_groups * kPathHead * 16 + chainG * 8;
+    const bool chain2 = chain2_smem <= kChain2MaxSmem;
+    if ((rc = reserve(S_GFN, (size_t)chain_groups * kPathHead * 16 + ((size_t)npt + 4) * 4, &p)) != ZB_OK) return rc;
+    uint4 *d_gfn = static_cast<uint4 *>(p);
+    uint32_t *d_mark_cnt = reinterpret_cast<uint32_t *>(d_gfn + (size_t)chain_groups * kPathHead); // k_path_mark's work list
+    uint32_t *d_mark_list = d_mark_cnt + 4;
+    auto launch_chain = [&](uint32_t first_tile) {
+        if (chain2) {
+            k_path_groups<<<chain_groups, 1024, chainG * kPathHead * 8, st>>>(jb, npt, chainG, d_gfn, d_mark_cnt);
+            k_path_chain2<<<chain_groups, 1024, chain2_smem, st>>>(jb, npt, chainG, d_gfn, d_mark_list, d_mark_cnt);
+            launches++; // one more than the single-CTA walk the callers count
+        } else k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt, first_tile);
+    };
+    auto launch_mark = [&](uint32_t grid) { // with the two-level chain the tiles to mark come as a device list; any grid is correct
+        if (chain2) k_path_mark<<<grid < npt ? grid : npt, 1024, kPathSmemBytes, st>>>(jb, d_mark_list, d_mark_cnt);
+        else k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb, nullptr, nullptr);
+    };
     uint32_t *d_lists;
     const uint32_t max_list = N / 512 + 2;
     if ((rc = reserve(S_LISTS, ((size_t)max_list + npt + nmt + 8) * 4, &p)) != ZB_OK) return rc;
@@ -411,8 +437,8 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     if (profile) phase_ms[11] = phase_ms[1];
                     pbegin();
                     k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
-                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt, 0);
-                    k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    launch_chain(0);
+                    launch_mark(npt);
                     pend(3, 3);
                     pbegin();
                     k_emit_slow<<<(N + 255) / 256, 256, 0, st>>>(jb);
@@ -436,7 +462,7 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     // later passes cut the dirty tiles into enough pieces for about four CTAs per SM, because a sparse pass is
                     // bounded by its slowest piece, not by throughput.
                     uint32_t mthreads = 1024;
-                    if (iters == 1) jb.match_sub = 4096;
+                    if (iters == 1) jb.match_sub = ZB_MATCH_CTX ? 8192 : 4096; // context schedule: one CTA of 1024 threads per SM
                     else if (n_dirty <= 2) { jb.match_sub = 512; mthreads = 256; }
                     else {
                         const uint64_t per_cta = (uint64_t)n_dirty * kMatchTile / (4 * 148);
@@ -447,6 +473,9 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                         if (e_sub && n_dirty > 9) jb.match_sub = (uint32_t)atoi(e_sub);
                         if (e_thr && n_dirty > 9) mthreads = (uint32_t)atoi(e_thr);
                     }
+#ifdef ZB_MATCH_MAXT
+                    if (mthreads > ZB_MATCH_MAXT) mthreads = ZB_MATCH_MAXT; // experiment builds with a smaller launch bound
+#endif
                     uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     uint32_t n_ptiles = npt, first_ptile = 0;
                     jb.match_list = nullptr;
@@ -491,7 +520,8 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     }
                     // the dirty-bucket map and the changed-hole bitmaps are only staged from the second iteration on
                     const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 +
-                                           (iters > 1 ? ((kWSize + jb.match_sub) / 32 + 1) * 4 * 4 + 8192 : 64);
+                                           (iters > 1 ? ((kWSize + jb.match_sub) / 32 + 1) * 4 * 4 + 8192 : 64) +
+                                           (ZB_MATCH_CTX && !jb.lp.early_exit ? ZB_CTX * 16 * mthreads : 0); // walk contexts
                     jb.use_bucket_map = iters > 1;
                     pbegin();
                     k_match<<<nsub, mthreads, msmem, st>>>(jb);
@@ -501,9 +531,9 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     k_nxt<<<n_ptiles * (kPathTile / 1024), 1024, 0, st>>>(jb);
                     pend(2, 1);
                     pbegin();
-                    k_path_tiles<<<npt, 1024, kPathSmemBytes, st>>>(jb);
-                    k_path_chain<<<1, 1024, kChainSmemBytes, st>>>(jb, npt, first_ptile);
-                    k_path_mark<<<npt, 1024, kPathSmemBytes, st>>>(jb);
+                    k_path_tiles<<<n_ptiles, 1024, kPathSmemBytes, st>>>(jb); // jb.nxt_list: the tiles whose nxt may have changed
+                    launch_chain(first_ptile);
+                    launch_mark(iters == 1 ? npt : 2 * n_ptiles + 16);
                     pend(3, 3);
                     pbegin();
                     k_holes<<<(nlists * kLongPerSub + 255) / 256, 256, 0, st>>>(jb, nlists);

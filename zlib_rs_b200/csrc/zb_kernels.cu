@@ -87,9 +87,9 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte
 // k_links2 / k_links_fix: L[x] = distance to the previous position with the same hash (hash_calc.rs:40-59), i.e. the
 // reference's head/prev chains as if every position were inserted (k_skip bridges the holes later).  No warm-up replay of the
 // window before a tile and no redundant hashing: a CTA handles one 32 KiB tile on its own:
-//   A. all threads hash the tile's positions once into a shared key array;
-//   B. warp w owns the keys with key % 32 == w and replays their insertions in position order against the shared head
-//      table (32 positions per step, __match_any_sync orders equal keys inside a step);
+//   A. the tile's positions are grouped by key % 32 (a stable partition in shared memory: count, scan, scatter);
+//   B. warp w replays the insertions of group w in position order against the shared head table (32 positions per step,
+//      __match_any_sync orders equal keys inside a step) -- every warp touches only its own 1/32 of the positions;
 //   C. the head table (last occurrence of every key in the tile) goes to global memory; a position that is the first of
 //      its key in the tile is flagged and k_links_fix links it to the last occurrence in the PREVIOUS tile (a link
 //      never reaches further: tile >= max distance).
@@ -103,8 +103,10 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
     uint16_t *head = reinterpret_cast<uint16_t *>(smem);                 // kKeys entries: 1 + position in the tile
-    uint16_t *keys = reinterpret_cast<uint16_t *>(smem + kKeys * 2);     // kLinkTile entries
+    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + kKeys * 2);    // kLinkTile entries: the tile's positions grouped by key % 32
     uint8_t *sd = smem + kKeys * 2 + kLinkTile * 2;                      // kLinkTile + 16 bytes of data
+    uint16_t *run = reinterpret_cast<uint16_t *>(smem + kKeys * 2 + kLinkTile * 2 + kLinkTile + 64); // [32 chunks][32 classes]
+    __shared__ uint16_t c_base[32], c_total[32];
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
@@ -112,36 +114,72 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     const uint32_t te = min(ts + kLinkTile, N);
     const uint32_t tv = N >= need ? min(te, N - need + 1) : ts; // positions with enough bytes to hash
     for (uint32_t i = tid; i < kKeys / 2; i += 1024) reinterpret_cast<uint32_t *>(head)[i] = 0;
+    run[tid] = 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(jb.in + ts); // zero padded behind N
         uint4 *dst = reinterpret_cast<uint4 *>(sd);
         for (uint32_t i = tid; i < (te - ts + 16 + 15) / 16; i += 1024) dst[i] = src[i];
     }
     __syncthreads();
-    for (uint32_t i = tid; i < te - ts; i += 1024) {
-        uint32_t k;
-        if (kRoll) k = hash_roll3(sd[i], sd[i + 1], sd[i + 2]);
-        else k = hash_u32(lds_u32(words, i));
-        keys[i] = (uint16_t)k;
+    const uint32_t nv = tv > ts ? tv - ts : 0;
+    auto key_of = [&](uint32_t i) -> uint32_t { return kRoll ? hash_roll3(sd[i], sd[i + 1], sd[i + 2]) : hash_u32(lds_u32(words, i)); };
+    // A. stable partition of the positions by class = key % 32 (warp w takes the 1024 positions of chunk w): count, scan, scatter
+    uint16_t *myrun = run + warp * 32;
+    for (uint32_t b = 0; b < 32; b++) {
+        const uint32_t i = warp * 1024 + b * 32 + lane;
+        const uint32_t c = i < nv ? (key_of(i) & 31u) : 32u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        if (c < 32u && (peers & ((1u << lane) - 1u)) == 0) myrun[c] += (uint16_t)__popc(peers);
+        __syncwarp();
     }
     __syncthreads();
-    const uint32_t nv = tv > ts ? tv - ts : 0;
-    for (uint32_t base = 0; base < nv; base += 32) {
-        const uint32_t i = base + lane;
-        const uint32_t key = i < nv ? keys[i] : 0u;
-        const bool mine = i < nv && (key & 31u) == warp;
-        const uint32_t m = __ballot_sync(0xffffffffu, mine);
-        if (m == 0) continue;
-        if (mine) {
-            const uint32_t peers = __match_any_sync(m, key);
-            const uint32_t lower = peers & ((1u << lane) - 1u);
-            uint32_t pred = lower ? base + (31 - __clz(lower)) + 1 : head[key]; // 1 + position, 0 = none in this tile
-            uint32_t d = pred ? i + 1 - pred : kFirstFlag;
-            if (pred && d > cap) d = 0;
-            jb.L[ts + i] = (uint16_t)d;
-            if ((peers >> lane) == 1u) head[key] = (uint16_t)(i + 1);
+    if (warp == 0) { // lane = class
+        uint32_t tot = 0;
+        for (uint32_t w = 0; w < 32; w++) { const uint32_t t = run[w * 32 + lane]; run[w * 32 + lane] = (uint16_t)tot; tot += t; }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+        const uint32_t base = incl - tot;
+        for (uint32_t w = 0; w < 32; w++) run[w * 32 + lane] += (uint16_t)base;
+        c_base[lane] = (uint16_t)base;
+        c_total[lane] = (uint16_t)tot;
+    }
+    __syncthreads();
+    for (uint32_t b = 0; b < 32; b++) {
+        const uint32_t i = warp * 1024 + b * 32 + lane;
+        const uint32_t c = i < nv ? (key_of(i) & 31u) : 32u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t lower = peers & ((1u << lane) - 1u);
+        if (c < 32u) {
+            const uint32_t at = myrun[c];
+            lists[at + __popc(lower)] = (uint16_t)i;
         }
         __syncwarp();
+        if (c < 32u && lower == 0) myrun[c] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // B. warp w replays the insertions of class w in position order against the shared head table, 32 per step
+    //    (__match_any_sync orders equal keys inside a step)
+    {
+        const uint32_t lb = c_base[warp], ln = c_total[warp];
+        for (uint32_t k = 0; k < ln; k += 32) {
+            const bool mine = k + lane < ln;
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const uint32_t i = lists[lb + k + lane];
+                const uint32_t key = key_of(i);
+                const uint32_t peers = __match_any_sync(m, key);
+                const uint32_t lower = peers & ((1u << lane) - 1u);
+                const uint32_t pi = __shfl_sync(m, i, lower ? 31 - __clz(lower) : lane);
+                const uint32_t pred = lower ? pi + 1 : head[key]; // 1 + position, 0 = none in this tile
+                uint32_t d = pred ? i + 1 - pred : kFirstFlag;
+                if (pred && d > cap) d = 0;
+                jb.L[ts + i] = (uint16_t)d;
+                if ((peers >> lane) == 1u) head[key] = (uint16_t)(i + 1);
+            }
+            __syncwarp();
+        }
     }
     for (uint32_t x = tv + tid; x < te; x += 1024) jb.L[x] = 0; // positions without enough input are never hashed
     __syncthreads();
@@ -260,6 +298,13 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 #ifndef ZB_CMP_BURST
 #define ZB_CMP_BURST 4
 #endif
+#ifndef ZB_SECOND_LOOK
+#define ZB_SECOND_LOOK 1
+#endif
+#ifndef ZB_COOP_CMP
+#define ZB_COOP_CMP 0 // most lanes with a long compare for which the warp would finish them together; measured (r2p): 12 costs
+                      // 0.26 ms, 32 costs 1.7 ms over the twelve passes -- off
+#endif
 constexpr uint32_t kBatch = ZB_T_IDLE;         // idle lanes that trigger a refill
 constexpr uint32_t kBatchCmp = ZB_T_CMP;       // pending lanes that trigger a compare burst
 constexpr uint32_t kWalkBurst = ZB_WALK_BURST; // walk steps between two schedule checks
@@ -330,32 +375,58 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
 #ifdef ZB_QUICK16
     uint32_t xw0 = 0, xw1 = 0, xw2 = 0, xw3 = 0; // first 16 bytes of x: a filter hit is compared against them at once
 #endif
+    uint32_t xw4 = 0;    // the four bytes of x that end at index `best` (index 0..3 while best == 2)
     uint32_t state = LS_IDLE;
+    // A filter hit is looked at a second time before it costs a full compare: a longer match must reproduce all of x[0..best], so
+    // also the four bytes ending at index `best` (the first three while best == 2: a match of exactly three bytes still counts).
+    // One candidate in ten passes the one-byte filter; most of those fail here (cf. the word pre-checks, longest_match.rs:198-234).
+    auto second_look = [&]() -> bool {
+#if ZB_SECOND_LOOK
+        const uint32_t w = sld_u32u((best >= 3u ? fbase - 3u : dbase) + cr) ^ xw4;
+        return (best >= 3u ? w : (w & 0x00ffffffu)) == 0u;
+#else
+        return true;
+#endif
+    };
+    auto load_xw4 = [&]() { xw4 = sld_u32u((best >= 3u ? fbase - 3u : dbase) + xr); };
     for (;;) {
         // ---- walk burst
         if (state == LS_WALK) {
             if (chain > kWalkBurst) {
-                // exits carry no extra state: what happened is re-derived from fb / dn / cr after the loop
-                uint32_t fb;
+                // exits carry no extra state: what happened is re-derived from dn / cr after the loop (the filter byte is loaded
+                // again).  Inside the burst the candidate is kept relative to the lowest admissible one, so that the range test is
+                // one compare against the link: ten instructions per candidate.
+                uint32_t crl = cr - lowr;
+                uint32_t fl = fbase + lowr, ll = lbase + 2 * lowr;
+                asm volatile("" : "+r"(fl), "+r"(ll)); // keep the two bases as they are (no re-association into the loop)
                 bool more = false;
 #pragma unroll
                 for (uint32_t k = 0; k < kWalkBurst; k++) {
-                    fb = sld_u8(fbase + cr);
-                    dn = sld_u16(lbase + 2 * cr);
-                    if (fb == xb) break;
+                    const uint32_t fbk = sld_u8(fl + crl);
+                    dn = sld_u16(ll + 2 * crl);
+                    if (fbk == xb) break;
                     chain--;
-                    if (cr < lowr + dn) break; // the chain ends or leaves the window
-                    cr -= dn;
+                    if ((int32_t)crl < (int32_t)dn) break; // the chain ends or leaves the window (crl is -1 for a first candidate at the very limit)
+                    crl -= dn;
                     if (k + 1 == kWalkBurst) more = true;
                 }
+                cr = crl + lowr;
+                const uint32_t fb = more ? ~xb : sld_u8(fl + crl);
                 if (!more) {
-                    if (fb == xb) { state = kHitState; clen = 0; }
+                    if (fb == xb) {
+                        if (second_look()) { state = kHitState; clen = 0; }
+                        else { // cannot be longer than `best`: a filter miss after all (chain >= 2 here: the burst started above kWalkBurst)
+                            chain--;
+                            if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
+                            else cr -= dn;
+                        }
+                    }
                     else { rd = 0xffffu; state = LS_FIN; }
                 }
             } else {
                 const uint32_t fb = sld_u8(fbase + cr);
                 dn = sld_u16(lbase + 2 * cr);
-                if (fb == xb) { state = kHitState; clen = 0; }
+                if (fb == xb && second_look()) { state = kHitState; clen = 0; }
                 else if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; } // budget
                 else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
                 else cr -= dn;
@@ -377,7 +448,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     best = len;
                     res = (len << 16) | (xr - cr);
                     if (best >= nice) { rd = xr - cr; state = LS_FIN; }
-                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
+                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); load_xw4(); }
                 }
                 if (state == LS_WALK) { // on to the next candidate
                     if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; }
@@ -391,10 +462,10 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
         const uint32_t m_walk = __ballot_sync(0xffffffffu, state == LS_WALK);
         const uint32_t m_pend = __ballot_sync(0xffffffffu, state == LS_PEND);
         if (m_pend && (__popc(m_pend) >= (int)kBatchCmp || m_walk == 0)) {
+            uint32_t len = 0;
+            bool resolved = false;
             if (state == LS_PEND) {
                 uint32_t pa = dbase + xr + clen, pb = dbase + cr + clen;
-                uint32_t len = 0;
-                bool resolved = false;
 #pragma unroll 1
                 for (uint32_t k = 0; k < kCmpBurst; k++) {
                     uint32_t a0, a1, b0, b1;
@@ -408,20 +479,46 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     }
                     clen += 8; pa += 8; pb += 8;
                 }
-                if (resolved) {
-                    if (len > kMaxMatch) len = kMaxMatch;
-                    state = LS_WALK;
-                    if (len > best) {
-                        best = len;
-                        res = (len << 16) | (xr - cr);
-                        if (best >= nice) { rd = xr - cr; state = LS_FIN; }
-                        else { fbase = dbase + best; xb = sld_u8(fbase + xr); }
+            }
+#if ZB_COOP_CMP
+            {
+                // A compare that survived a burst is a long one (repetitive data: up to 258 bytes, 33 steps).  While few lanes
+                // hold one, the warp finishes them one after the other, 8 bytes per lane = 256 bytes per step; the lane's serial
+                // loop would keep the other lanes of the warp waiting for up to 29 more steps.
+                uint32_t m_long = __ballot_sync(0xffffffffu, state == LS_PEND && !resolved);
+                if (m_long && __popc(m_long) <= ZB_COOP_CMP) {
+                    while (m_long) {
+                        const uint32_t src = __ffs(m_long) - 1;
+                        m_long &= m_long - 1;
+                        const uint32_t cl0 = __shfl_sync(0xffffffffu, clen, src);
+                        const uint32_t pa0 = __shfl_sync(0xffffffffu, dbase + xr + clen, src) + 8u * lane;
+                        const uint32_t pb0 = __shfl_sync(0xffffffffu, dbase + cr + clen, src) + 8u * lane;
+                        uint32_t a0, a1, b0, b1;
+                        sld_u64u(pa0, a0, a1);
+                        sld_u64u(pb0, b0, b1);
+                        const uint32_t d0 = a0 ^ b0, d1 = a1 ^ b1;
+                        const uint32_t mm = __ballot_sync(0xffffffffu, (d0 | d1) != 0);
+                        const uint32_t first = mm ? __ffs(mm) - 1 : 0u;
+                        const uint32_t mine = d0 ? ((__ffs(d0) - 1) >> 3) : 4u + ((__ffs(d1) - 1) >> 3);
+                        const uint32_t bo = __shfl_sync(0xffffffffu, mine, first);
+                        if (lane == src) { len = mm ? cl0 + 8u * first + bo : cl0 + 256u; resolved = true; } // cl0 >= 32: 256 more bytes pass 258
                     }
-                    if (state == LS_WALK) { // on to the next candidate
-                        if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; }
-                        else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
-                        else cr -= dn;
-                    }
+                }
+            }
+#endif
+            if (resolved) {
+                if (len > kMaxMatch) len = kMaxMatch;
+                state = LS_WALK;
+                if (len > best) {
+                    best = len;
+                    res = (len << 16) | (xr - cr);
+                    if (best >= nice) { rd = xr - cr; state = LS_FIN; }
+                    else { fbase = dbase + best; xb = sld_u8(fbase + xr); load_xw4(); }
+                }
+                if (state == LS_WALK) { // on to the next candidate
+                    if (--chain == 0) { rd = (xr - cr) | 0x8000u; state = LS_FIN; }
+                    else if (cr < lowr + dn) { rd = 0xffffu; state = LS_FIN; }
+                    else cr -= dn;
                 }
             }
         }
@@ -489,6 +586,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                             best = 2; chain = budget; res = 0;
                             fbase = dbase + 2;
                             xb = sld_u8(fbase + xr);
+                            load_xw4();
 #ifdef ZB_QUICK16
                             {
                                 const uint32_t pa = dbase + xr, al = pa & ~3u, sh = (pa & 3u) * 8u;
@@ -506,7 +604,224 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
     }
 }
 
-__global__ void __launch_bounds__(1024) k_match(JobBufs jb)
+// ------------------------------------------------------------------------------------------------
+// match_tile_ctx: the same walks as match_tile_fast under a different schedule.  A lane owns kCtx walk contexts that live in
+// shared memory (16 bytes each: position, candidate, best length, budget, result, compare progress, window limit) instead of one
+// in registers.  The warp runs ROUNDS of one kind: a walk round (every lane that has a walking context takes it through a burst
+// of candidates), a compare round (every lane that has a context waiting for a compare runs a burst of 8-byte steps) or a
+// refill round (lanes with a free slot fetch the next positions).  Because a lane almost always has a context of the kind the
+// round needs, the rounds run with nearly full warps, where the register version's lanes sit out the phases they are not in
+// (measured there: 12 active lanes in the walk burst, 6 in the compare loop, 4 in the code after a compare).
+// ------------------------------------------------------------------------------------------------
+#ifndef ZB_T_FILL
+#define ZB_T_FILL 16
+#endif
+constexpr uint32_t kCtx = ZB_CTX;
+constexpr uint32_t kFillLanes = ZB_T_FILL; // lanes with a free slot that trigger a refill round
+
+__device__ __forceinline__ uint4 slds_u4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ssts_u4(uint32_t a, const uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void match_tile_ctx(const JobBufs &jb, const uint8_t *sdata, const uint16_t *sL, const uint32_t *sbm,
+                                               const DiffMaps dm, uint32_t ws, uint32_t te, uint32_t *s_next, uint4 *ctx)
+{
+    const bool filt = jb.use_bucket_map != 0;
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(sdata);
+    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(sL);
+    const uint32_t N = jb.N, nice = jb.lp.nice, budget = jb.lp.chain;
+    const uint32_t md = jb.wsize - kMinLookahead; // the window's match range (kMaxDist for 32 KiB)
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t *const Mout = jb.M + ws;
+    uint16_t *const RDout = jb.SK + ws;
+    // slot j of this lane: cbase + j * 512.  Context words: x = xr | cr << 16, y = best | chain << 16, z = result, w = clen | lowr << 16
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(ctx) + ((threadIdx.x >> 5) * kCtx * 32u + lane) * 16u;
+    uint32_t mW = 0, mP = 0; // slots with a walking context / with a context waiting for its compare
+    bool exhausted = false;  // the piece has no more positions to hand out
+    auto finish = [&](uint32_t xr, uint32_t res, uint32_t rd) {
+        if (filt && Mout[xr] != res) jb.mchg[(ws + xr) >> 6] = 1; // k_nxt redoes only the macro steps that read a changed M
+        Mout[xr] = res;
+        RDout[xr] = (uint16_t)rd;
+    };
+    for (;;) {
+        const uint32_t fr = ~(mW | mP) & ((1u << kCtx) - 1u);
+        const uint32_t bW = __ballot_sync(0xffffffffu, mW != 0);
+        const uint32_t bP = __ballot_sync(0xffffffffu, mP != 0);
+        const uint32_t bF = exhausted ? 0u : __ballot_sync(0xffffffffu, fr != 0);
+        if ((bW | bP | bF) == 0) break;
+        const int nW = __popc(bW), nP = __popc(bP), nF = __popc(bF);
+        if (nF && (nF >= (int)kFillLanes || (bW | bP) == 0)) {
+            // ---- refill round: warp-aggregated fetch of consecutive positions
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(bF) - 1;
+            if (lane == leader) base = atomicAdd(s_next, (uint32_t)nF);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (uint32_t)nF >= te;
+            if (fr) {
+                const uint32_t x = base + __popc(bF & ((1u << lane) - 1u));
+                if (x >= te) {}
+                else if (x + kMSafe > N) { jb.M[x] = 0; }
+                else {
+                    const uint32_t xr = x - ws;
+                    bool skip = false;
+                    if (filt) { // only buckets in which a hole changed can have a different M ...
+                        const uint32_t h = hash_u32(sld_u32u(dbase + xr));
+                        skip = !((sbm[h >> 5] >> (h & 31)) & 1u);
+                        if (!skip) {
+                            // ... and only if the change can alter the previous walk (see match_tile_fast)
+                            const uint32_t rdo = RDout[xr];
+                            const bool on_budget = rdo != 0xffffu && (rdo & 0x8000u);
+                            const uint32_t lo = rdo == 0xffffu ? (xr > md ? xr - md : 0u) : xr - (rdo & 0x7fffu);
+                            bool redo = DiffMaps::any(dm.del, dm.pdel, lo, xr);
+                            if (!redo) {
+                                if (on_budget) redo = DiffMaps::any(dm.add, dm.padd, lo, xr);
+                                else {
+                                    const uint32_t m = Mout[xr];
+                                    if (m) { const uint32_t h2 = xr - (m & 0xffffu); redo = (dm.add[h2 >> 5] >> (h2 & 31)) & 1u; }
+                                }
+                            }
+                            if (!redo) redo = sld_u16(lbase + 2 * xr) == md;
+                            skip = !redo;
+                        }
+                    }
+                    if (!skip) {
+                        // first candidate may be kMaxDist away, later ones kMaxDist-1 (medium.rs:76, longest_match.rs:44,84);
+                        // absolute position 0 is never a candidate
+                        const uint32_t d0 = sld_u16(lbase + 2 * xr);
+                        uint32_t lowr = xr > md ? xr - md : 0;
+                        if (ws == 0 && lowr == 0) lowr = 1;
+                        if (xr < lowr + d0) { // no candidate in the window
+                            if (filt && Mout[xr] != 0) jb.mchg[(ws + xr) >> 6] = 1;
+                            Mout[xr] = 0; RDout[xr] = 0xffffu;
+                        } else {
+                            const uint32_t cr = xr - d0;
+                            if (lowr + md == xr) lowr++; // after the first candidate the limit tightens by one
+                            const uint32_t j = __ffs(fr) - 1;
+                            ssts_u4(cbase + j * 512u, make_uint4(xr | (cr << 16), 2u | (budget << 16), 0u, lowr << 16));
+                            mW |= 1u << j;
+                        }
+                    }
+                }
+            }
+        } else if (nW >= nP) {
+            // ---- walk round
+            if (mW) {
+                const uint32_t j = __ffs(mW) - 1, ca = cbase + j * 512u;
+                uint4 c = slds_u4(ca);
+                const uint32_t xr = c.x & 0xffffu, best = c.y & 0xffffu, lowr = c.w >> 16;
+                uint32_t cr = c.x >> 16, chain = c.y >> 16, dn;
+                uint32_t fl = dbase + best + lowr, ll = lbase + 2 * lowr;
+                const uint32_t xb = sld_u8(dbase + best + xr);
+                uint32_t crl = cr - lowr;
+                asm volatile("" : "+r"(fl), "+r"(ll)); // keep the two bases as they are (no re-association into the loop)
+                uint32_t out = 0; // 0: still walking, 1: filter hit at cr, 2: chain ended, 3: budget
+                if (chain > kWalkBurst) {
+                    bool more = false;
+#pragma unroll
+                    for (uint32_t k = 0; k < kWalkBurst; k++) {
+                        const uint32_t fbk = sld_u8(fl + crl);
+                        dn = sld_u16(ll + 2 * crl);
+                        if (fbk == xb) break;
+                        chain--;
+                        if ((int32_t)crl < (int32_t)dn) break; // the chain ends or leaves the window (crl is -1 for a first candidate at the very limit)
+                        crl -= dn;
+                        if (k + 1 == kWalkBurst) more = true;
+                    }
+                    if (!more) out = sld_u8(fl + crl) == xb ? 1u : 2u;
+                } else {
+#pragma unroll 1
+                    for (uint32_t k = 0; k < kWalkBurst; k++) {
+                        const uint32_t fbk = sld_u8(fl + crl);
+                        dn = sld_u16(ll + 2 * crl);
+                        if (fbk == xb) { out = 1; break; }
+                        if (--chain == 0) { out = 3; break; }
+                        if ((int32_t)crl < (int32_t)dn) { out = 2; break; }
+                        crl -= dn;
+                    }
+                }
+                cr = crl + lowr;
+                if (out == 1) {
+                    // second look (see match_tile_fast): the four bytes ending at index `best` (three while best == 2)
+                    const uint32_t b4 = best >= 3u ? dbase + best - 3u : dbase;
+                    const uint32_t w = sld_u32u(b4 + cr) ^ sld_u32u(b4 + xr);
+                    if ((best >= 3u ? w : (w & 0x00ffffffu)) == 0u) { // compare it
+                        c.x = xr | (cr << 16); c.y = best | (chain << 16); c.w = lowr << 16;
+                        ssts_u4(ca, c);
+                        mW &= ~(1u << j); mP |= 1u << j;
+                    } else { // a filter miss after all
+                        if (--chain == 0) out = 3;
+                        else if ((int32_t)crl < (int32_t)dn) out = 2;
+                        else { cr -= dn; out = 0; }
+                    }
+                }
+                if (out == 0) { c.x = xr | (cr << 16); c.y = best | (chain << 16); ssts_u4(ca, c); }
+                else if (out >= 2) { finish(xr, c.z, out == 2 ? 0xffffu : ((xr - cr) | 0x8000u)); mW &= ~(1u << j); }
+            }
+        } else {
+            // ---- compare round
+            if (mP) {
+                const uint32_t j = __ffs(mP) - 1, ca = cbase + j * 512u;
+                uint4 c = slds_u4(ca);
+                const uint32_t xr = c.x & 0xffffu, cr = c.x >> 16, lowr = c.w >> 16;
+                uint32_t best = c.y & 0xffffu, chain = c.y >> 16, clen = c.w & 0xffffu;
+                uint32_t pa = dbase + xr + clen, pb = dbase + cr + clen;
+                uint32_t len = 0;
+                bool resolved = false;
+#pragma unroll 1
+                for (uint32_t k = 0; k < kCmpBurst; k++) {
+                    uint32_t a0, a1, b0, b1;
+                    sld_u64u(pa, a0, a1);
+                    sld_u64u(pb, b0, b1);
+                    const uint32_t d0 = a0 ^ b0, d1 = a1 ^ b1;
+                    if ((d0 | d1) != 0 || clen + 8 >= kMaxMatch) {
+                        len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                        resolved = true;
+                        break;
+                    }
+                    clen += 8; pa += 8; pb += 8;
+                }
+                if (!resolved) { c.w = clen | (lowr << 16); ssts_u4(ca, c); }
+                else {
+                    if (len > kMaxMatch) len = kMaxMatch;
+                    uint32_t out = 0;
+                    if (len > best) {
+                        best = len;
+                        c.z = (len << 16) | (xr - cr);
+                        if (best >= nice) out = 1;
+                    }
+                    uint32_t ncr = cr;
+                    if (out == 0) { // on to the next candidate
+                        const uint32_t dn = sld_u16(lbase + 2 * cr);
+                        if (--chain == 0) out = 3;
+                        else if (cr < lowr + dn) out = 2;
+                        else ncr = cr - dn;
+                    }
+                    mP &= ~(1u << j);
+                    if (out == 0) {
+                        c.x = xr | (ncr << 16); c.y = best | (chain << 16); c.w = lowr << 16;
+                        ssts_u4(ca, c);
+                        mW |= 1u << j;
+                    } else finish(xr, c.z, out == 1 ? xr - cr : out == 2 ? 0xffffu : ((xr - cr) | 0x8000u));
+                }
+            }
+        }
+    }
+}
+
+#ifndef ZB_MATCH_MAXT
+#define ZB_MATCH_MAXT 1024 // two CTAs of 1024 threads per SM: 32 registers
+#endif
+#ifndef ZB_MATCH_MINB
+#define ZB_MATCH_MINB (ZB_MATCH_CTX ? 1 : 2)
+#endif
+__global__ void __launch_bounds__(ZB_MATCH_MAXT, ZB_MATCH_MINB) k_match(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_next;
@@ -531,19 +846,23 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     if (jb.use_bucket_map) {
-        // nothing to do unless a position of this piece hashes into a bucket with a changed hole
+        // nothing to do unless a position of this piece hashes into a bucket with a changed hole.  The bucket maps are kept per
+        // 32 KiB tile: the window of a piece lies in its own tile and the one before it, so a hole that changed anywhere else
+        // (in the second iteration: nearly every bucket, somewhere in the input) does not make this piece's positions candidates.
+        const uint32_t mt = ts / kMatchTile;
+        const uint32_t *bm1 = jb.bucket_map + (size_t)mt * 2048, *bm0 = mt ? bm1 - 2048 : bm1;
         int hit = 0;
         for (uint32_t x = ts + tid; x < te; x += nthr) {
             const uint8_t *q = jb.in + x; // zero padded behind N
             const uint32_t h = hash_u32((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
-            if ((jb.bucket_map[h >> 5] >> (h & 31)) & 1u) {
+            if (((bm0[h >> 5] | bm1[h >> 5]) >> (h & 31)) & 1u) {
                 const uint32_t rd = jb.SK[x];
                 const uint32_t lo = rd == 0xffffu ? (x > jb.wsize - kMinLookahead ? x - (jb.wsize - kMinLookahead) : 0u) : x - (rd & 0x7fffu);
                 for (uint32_t b = lo >> 10; b <= (x >> 10); b++) hit |= jb.hcoarse[b];
             }
         }
         if (!__syncthreads_or(hit)) return;
-        for (uint32_t i = tid; i < 2048; i += nthr) sbm[i] = jb.bucket_map[i];
+        for (uint32_t i = tid; i < 2048; i += nthr) sbm[i] = bm0[i] | bm1[i];
         // changed-hole bitmaps of [ws, te) and their exclusive prefix counts: every thread owns a run of consecutive words
         const uint32_t nwd = (te - ws + 31) / 32;
         const uint32_t per = (nwd + 1 + nthr - 1) / nthr;
@@ -626,7 +945,13 @@ __global__ void __launch_bounds__(1024) k_match(JobBufs jb)
     const long long t_2 = clock64();
     const LevelParams lp = jb.lp;
     if (!lp.early_exit) {
+#if ZB_MATCH_CTX
+        // the walk contexts follow the staged window (and the filter maps of the later passes)
+        uint4 *ctx = reinterpret_cast<uint4 *>(smem + data_bytes + (kWSize + sub) * 2 + (jb.use_bucket_map ? wmax * 16 + 8192 : 64));
+        match_tile_ctx(jb, sdata, sL, sbm, DiffMaps{sdel, pdel, sadd, padd}, ws, te, &s_next, ctx);
+#else
         match_tile_fast(jb, sdata, sL, sbm, DiffMaps{sdel, pdel, sadd, padd}, ws, te, &s_next);
+#endif
         __syncthreads();
         if (tid == 0) {
             const long long t_3 = clock64();
@@ -675,7 +1000,9 @@ __device__ __forceinline__ bool path_tile_dirty(const JobBufs &jb, uint32_t pt)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
 {
-    // 16 CTAs per path tile, one position per thread; CTAs of clean tiles exit at once
+    // 16 CTAs per path tile, one position per thread; CTAs of clean tiles exit at once.  (Staging M and the nearby data bytes of a
+    // CTA's 1024 positions in shared memory was measured slower, 2.1 instead of 1.4 ms over the twelve passes: the threads that
+    // have work are few in the later passes and the loads of the first pass are not what bounds it.)
     constexpr uint32_t per = kPathTile / 1024;
     const uint32_t tile = jb.nxt_list ? jb.nxt_list[blockIdx.x / per] : blockIdx.x / per;
     if (!path_tile_dirty(jb, tile)) return;
@@ -693,17 +1020,22 @@ __global__ void __launch_bounds__(1024) k_nxt(JobBufs jb)
     }
     GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
     const uint32_t long_len = 16 * jb.lp.lazy;
-    uint32_t ns = 0;
-    bool is_long = false;
+    uint32_t ns = 0, nlong = 0, lpos = 0, llen = 0;
     auto see = [&](const Sym &s) {
-        if (s.dist && (uint32_t)s.lc + 3u > long_len) is_long = true; // leaves holes (medium.rs:251-261)
+        if (s.dist && (uint32_t)s.lc + 3u > long_len) { nlong++; lpos = s.pos; llen = s.lc + 3u; } // leaves holes (medium.rs:251-261)
     };
     // the 32 KiB window is compiled in; smaller windows (windowBits 9..14) take the same step with the window as a parameter
     const uint32_t np = jb.wsize == kWSize ? macro_step(a, p, jb.lp, jb.tail_start, see, &ns)
                                            : macro_step(a, p, jb.lp, jb.tail_start, see, &ns, DynWin{jb.wsize});
     const uint32_t delta = np - p;
     if (delta > 0xffffu || ns > 0xffu || delta == 0) atomicOr(&jb.info->error, 1u);
-    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (is_long ? kNxtLong : 0u) | (np >= jb.tail_start ? kNxtTail : 0u);
+    // A long match is never fizzled away (fizzle_matches stops growing the next match at 256, medium.rs:299-318), so it is the
+    // last symbol of its macro step, and with 16 * max_lazy = 256 it is 257 or 258 bytes long: k_holes rebuilds it from the
+    // step's end and one flag.  (Levels 3/4 have one-symbol steps: the match is the step.)  Checked here, relied on there.
+    if (nlong && (nlong != 1 || lpos + llen != np || (jb.lp.early_exit ? lpos != p : (llen != 257u && llen != 258u))))
+        atomicOr(&jb.info->error, 16u);
+    jb.nxt[p] = (delta & 0xffffu) | ((ns & 0xffu) << 16) | (nlong ? kNxtLong : 0u) | (llen == 258u ? kNxtLong258 : 0u) |
+                (np >= jb.tail_start ? kNxtTail : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -752,8 +1084,9 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
     uint32_t *nx = reinterpret_cast<uint32_t *>(smem);
     uint32_t *ex = nx + kPathTile;
     uint32_t *cn = ex + kPathTile;
-    const uint32_t tbeg = blockIdx.x * kPathTile;
-    if (!path_tile_dirty(jb, blockIdx.x)) return; // nxt of this tile is unchanged: exits stay valid
+    const uint32_t tile = jb.nxt_list ? jb.nxt_list[blockIdx.x] : blockIdx.x; // later iterations: the tiles k_nxt touched
+    const uint32_t tbeg = tile * kPathTile;
+    if (!path_tile_dirty(jb, tile)) return; // nxt of this tile is unchanged: exits stay valid
     path_load(jb, tbeg, nx);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -777,7 +1110,7 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
             jb.pexit[p] = xa;
             jb.pcnt[p] = cn[i];
         }
-        if (i < kPathHead) jb.phead[(size_t)blockIdx.x * kPathHead + i] = make_uint2(xa, cn[i]);
+        if (i < kPathHead) jb.phead[(size_t)tile * kPathHead + i] = make_uint2(xa, cn[i]);
     }
 }
 
@@ -839,64 +1172,186 @@ __global__ void __launch_bounds__(1024) k_path_chain(JobBufs jb, uint32_t ntiles
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-level form of the walk above (the default; the single-CTA walk stays for inputs with more tiles than the group tables
+// hold).  The tiles are cut into groups of G ~ sqrt(tiles).  k_path_groups: one CTA per group stages the group's head table and
+// kPathHead threads walk the group, one from each head entry of its first tile -> the group's transfer function on those
+// entries.  k_path_chain2: one CTA per group composes the transfer functions of the groups before it (a group entered elsewhere
+// than at a head entry of its first tile is walked tile by tile -- rare), then walks its own tiles and writes what the
+// serial walk wrote.  Critical path: G + tiles/G + G shared-memory steps instead of `tiles`.
+// ------------------------------------------------------------------------------------------------
+struct ChainState { uint32_t e, base, done, tail; };
+
+template <bool OUT>
+__device__ __forceinline__ void chain_walk_group(const JobBufs &jb, const uint2 *hd, uint32_t t0, uint32_t nt, ChainState &s,
+                                                 uint32_t *c_entry, uint32_t *c_base)
+{
+    for (uint32_t k = 0; k < nt; k++) {
+        const uint32_t tbeg = (t0 + k) * kPathTile, tend = tbeg + kPathTile;
+        if (OUT) c_base[k] = s.base;
+        if (s.done || s.e >= tend || s.e >= jb.tail_start) { if (OUT) c_entry[k] = 0xffffffffu; continue; }
+        if (OUT) c_entry[k] = s.e;
+        uint32_t x, c;
+        if (s.e - tbeg < kPathHead) { const uint2 v = hd[k * kPathHead + (s.e - tbeg)]; x = v.x; c = v.y; }
+        else { x = jb.pexit[s.e]; c = jb.pcnt[s.e]; }
+        s.base += c;
+        if (x & kStuck) { s.tail = x & ~kStuck; s.done = 1; }
+        else s.e = x;
+    }
+}
+
+__device__ __forceinline__ void chain_stage_heads(const JobBufs &jb, uint2 *hd, uint32_t t0, uint32_t nt)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(jb.phead + (size_t)t0 * kPathHead);
+    uint4 *dst = reinterpret_cast<uint4 *>(hd);
+    for (uint32_t i = threadIdx.x; i < nt * kPathHead / 2; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(1024) k_path_groups(JobBufs jb, uint32_t ntiles, uint32_t G, uint4 *gfn, uint32_t *mark_cnt)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *mark_cnt = 0;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint2 *hd = reinterpret_cast<uint2 *>(smem);
+    const uint32_t t0 = blockIdx.x * G, nt = min(G, ntiles - t0);
+    chain_stage_heads(jb, hd, t0, nt);
+    __syncthreads();
+    if (threadIdx.x < kPathHead) {
+        ChainState s{t0 * kPathTile + threadIdx.x, 0u, 0u, 0u};
+        chain_walk_group<false>(jb, hd, t0, nt, s, nullptr, nullptr);
+        gfn[(size_t)blockIdx.x * kPathHead + threadIdx.x] = make_uint4(s.e, s.base, s.done, s.tail);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_path_chain2(JobBufs jb, uint32_t ntiles, uint32_t G, const uint4 *gfn, uint32_t *mark_list,
+                                                        uint32_t *mark_cnt)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint2 *hd = reinterpret_cast<uint2 *>(smem);                           // G x kPathHead
+    uint4 *sg = reinterpret_cast<uint4 *>(smem + (size_t)G * kPathHead * 8); // transfer functions of the groups before this one
+    uint32_t *c_entry = reinterpret_cast<uint32_t *>(sg + (size_t)blockIdx.x * kPathHead), *c_base = c_entry + G;
+    __shared__ ChainState s_st;
+    __shared__ uint32_t s_j;
+    const uint32_t g = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < g * kPathHead; i += blockDim.x) sg[i] = gfn[i];
+    if (threadIdx.x == 0) { s_st = ChainState{jb.start, 0u, jb.tail_start == 0 ? 1u : 0u, jb.start}; s_j = 0; }
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) {
+            ChainState s = s_st;
+            uint32_t j = s_j;
+            for (; j < g; j++) {
+                const uint32_t gbeg = j * G * kPathTile;
+                if (s.done || s.e >= jb.tail_start || s.e - gbeg >= G * kPathTile) continue; // nothing of the path starts in group j
+                if (s.e - gbeg >= kPathHead) break;                   // entered off the head of its first tile: walk it
+                const uint4 f = sg[j * kPathHead + (s.e - gbeg)];
+                s.e = f.x; s.base += f.y;
+                if (f.z) { s.done = 1; s.tail = f.w; }
+            }
+            s_st = s; s_j = j;
+        }
+        __syncthreads();
+        const uint32_t j = s_j;
+        if (j >= g) break;
+        chain_stage_heads(jb, hd, j * G, G); // j < g: a full group
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ChainState s = s_st;
+            chain_walk_group<false>(jb, hd, j * G, G, s, nullptr, nullptr);
+            s_st = s; s_j = j + 1;
+        }
+        __syncthreads();
+    }
+    const uint32_t t0 = g * G, nt = min(G, ntiles - t0);
+    chain_stage_heads(jb, hd, t0, nt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ChainState s = s_st;
+        chain_walk_group<true>(jb, hd, t0, nt, s, c_entry, c_base);
+        if (g == gridDim.x - 1) {
+            uint32_t tail_entry = s.tail;
+            if (!s.done) { tail_entry = s.e; if (s.e < jb.tail_start) atomicOr(&jb.info->error, 2u); }
+            jb.info->tail_entry = tail_entry;
+            jb.info->n_mid_syms = s.base;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
+        const uint32_t t = t0 + k;
+        jb.tile_symbase[t] = c_base[k];
+        const bool mn = (jb.tile_entry[t] != c_entry[k]) || path_tile_dirty(jb, t);
+        jb.mark_needed[t] = mn;
+        jb.tile_entry[t] = c_entry[k];
+        if (mn) mark_list[atomicAdd(mark_cnt, 1u)] = t; // k_path_mark's work list (k_path_groups zeroed the counter)
+    }
+}
+
 // Mark the path nodes of a tile: symidx[p] = 1 + index of the node's first symbol.
-__global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb)
+// `list` (k_path_chain2): the tiles whose entry or nxt changed; the CTAs stride over it, so any grid size is correct.
+__global__ void __launch_bounds__(1024) k_path_mark(JobBufs jb, const uint32_t *list, const uint32_t *list_cnt)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *nx = reinterpret_cast<uint32_t *>(smem);
     uint32_t *ex = nx + kPathTile;
     uint32_t *cn = ex + kPathTile;
     __shared__ uint32_t sub_entry[kPathTile / kPathSub], sub_base[kPathTile / kPathSub];
-    const uint32_t tbeg = blockIdx.x * kPathTile;
-    if (!jb.mark_needed[blockIdx.x]) return; // same entry, same nxt: the marks of this tile are still right
-    const uint32_t entry = jb.tile_entry[blockIdx.x];
     constexpr uint32_t nsub = kPathTile / kPathSub;
-    if (threadIdx.x < nsub) jb.long_cnt[blockIdx.x * nsub + threadIdx.x] = 0;
-    if (entry == 0xffffffffu) { // no path node starts in this tile
-        for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
-            if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = 0;
-        return;
-    }
-    path_load(jb, tbeg, nx);
-    __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t cur = entry - tbeg, cbase = 0; // symbol indices are relative to the tile's symbol base
-        for (uint32_t j = 0; j < nsub; j++) {
-            if (!(cur & kStuck) && cur < (j + 1) * kPathSub) {
-                sub_entry[j] = cur;
-                sub_base[j] = cbase;
-                cbase += cn[cur];
-                cur = ex[cur];
-            } else sub_entry[j] = 0xffffffffu;
+    const uint32_t count = list ? *list_cnt : gridDim.x;
+    for (uint32_t b = blockIdx.x; b < count; b += gridDim.x) {
+        const uint32_t tile = list ? list[b] : b;
+        const uint32_t tbeg = tile * kPathTile;
+        if (!jb.mark_needed[tile]) continue; // same entry, same nxt: the marks of this tile are still right
+        const uint32_t entry = jb.tile_entry[tile];
+        if (threadIdx.x < nsub) jb.long_cnt[tile * nsub + threadIdx.x] = 0;
+        if (entry == 0xffffffffu) { // no path node starts in this tile
+            for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
+                if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = 0;
+            continue;
         }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) ex[i] = 0; // ex becomes the mark array
-    __syncthreads();
-    if (lane == 0) {
-        for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) {
-            uint32_t p = sub_entry[s];
-            if (p == 0xffffffffu) continue;
-            uint32_t idx = sub_base[s], nlong = 0;
-            const uint32_t s1 = (s + 1) * kPathSub;
-            uint32_t *ll = jb.long_list + (size_t)(blockIdx.x * nsub + s) * kLongPerSub;
-            while (p < s1) {
-                const uint32_t v = nx[p];
-                if (v & kNxtTail) break; // the tail entry is emitted by k_tail
-                if ((v & kNxtLong) && nlong < kLongPerSub) ll[nlong++] = tbeg + p; // its macro step leaves holes
-                ex[p] = idx + 1;
-                idx += (v >> 16) & 0xffu;
-                p += v & 0xffffu;
+        __syncthreads(); // the previous tile of this CTA is done with the shared arrays
+        path_load(jb, tbeg, nx);
+        __syncthreads();
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cur = entry - tbeg, cbase = 0; // symbol indices are relative to the tile's symbol base
+            for (uint32_t j = 0; j < nsub; j++) {
+                if (!(cur & kStuck) && cur < (j + 1) * kPathSub) {
+                    sub_entry[j] = cur;
+                    sub_base[j] = cbase;
+                    cbase += cn[cur];
+                    cur = ex[cur];
+                } else sub_entry[j] = 0xffffffffu;
             }
-            jb.long_cnt[blockIdx.x * nsub + s] = nlong;
         }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) ex[i] = 0; // ex becomes the mark array
+        __syncthreads();
+        if (threadIdx.x < nsub) { // one thread per sub-tile: at most kPathSub dependent steps
+            const uint32_t s = threadIdx.x;
+            uint32_t p = sub_entry[s];
+            if (p != 0xffffffffu) {
+                uint32_t idx = sub_base[s], nlong = 0;
+                const uint32_t s1 = (s + 1) * kPathSub;
+                uint32_t *ll = jb.long_list + (size_t)(tile * nsub + s) * kLongPerSub;
+                while (p < s1) {
+                    const uint32_t v = nx[p];
+                    if (v & kNxtTail) break; // the tail entry is emitted by k_tail
+                    if (v & kNxtLong) { // its macro step leaves holes
+                        if (nlong < kLongPerSub) ll[nlong++] = tbeg + p;
+                        else atomicOr(&jb.info->error, 32u);
+                    }
+                    ex[p] = idx + 1;
+                    idx += (v >> 16) & 0xffu;
+                    p += v & 0xffffu;
+                }
+                jb.long_cnt[tile * nsub + s] = nlong;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
+            if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = ex[i];
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x)
-        if (tbeg + i < jb.tail_start) jb.symidx[tbeg + i] = ex[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -910,7 +1365,7 @@ __global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
         // the per-iteration flags that k_holes_cmp (next launch) sets, and the changed-M flags k_nxt (previous launch) consumed
         const uint32_t nthr = gridDim.x * blockDim.x;
         for (uint32_t i = t; i < jb.nmt; i += nthr) jb.tile_dirty[i] = 0;
-        for (uint32_t i = t; i < 2048; i += nthr) jb.bucket_map[i] = 0;
+        for (uint32_t i = t; i < jb.nmt * 512; i += nthr) reinterpret_cast<uint4 *>(jb.bucket_map)[i] = make_uint4(0, 0, 0, 0);
         for (uint32_t i = t; i < (jb.N >> 10) + 16; i += nthr) jb.hcoarse[i] = 0;
         for (uint32_t i = t; i < (jb.N >> 8) + 16; i += nthr) reinterpret_cast<uint32_t *>(jb.mchg)[i] = 0; // 1 byte / 64 positions
         if (t == 0) jb.info->holes_changed = 0;
@@ -918,25 +1373,20 @@ __global__ void __launch_bounds__(256) k_holes(JobBufs jb, uint32_t nlists)
     const uint32_t list = t / kLongPerSub, slot = t % kLongPerSub;
     if (list >= nlists || slot >= jb.long_cnt[list]) return;
     const uint32_t p = jb.long_list[(size_t)list * kLongPerSub + slot];
-    GAcc a{jb.in, jb.N, jb.L, jb.holes, jb.M, jb.wsize};
-    uint32_t ns = 0;
-    const uint32_t long_len = 16 * jb.lp.lazy;
+    // the long match is the last symbol of p's macro step (k_nxt checked it): [np - len, np)
+    const uint32_t v = jb.nxt[p], delta = v & 0xffffu;
+    const uint32_t len = jb.lp.early_exit ? delta : ((v & kNxtLong258) ? 258u : 257u);
+    const uint32_t pos = p + delta - len;
+    // interior positions pos+1 .. pos+len-2 are never inserted (medium.rs:251-261)
+    uint32_t y0 = pos + 1, y1 = pos + len - 1; // [y0, y1)
     uint32_t *hn = jb.holes_new;
-    auto mark = [&](const Sym &s) {
-        if (s.dist && (uint32_t)s.lc + 3u > long_len) {
-            // interior positions pos+1 .. pos+len-2 are never inserted (medium.rs:251-261)
-            uint32_t y0 = s.pos + 1, y1 = s.pos + s.lc + 3u - 1; // [y0, y1)
-            while (y0 < y1) {
-                const uint32_t w = y0 >> 5, lo = y0 & 31;
-                const uint32_t n = min(32u - lo, y1 - y0);
-                const uint32_t mask = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << lo;
-                atomicOr(&hn[w], mask);
-                y0 += n;
-            }
-        }
-    };
-    if (jb.wsize == kWSize) macro_step(a, p, jb.lp, jb.tail_start, mark, &ns);
-    else macro_step(a, p, jb.lp, jb.tail_start, mark, &ns, DynWin{jb.wsize});
+    while (y0 < y1) {
+        const uint32_t w = y0 >> 5, lo = y0 & 31;
+        const uint32_t n = min(32u - lo, y1 - y0);
+        const uint32_t mask = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << lo;
+        atomicOr(&hn[w], mask);
+        y0 += n;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_emit(JobBufs jb)
@@ -993,7 +1443,8 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
         jb.holes_new[w] = 0;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) if (sb[i]) atomicOr(&jb.bucket_map[i], sb[i]);
+    uint32_t *bm = jb.bucket_map + (size_t)((blockIdx.x * blockDim.x * 32) / kMatchTile) * 2048; // this CTA's positions lie in one tile
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) if (sb[i]) atomicOr(&bm[i], sb[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1096,22 +1547,296 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
     }
 }
 
-// One CTA per deflate block; the serial heap construction runs out of shared memory (zng_tr_flush_block).
+// ------------------------------------------------------------------------------------------------
+// k_build_blocks: one warp per deflate block (zng_tr_flush_block).  build_block() of zb_huff.h is the scalar statement of the
+// algorithm (the host model runs it); here the warp shares its linear parts -- histogram load, heap fill (ballot compaction),
+// bottom-up heapify (the sift-downs of one heap level touch disjoint subtrees), the bit-length statistics, gen_codes -- and lane 0
+// keeps the inherently serial ones: the extract-min loop (its tie behaviour is the binary heap's, deflate.rs:3045-3085), the
+// top-down length assignment and the run-length scan of the code lengths.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t brev_bits(uint32_t code, uint32_t len) { return __brev(code) >> (32u - len); }
+
+template <int KIND>
+__device__ __forceinline__ uint32_t xbits_of(uint32_t n) { return KIND == 0 ? (n >= 257 ? extra_lbits(n - 257) : 0u) : KIND == 1 ? extra_dbits(n) : extra_blbits(n); }
+
+template <int KIND>
+__device__ int build_tree_warp(TreeScratch &s, TreeState &st, CtData *tree, uint32_t *sh_cnt /* >= 16 words */)
+{
+    constexpr int elems = KIND == 0 ? kLCodes : KIND == 1 ? kDCodes : kBlCodes;
+    constexpr int max_length = KIND == 2 ? kMaxBlBits : kMaxBits;
+    const uint32_t lane = threadIdx.x & 31;
+    int heap_len = 0, max_code = -1;
+    for (int b0 = 0; b0 < elems; b0 += 32) {
+        const int n = b0 + (int)lane;
+        const bool nz = n < elems && tree[n].fc != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, nz);
+        if (nz) { s.heap[heap_len + 1 + __popc(m & ((1u << lane) - 1u))] = (uint32_t)n; s.depth[n] = 0; }
+        else if (n < elems) tree[n].dl = 0;
+        heap_len += __popc(m);
+        if (m) max_code = b0 + 31 - __clz(m);
+    }
+    __syncwarp();
+    if (heap_len < 2) { // deflate.rs:2012-2027: force two codes
+        if (lane == 0) {
+            while (heap_len < 2) {
+                const int node = max_code < 2 ? ++max_code : 0;
+                s.heap[++heap_len] = (uint32_t)node;
+                tree[node].fc = 1;
+                s.depth[node] = 0;
+                st.opt_len--;
+                if (KIND == 0) st.static_len -= c_tab.sl_len[node];
+                else if (KIND == 1) st.static_len -= 5;
+            }
+        }
+        heap_len = 2;
+        max_code = __shfl_sync(0xffffffffu, max_code, 0);
+        __syncwarp();
+    }
+    for (int n = 1 + (int)lane; n <= heap_len; n += 32) s.hk[n] = heap_entry(tree, s.depth, s.heap[n]);
+    __syncwarp();
+    // heapify: sift down nodes heap_len/2 .. 1; the nodes of one level own disjoint subtrees, so a level runs in parallel
+    for (int lvl = 31 - __clz(heap_len / 2); lvl >= 0; lvl--) {
+        const int first = 1 << lvl, last = min((2 << lvl) - 1, heap_len / 2);
+        for (int k = first + (int)lane; k <= last; k += 32) pqdownheap(s, heap_len, k);
+        __syncwarp();
+    }
+    int heap_max = kHeapSize;
+    if (lane == 0) {
+        int node = elems;
+        do {
+            const int n = (int)(s.hk[1] & 0xffffu);
+            s.hk[1] = s.hk[heap_len--];
+            pqdownheap(s, heap_len, 1);
+            const int m = (int)(s.hk[1] & 0xffffu);
+            s.heap[--heap_max] = (uint32_t)n;
+            s.heap[--heap_max] = (uint32_t)m;
+            tree[node].fc = (uint16_t)(tree[n].fc + tree[m].fc);
+            s.depth[node] = (uint8_t)((s.depth[n] >= s.depth[m] ? s.depth[n] : s.depth[m]) + 1);
+            tree[n].dl = tree[m].dl = (uint16_t)node;
+            s.hk[1] = heap_entry(tree, s.depth, (uint32_t)node);
+            node++;
+            pqdownheap(s, heap_len, 1);
+        } while (heap_len >= 2);
+        s.heap[--heap_max] = (uint32_t)(s.hk[1] & 0xffffu);
+        // gen_bitlen, the top-down part: a node's length is its parent's + 1 (parents come first in heap[])
+        int overflow = 0;
+        tree[s.heap[heap_max]].dl = 0;
+        for (int h = heap_max + 1; h < kHeapSize; h++) {
+            const int n = (int)s.heap[h];
+            int bits = tree[tree[n].dl].dl + 1;
+            if (bits > max_length) { bits = max_length; overflow++; }
+            tree[n].dl = (uint16_t)bits;
+        }
+        sh_cnt[0] = (uint32_t)overflow;
+    }
+    heap_max = __shfl_sync(0xffffffffu, heap_max, 0);
+    __syncwarp();
+    const int overflow = (int)sh_cnt[0];
+    __syncwarp();
+    // bl_count and the bit totals over the leaves
+    if (lane < 16) sh_cnt[lane] = 0;
+    __syncwarp();
+    uint64_t opt = 0, stat = 0;
+    for (int n = (int)lane; n <= max_code; n += 32) {
+        // internal nodes and unused codes (dl == 0 was stored for them above; a used leaf has dl >= 1)
+        const uint32_t bits = tree[n].dl;
+        if (tree[n].fc == 0 || bits == 0) continue;
+        atomicAdd(&sh_cnt[bits], 1u);
+        const uint32_t xb = xbits_of<KIND>((uint32_t)n);
+        const uint64_t f = tree[n].fc;
+        opt += f * (uint64_t)(bits + xb);
+        if (KIND == 0) stat += f * (uint64_t)(c_tab.sl_len[n] + xb);
+        else if (KIND == 1) stat += f * (uint64_t)(5 + xb);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { opt += __shfl_xor_sync(0xffffffffu, opt, d); stat += __shfl_xor_sync(0xffffffffu, stat, d); }
+    __syncwarp();
+    if (lane == 0) {
+        st.opt_len += opt;
+        st.static_len += stat;
+        if (overflow > 0) { // deflate.rs:2107-2160 (rare: a code longer than max_length)
+            int ov = overflow, bits;
+            do {
+                bits = max_length - 1;
+                while (sh_cnt[bits] == 0) bits--;
+                sh_cnt[bits]--;
+                sh_cnt[bits + 1] += 2;
+                sh_cnt[max_length]--;
+                ov -= 2;
+            } while (ov > 0);
+            int h = kHeapSize;
+            for (bits = max_length; bits != 0; bits--) {
+                int n = (int)sh_cnt[bits];
+                while (n != 0) {
+                    const int m = (int)s.heap[--h];
+                    if (m > max_code) continue;
+                    if (tree[m].dl != (uint16_t)bits) {
+                        st.opt_len += (uint64_t)bits * tree[m].fc;
+                        st.opt_len -= (uint64_t)tree[m].dl * tree[m].fc;
+                        tree[m].dl = (uint16_t)bits;
+                    }
+                    n--;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // gen_codes: codes of one length are handed out in symbol order
+    uint32_t nc = 0;
+    {
+        uint32_t code = 0;
+        // next_code[len] for this lane's len = lane (1..15)
+        for (uint32_t b = 1; b <= (uint32_t)kMaxBits; b++) { code = (code + sh_cnt[b - 1]) << 1; if (b == lane) nc = code; }
+    }
+    for (int b0 = 0; b0 <= max_code; b0 += 32) {
+        const int n = b0 + (int)lane;
+        const uint32_t len = n <= max_code ? tree[n].dl : 0u;
+        // rank of n among the symbols of the same length in this batch
+        const uint32_t same = __match_any_sync(0xffffffffu, len);
+        const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+        const uint32_t base = __shfl_sync(0xffffffffu, nc, len & 31u);
+        if (len) tree[n].fc = (uint16_t)brev_bits(base + rank, len);
+        // advance next_code[len] by the batch's count of that length
+#pragma unroll 1
+        for (uint32_t l = 1; l <= (uint32_t)kMaxBits; l++) {
+            const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, len == l));
+            if (lane == l) nc += cnt;
+        }
+    }
+    __syncwarp();
+    return max_code;
+}
+
+struct WordSink { // LSB-first bit sink (block headers): codes of at most 16 bits
+    uint8_t *buf;
+    uint32_t nbits;
+    __device__ __forceinline__ void put(uint32_t val, uint32_t len)
+    {
+        const uint32_t byte = nbits >> 3, sh = nbits & 7u;
+        const uint32_t v = (val & ((1u << len) - 1u)) << sh;
+        if (sh == 0) buf[byte] = (uint8_t)v; else buf[byte] |= (uint8_t)v;
+        if (sh + len > 8) { buf[byte + 1] = (uint8_t)(v >> 8); if (sh + len > 16) buf[byte + 2] = (uint8_t)(v >> 16); }
+        nbits += len;
+    }
+};
+
+__device__ void send_tree_fast(WordSink &o, const CtData *bltree, const CtData *tree, int max_code)
+{
+    int prevlen = -1, curlen, nextlen = tree[0].dl, count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    for (int n = 0; n <= max_code; n++) {
+        curlen = nextlen;
+        nextlen = tree[n + 1].dl;
+        if (++count < max_count && curlen == nextlen) continue;
+        else if (count < min_count) { do { o.put(bltree[curlen].fc, bltree[curlen].dl); } while (--count != 0); }
+        else if (curlen != 0) {
+            if (curlen != prevlen) { o.put(bltree[curlen].fc, bltree[curlen].dl); count--; }
+            o.put(bltree[16].fc, bltree[16].dl);
+            o.put((uint32_t)(count - 3), 2);
+        } else if (count <= 10) {
+            o.put(bltree[17].fc, bltree[17].dl);
+            o.put((uint32_t)(count - 3), 3);
+        } else {
+            o.put(bltree[18].fc, bltree[18].dl);
+            o.put((uint32_t)(count - 11), 7);
+        }
+        count = 0;
+        prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
+// zng_tr_flush_block for one block, one warp (cf. build_block() in zb_huff.h).
+__device__ void build_block_warp(TreeScratch &s, BlockDesc &b, const uint32_t *lfreq, const uint32_t *dfreq, bool have_window,
+                                 bool strategy_fixed, uint32_t *sh_cnt, TreeState *sh_st)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t opt_lenb = 0, static_lenb = 0;
+    int max_blindex = 0, lmax = 0, dmax = 0;
+    TreeState &st = *sh_st;
+    if (lane == 0) { st = TreeState{0, 0}; b.data_type = 2; b.no_eob = 0; }
+    __syncwarp();
+    if (b.sym_count == 0) {
+        if (lane == 0) st.static_len = 7;
+    } else {
+        {   // detect_data_type (deflate.rs:1523-1550)
+            bool black = false, white = false;
+            for (uint32_t n = lane; n < 256; n += 32) {
+                if (lfreq[n] == 0) continue;
+                if (n < 32 && ((0xf3ffc07fu >> n) & 1u)) black = true;
+                if (n == 9 || n == 10 || n == 13 || n >= 32) white = true;
+            }
+            const bool ab = __any_sync(0xffffffffu, black), aw = __any_sync(0xffffffffu, white);
+            if (lane == 0) b.data_type = ab ? 0u : aw ? 1u : 0u;
+        }
+        for (int n = (int)lane; n < kHeapSize; n += 32) s.ltree[n] = CtData{(uint16_t)(n < kLCodes ? lfreq[n] : 0), 0};
+        for (int n = (int)lane; n < 2 * kDCodes + 1; n += 32) s.dtree[n] = CtData{(uint16_t)(n < kDCodes ? dfreq[n] : 0), 0};
+        for (int n = (int)lane; n < 2 * kBlCodes + 1; n += 32) s.bltree[n] = CtData{0, 0};
+        __syncwarp();
+        if (lane == 0) s.ltree[kEndBlock].fc = 1;
+        __syncwarp();
+        lmax = build_tree_warp<0>(s, st, s.ltree, sh_cnt);
+        dmax = build_tree_warp<1>(s, st, s.dtree, sh_cnt);
+        if (lane == 0) {
+            scan_tree(s.bltree, s.ltree, lmax);
+            scan_tree(s.bltree, s.dtree, dmax);
+        }
+        __syncwarp();
+        build_tree_warp<2>(s, st, s.bltree, sh_cnt);
+        for (max_blindex = kBlCodes - 1; max_blindex >= 3; max_blindex--)
+            if (s.bltree[bl_order(max_blindex)].dl != 0) break;
+        if (lane == 0) st.opt_len += 3 * ((uint64_t)max_blindex + 1) + 5 + 5 + 4;
+        __syncwarp();
+        opt_lenb = (st.opt_len + 3 + 7) >> 3;
+        static_lenb = (st.static_len + 3 + 7) >> 3;
+        if (static_lenb <= opt_lenb || strategy_fixed) opt_lenb = static_lenb;
+    }
+    __syncwarp();
+    if ((uint64_t)b.in_len + 4 <= opt_lenb && have_window) {
+        if (lane == 0) { b.type = 0; b.hdr[0] = (uint8_t)b.last; b.hdr_bits = 3; b.body_bits = 0; }
+    } else if (static_lenb == opt_lenb) {
+        if (lane == 0) { b.type = 1; b.hdr[0] = (uint8_t)(2 | b.last); b.hdr_bits = 3; b.body_bits = st.static_len; }
+        for (int n = (int)lane; n < kLCodes; n += 32) { b.lcode[n] = c_tab.sl_code[n]; b.llen[n] = c_tab.sl_len[n]; }
+        if (lane < (uint32_t)kDCodes) { b.dcode[lane] = c_tab.sd_code[lane]; b.dlen[lane] = 5; }
+    } else {
+        if (lane == 0) {
+            b.type = 2;
+            WordSink o{b.hdr, 0};
+            o.put(4 | b.last, 3);
+            const int lcodes = lmax + 1, dcodes = dmax + 1, blcodes = max_blindex + 1;
+            o.put((uint32_t)(lcodes - 257), 5);
+            o.put((uint32_t)(dcodes - 1), 5);
+            o.put((uint32_t)(blcodes - 4), 4);
+            for (int r = 0; r < blcodes; r++) o.put(s.bltree[bl_order(r)].dl, 3);
+            send_tree_fast(o, s.bltree, s.ltree, lcodes - 1);
+            send_tree_fast(o, s.bltree, s.dtree, dcodes - 1);
+            b.hdr_bits = o.nbits;
+            b.body_bits = 3 + st.opt_len - o.nbits;
+        }
+        for (int n = (int)lane; n < kLCodes; n += 32) { b.lcode[n] = n <= lmax ? s.ltree[n].fc : 0; b.llen[n] = n <= lmax ? (uint8_t)s.ltree[n].dl : 0; }
+        if (lane < (uint32_t)kDCodes) { b.dcode[lane] = (int)lane <= dmax ? s.dtree[lane].fc : 0; b.dlen[lane] = (int)lane <= dmax ? (uint8_t)s.dtree[lane].dl : 0; }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(32) k_build_blocks(JobBufs jb, const uint32_t *freq)
 {
     __shared__ TreeScratch s;
     __shared__ BlockDesc bd;
     __shared__ uint32_t fr[320];
+    __shared__ uint32_t sh_cnt[16];
+    __shared__ TreeState sh_st;
     const uint32_t b = blockIdx.x;
     if (b >= jb.info->n_blocks) return;
     for (uint32_t i = threadIdx.x; i < 320; i += 32) fr[i] = freq[b * 320 + i];
     for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
         reinterpret_cast<uint32_t *>(&bd)[i] = reinterpret_cast<const uint32_t *>(&jb.blocks[b])[i];
     __syncwarp();
-    if (threadIdx.x == 0) {
-        if (jb.serial_mode == 1) build_quick_piece(c_tab, bd, fr, fr + kLCodes, b == 0, b + 1 == jb.info->n_blocks, jb.not_last == 0);
-        else build_block(c_tab, s, bd, fr, fr + kLCodes, bd.have_window != 0, jb.strategy_fixed != 0);
-    }
+    if (jb.serial_mode == 1) {
+        if (threadIdx.x == 0) build_quick_piece(c_tab, bd, fr, fr + kLCodes, b == 0, b + 1 == jb.info->n_blocks, jb.not_last == 0);
+    } else build_block_warp(s, bd, fr, fr + kLCodes, bd.have_window != 0, jb.strategy_fixed != 0, sh_cnt, &sh_st);
     __syncwarp();
     for (uint32_t i = threadIdx.x; i < sizeof(BlockDesc) / 4; i += 32)
         reinterpret_cast<uint32_t *>(&jb.blocks[b])[i] = reinterpret_cast<const uint32_t *>(&bd)[i];

@@ -13,15 +13,23 @@ constexpr uint32_t kLinkTile = 32768;   // positions per k_links2 CTA (>= the la
 constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the match phase
 constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA (126 KiB of shared memory)
 constexpr uint32_t kPathTile = 16384;   // positions per path tile
-constexpr uint32_t kPathSub = 1024;     // positions per path sub-tile (one warp)
-constexpr uint32_t kLongPerSub = 8;     // a 1 KiB sub-tile holds at most 1024/257+1 long-match nodes
+constexpr uint32_t kPathSub = 256;      // positions per path sub-tile (exits: one warp; marks: one thread)
+constexpr uint32_t kLongPerSub = 4;     // long-match nodes are more than 16*max_lazy >= 96 positions apart: at most 3 per sub-tile
 #ifndef ZB_PATH_HEAD
 #define ZB_PATH_HEAD 64
 #endif
 constexpr uint32_t kPathHead = ZB_PATH_HEAD; // leading positions of a path tile mirrored in the compact head table
 constexpr uint32_t kChainChunkTiles = ZB_PATH_HEAD > 64 ? 96 : 320; // tiles per staged chunk of that table in k_path_chain
+#ifndef ZB_MATCH_CTX
+#define ZB_MATCH_CTX 0 // k_match schedule: 0 = one walk context per lane in registers; 1 = contexts in shared memory, rounds of one kind per
+                       // warp (experiment, measured slower: first pass 2.45..2.7 ms against 1.98 ms, r2r)
+#endif
+#ifndef ZB_CTX
+#define ZB_CTX 4       // contexts per lane (16 bytes of shared memory each)
+#endif
 constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches the tail zone
 constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
+constexpr uint32_t kNxtLong258 = 0x20000000u; // ... and that match is 258 bytes long (levels 5/6: 257 otherwise)
 constexpr uint32_t kSymsPerThread = 16;
 constexpr uint32_t kSlowSub = 8192;     // positions per k_slow CTA
 constexpr uint32_t kSlowAhead = 1024;   // bytes/links staged behind the last position of a k_slow CTA (<= kPad)
@@ -93,7 +101,7 @@ struct JobBufs {
     const uint32_t *match_list; // k_match: sub-tile index per CTA (nullptr: all sub-tiles)
     const uint32_t *nxt_list;   // k_nxt: path tile per 16 CTAs (nullptr: all tiles)
     uint4 *chain_state;       // k_path_chain: (entry, symbol base, done, tail entry) at every tile boundary
-    uint32_t *bucket_map;     // 65536 bits: hash buckets in which a hole changed in the last iteration
+    uint32_t *bucket_map;     // per 32 KiB tile, 65536 bits: hash buckets in which a hole of that tile changed in the last iteration
     uint32_t use_bucket_map;  // k_match recomputes only positions of those buckets (later iterations)
     uint32_t not_last;        // segment mode: no BFINAL; what follows the last block is end_mode
     uint32_t end_mode;        // not_last: 0 Z_SYNC_FLUSH marker (empty stored block, byte aligned), 1 Z_PARTIAL_FLUSH (empty static block,

@@ -93,7 +93,6 @@ ZB_HDN uint32_t headpos(const A &a, uint32_t x, uint32_t p, uint32_t B, uint32_t
     return q > B ? q : B;
 }
 
-ZB_HD uint32_t min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // longest_match / longest_match_slow at loop-top p with prev_length pl (0 or 2: fresh), default result ms_in.
 // hh = hash_head (absolute, already validated by the caller).  Returns {len, start}: len <= pl means "nothing longer".
