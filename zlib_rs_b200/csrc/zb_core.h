@@ -180,18 +180,23 @@ ZB_HD bool fizzle(const A &a, uint32_t B, PMatch &current, PMatch &next, const W
     K = min_u32(K, n.len < 256u ? 256u - n.len : 0u);
     K = min_u32(K, n.ms > B + 1u ? n.ms - B - 1u : 0u);
     uint32_t changed = 0;
-    while (changed < K) { // eight bytes per round: the sixteen loads are independent of each other
-        const uint32_t m = K - changed < 8u ? K - changed : 8u;
-        uint32_t diff = 0;
+    while (changed < K) {
+        if (changed >= 4u && K - changed >= 8u) { // a long run: eight bytes per round, the sixteen loads are independent of each other
+            uint32_t diff = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (uint32_t j = 0; j < 8u; j++)
-            if (j < m && a.byte(n.ms - 1u - changed - j) != a.byte(n.ss - 1u - changed - j)) diff |= 1u << j;
-        uint32_t e = 0;
-        while (e < m && !((diff >> e) & 1u)) e++;
-        changed += e;
-        if (e < m) break;
+            for (uint32_t j = 0; j < 8u; j++)
+                if (a.byte(n.ms - 1u - changed - j) != a.byte(n.ss - 1u - changed - j)) diff |= 1u << j;
+            if (diff) {
+                while (!(diff & 1u)) { diff >>= 1; changed++; }
+                break;
+            }
+            changed += 8u;
+        } else { // most fizzles end at the first or second byte
+            if (a.byte(n.ms - 1u - changed) != a.byte(n.ss - 1u - changed)) break;
+            changed++;
+        }
     }
     n.ss -= changed; n.ms -= changed; n.len += changed; c.len -= changed;
     if (changed == 0) return false;

@@ -33,6 +33,7 @@ __global__ void k_path_chain(JobBufs, uint32_t, uint32_t);
 __global__ void k_path_groups(JobBufs, uint32_t, uint32_t, uint4 *, uint32_t *);
 __global__ void k_path_chain2(JobBufs, uint32_t, uint32_t, const uint4 *, uint32_t *, uint32_t *);
 __global__ void k_path_mark(JobBufs, const uint32_t *, const uint32_t *);
+__global__ void k_iter_lists(JobBufs, uint32_t *, uint32_t *, uint32_t);
 __global__ void k_emit(JobBufs);
 __global__ void k_holes(JobBufs, uint32_t);
 __global__ void k_holes_cmp(JobBufs, uint32_t, uint32_t);
@@ -59,7 +60,7 @@ __global__ void k_links_dict_ghost_apply(JobBufs, const uint32_t *);
 constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMatchSub) * 2 + ((kWSize + kMatchSub) / 32 + 1) * 4 * 4 + 8192;
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64 + 2048;
-constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + (2 * kWSize / 32) * 4 + 64;
+constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + 2 * (2 * kWSize / 32) * 4 + 8192 + 64; // links, hole + bucket-flag bitmaps, bucket map
 constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = kChainChunkTiles * kPathHead * 8;
 constexpr uint32_t kChain2MaxSmem = 200 * 1024; // two-level chain: group heads + transfer functions of the groups
@@ -165,7 +166,7 @@ int Engine::stage(size_t bytes)
 }
 
 enum { S_IN, S_L, S_HOLES, S_HOLESN, S_M, S_NXT, S_PEXIT, S_PCNT, S_SYMIDX, S_TENTRY, S_TSYMB, S_TDIRTY, S_SYMS, S_SYMB,
-       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_MCHG, S_GFN, S_COUNT };
+       S_BLOCKS, S_SCRATCH, S_FREQ, S_OUT, S_CK, S_INF0, S_INF1, S_PHEAD, S_SK, S_MARKN, S_LLIST, S_LCNT, S_BMAP, S_HDIFF, S_HCOARSE, S_CSTATE, S_LISTS, S_LR, S_LLAST, S_BBASE, S_MCHG, S_GFN, S_KEYS, S_COUNT };
 static_assert(S_COUNT <= Engine::kSlots, "slots");
 
 size_t deflate_bound(size_t n)
@@ -258,6 +259,7 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     RES(S_SYMB, 40000 * 4, sym_base, uint32_t *)
     RES(S_BMAP, (size_t)nmt * 8192, bucket_map, uint32_t *) // one 65536-bit map per 32 KiB tile
     RES(S_LR, npad * 2, Lr, uint16_t *)
+    RES(S_KEYS, npad * 2, keys, uint16_t *)
     RES(S_LLAST, (size_t)nmt * 65536 * 2, link_last, uint16_t *)
     RES(S_CSTATE, (size_t)(npt + 1) * 16, chain_state, uint4 *)
     // two-level path chain: groups of ~sqrt(tiles) path tiles (k_path_groups / k_path_chain2)
@@ -469,7 +471,8 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                         jb.match_sub = per_cta >= 8192 ? 8192 : per_cta >= 4096 ? 4096 : per_cta >= 2048 ? 2048 : 1024;
                     }
                     {   // experiment knobs for the dense passes (not part of the interface)
-                        static const char *e_sub = getenv("ZB_MSUB"), *e_thr = getenv("ZB_MTHREADS");
+                        static const char *e_sub = getenv("ZB_MSUB"), *e_thr = getenv("ZB_MTHREADS"), *e_sub1 = getenv("ZB_MSUB1");
+                        if (e_sub1 && iters == 1) jb.match_sub = (uint32_t)atoi(e_sub1);
                         if (e_sub && n_dirty > 9) jb.match_sub = (uint32_t)atoi(e_sub);
                         if (e_thr && n_dirty > 9) mthreads = (uint32_t)atoi(e_thr);
                     }
@@ -478,45 +481,22 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
 #endif
                     uint32_t nsub = (N + jb.match_sub - 1) / jb.match_sub;
                     uint32_t n_ptiles = npt, first_ptile = 0;
-                    jb.match_list = nullptr;
+                    jb.skip_list = nullptr;
                     jb.nxt_list = nullptr;
                     if (iters > 1) {
-                        // launch only the pieces a changed hole can reach (the kernels re-check the flags themselves)
-                        uint32_t nm = 0, np_ = 0;
-                        const uint32_t per = kMatchTile / jb.match_sub;
-                        uint32_t *sl = h_lists + max_list + npt, nsk = 0;
-                        for (uint32_t t = 0; t < nmt; t++) {
-                            if (!h_dirty[t]) continue;
-                            sl[nsk++] = t;
-                            for (uint32_t k = 0; k < per; k++) if ((uint64_t)(t * per + k) * jb.match_sub < N) h_lists[nm++] = t * per + k;
-                        }
-                        uint32_t *pl = h_lists + max_list;
-                        first_ptile = npt;
-                        for (uint32_t pt = 0; pt < npt; pt++) {
-                            const uint32_t m0 = (pt * kPathTile) / kMatchTile;
-                            uint32_t m1 = ((pt + 1) * kPathTile + 22016 - 1) / kMatchTile;
-                            if (m1 >= nmt) m1 = nmt - 1;
-                            bool d = false;
-                            for (uint32_t m = m0; m <= m1; m++) d = d || h_dirty[m];
-                            if (d) { pl[np_++] = pt; if (first_ptile == npt) first_ptile = pt; }
-                        }
-                        if (first_ptile == npt) first_ptile = 0;
-                        if (!nm) h_lists[0] = 0;
-                        if (!np_) pl[0] = 0;
-                        CK(cudaMemcpyAsync(d_lists, h_lists, (size_t)(nm ? nm : 1) * 4, cudaMemcpyHostToDevice, st));
-                        CK(cudaMemcpyAsync(d_lists + max_list, pl, (size_t)(np_ ? np_ : 1) * 4, cudaMemcpyHostToDevice, st));
-                        if (nsk) {
-                            CK(cudaMemcpyAsync(d_lists + max_list + npt, sl, (size_t)nsk * 4, cudaMemcpyHostToDevice, st));
-                            jb.skip_list = d_lists + max_list + npt;
+                        // only the pieces a changed hole can reach (the kernels re-check the flags themselves): the lists were built
+                        // on the device by k_iter_lists, their lengths came back with the iteration's control block
+                        jb.skip_list = d_lists;
+                        jb.nxt_list = d_lists + nmt + 8;
+                        n_ptiles = h_info->n_ptiles ? h_info->n_ptiles : 1;
+                        first_ptile = h_info->first_ptile;
+                        nsub = (n_dirty ? n_dirty : 1) * (kMatchTile / jb.match_sub);
+                        if (n_dirty) {
                             pbegin();
-                            k_skip<<<nsk, 1024, kSkipSmemBytes, st>>>(jb);
+                            k_skip<<<n_dirty, 1024, kSkipSmemBytes, st>>>(jb);
                             pend(1, 1);
                             launches++;
                         }
-                        jb.match_list = d_lists;
-                        jb.nxt_list = d_lists + max_list;
-                        nsub = nm ? nm : 1;
-                        n_ptiles = np_ ? np_ : 1;
                     }
                     // the dirty-bucket map and the changed-hole bitmaps are only staged from the second iteration on
                     const uint32_t msmem = (kWSize + jb.match_sub + 512) + (kWSize + jb.match_sub) * 2 +
@@ -540,8 +520,9 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     k_holes_cmp<<<(nwords + 255) / 256, 256, 0, st>>>(jb, nwords, nmt);
                     pend(4, 2);
                     launches += 7;
+                    k_iter_lists<<<1, 1024, 0, st>>>(jb, d_lists, d_lists + nmt + 8, npt);
+                    launches++;
                     CK(cudaMemcpyAsync(h_info, d_info, sizeof(JobInfo), cudaMemcpyDeviceToHost, st));
-                    CK(cudaMemcpyAsync(h_dirty, jb.tile_dirty, nmt, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                     if (h_info->error) { snprintf(g_err, sizeof g_err, "engine error flags 0x%x (parse)", h_info->error); return ZB_E_INTERNAL; }
                     if (getenv("ZB_DEBUG")) {
@@ -552,11 +533,11 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                                 (h_info->dbg[2] - last[2]) / 1e3 / (double)(h_info->dbg[0] - last[0] + 1e-9),
                                 (h_info->dbg[3] - last[3]) / 1e3 / (double)(h_info->dbg[0] - last[0] + 1e-9),
                                 (h_info->dbg[4] - last[4]) / (double)(h_info->dbg[0] - last[0] + 1e-9), h_info->holes_changed);
+                        if (h_info->dbg[5]) fprintf(stderr, "   walks %llu, M changed %llu\n", h_info->dbg[5] - last[5], h_info->dbg[6] - last[6]);
                         memcpy(last, h_info->dbg, sizeof last);
                     }
                     if (!h_info->holes_changed) break;
-                    n_dirty = 0;
-                    for (uint32_t i = 0; i < nmt; i++) n_dirty += h_dirty[i] != 0;
+                    n_dirty = h_info->n_dirty;
                     if (iters > N / 257u + 4096u) { snprintf(g_err, sizeof g_err, "hole iteration did not converge"); return ZB_E_INTERNAL; } // every iteration settles at least one long match
                 }
             }

@@ -127,7 +127,9 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     uint16_t *myrun = run + warp * 32;
     for (uint32_t b = 0; b < 32; b++) {
         const uint32_t i = warp * 1024 + b * 32 + lane;
-        const uint32_t c = i < nv ? (key_of(i) & 31u) : 32u;
+        const uint32_t key = i < nv ? key_of(i) : 0u;
+        const uint32_t c = i < nv ? (key & 31u) : 32u;
+        if (!kRoll && i < nv) jb.keys[ts + i] = (uint16_t)key; // k_skip tells by the key whether a position's bucket saw a change
         const uint32_t peers = __match_any_sync(0xffffffffu, c);
         if (c < 32u && (peers & ((1u << lane) - 1u)) == 0) myrun[c] += (uint16_t)__popc(peers);
         __syncwarp();
@@ -226,7 +228,9 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *sL = reinterpret_cast<uint16_t *>(smem);
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kSkipSpan * 2);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem + kSkipSpan * 2); // holes of the span
+    uint32_t *sf = sh + kSkipSpan / 32;                                // positions of the span whose hash bucket saw a hole change
+    uint32_t *sbm = sf + kSkipSpan / 32;                               // 65536 bits: those buckets (this tile's and the previous tile's map)
     const uint32_t tile = jb.skip_list ? jb.skip_list[blockIdx.x] : blockIdx.x;
     const uint32_t ts = tile * kMatchTile;
     if (ts >= jb.N) return;
@@ -239,26 +243,57 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
         uint4 *ld = reinterpret_cast<uint4 *>(sL);
         for (uint32_t i = tid; i < (span + 7) / 8; i += 1024) ld[i] = ls[i];
         for (uint32_t i = tid; i < (span + 31) / 32; i += 1024) sh[i] = jb.holes[(ws >> 5) + i];
+        const uint32_t *bm1 = jb.bucket_map + (size_t)tile * 2048, *bm0 = tile ? bm1 - 2048 : bm1;
+        for (uint32_t i = tid; i < 2048; i += 1024) sbm[i] = bm0[i] | bm1[i];
+    }
+    __syncthreads();
+    // Chains are per hash bucket, and only buckets in which a hole changed (in this tile or the one before it: the staged span) can
+    // have different bridged links than Lr already holds: everything below touches only positions of those buckets.  In the first
+    // iterations that is nearly every position, in the last ones a few hundred.
+    for (uint32_t i = tid; i < ((span + 31) & ~31u); i += 1024) {
+        bool f = false;
+        if (i < span) { const uint32_t key = jb.keys[ws + i]; f = (sbm[key >> 5] >> (key & 31u)) & 1u; }
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if ((tid & 31u) == 0) sf[i >> 5] = m;
     }
     __syncthreads();
     // Pointer jumping over the staged window.  Measured alternatives (r2e, r2h): visiting only the set bits of the hole bitmap
     // (0.13 instead of 0.07..0.11 ms per launch) and one serial walk per position through the holes (0.62 ms on the hole-dense
     // tiles of the first iterations) were both slower than this dense sweep.
+    // Thread tid owns the positions tid + 1024 k, i.e. lane `lane` of the bitmap words warp + 32 k: a warp first notes which of its
+    // 64 words hold a hole in play at all (two ballots), and the rounds visit only those -- in the last iterations a handful.
+    const uint32_t lane = tid & 31, warp = tid >> 5, nwords = (span + 31) / 32;
+    uint32_t nz[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t w = warp + 32 * (lane + 32 * h);
+        nz[h] = __ballot_sync(0xffffffffu, w < nwords && (sh[w] & sf[w]) != 0);
+    }
     for (uint32_t round = 0; round < 24; round++) {
         int ch = 0;
-        for (uint32_t i = tid; i < span; i += 1024) {
-            if (!((sh[i >> 5] >> (i & 31)) & 1u)) continue;
-            const uint32_t d = sL[i];
-            if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
-            const uint32_t t = i - d;
-            if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
-            const uint32_t d2 = sL[t];
-            sL[i] = (uint16_t)((d2 == 0 || d + d2 > md) ? 0u : d + d2);
-            ch = 1;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t m = nz[h];
+            while (m) {
+                const uint32_t w = warp + 32 * ((__ffs(m) - 1) + 32 * h);
+                m &= m - 1;
+                if (!(((sh[w] & sf[w]) >> lane) & 1u)) continue;
+                const uint32_t i = w * 32 + lane;
+                if (i >= span) continue;
+                const uint32_t d = sL[i];
+                if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
+                const uint32_t t = i - d;
+                if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
+                const uint32_t d2 = sL[t];
+                sL[i] = (uint16_t)((d2 == 0 || d + d2 > md) ? 0u : d + d2);
+                ch = 1;
+            }
         }
         if (!__syncthreads_or(ch)) break;
     }
     for (uint32_t i = ts - ws + tid; i < span; i += 1024) {
+        if (sf[i >> 5] == 0) continue;
+        if (!((sf[i >> 5] >> (i & 31)) & 1u)) continue; // its bucket is unchanged: Lr stands
         uint32_t d = sL[i];
         if (!((sh[i >> 5] >> (i & 31)) & 1u) && d != 0 && d <= i) {
             const uint32_t t = i - d;
@@ -302,8 +337,8 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 #define ZB_SECOND_LOOK 1
 #endif
 #ifndef ZB_COOP_CMP
-#define ZB_COOP_CMP 0 // most lanes with a long compare for which the warp would finish them together; measured (r2p): 12 costs
-                      // 0.26 ms, 32 costs 1.7 ms over the twelve passes -- off
+#define ZB_COOP_CMP 4 // stragglers: with at most this many lanes still busy, the warp finishes a long compare together
+                      // (256 bytes per step).  Offering it to every compare burst was measured slower (r2p: +0.26 ms at 12 lanes).
 #endif
 constexpr uint32_t kBatch = ZB_T_IDLE;         // idle lanes that trigger a refill
 constexpr uint32_t kBatchCmp = ZB_T_CMP;       // pending lanes that trigger a compare burst
@@ -485,8 +520,11 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                 // A compare that survived a burst is a long one (repetitive data: up to 258 bytes, 33 steps).  While few lanes
                 // hold one, the warp finishes them one after the other, 8 bytes per lane = 256 bytes per step; the lane's serial
                 // loop would keep the other lanes of the warp waiting for up to 29 more steps.
-                uint32_t m_long = __ballot_sync(0xffffffffu, state == LS_PEND && !resolved);
-                if (m_long && __popc(m_long) <= ZB_COOP_CMP) {
+                // Only for stragglers: at most ZB_COOP_CMP lanes of the warp still have a walk (the end of a piece, and the sparse pieces
+                // of the later passes, where one lane with a chain of 258-byte compares is the critical path of the whole launch).
+                uint32_t m_long = 0;
+                if (__popc(m_walk | m_pend) <= ZB_COOP_CMP) m_long = __ballot_sync(0xffffffffu, state == LS_PEND && !resolved);
+                if (m_long) {
                     while (m_long) {
                         const uint32_t src = __ffs(m_long) - 1;
                         m_long &= m_long - 1;
@@ -524,6 +562,10 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
         }
         // ---- results
         if (state == LS_FIN) {
+#ifdef ZB_COUNT
+            atomicAdd(&jb.info->dbg[5], 1ull);                      // walks finished
+            if (Mout[xr] != res) atomicAdd(&jb.info->dbg[6], 1ull); // ... with a different result
+#endif
             if (filt && Mout[xr] != res) jb.mchg[(ws + xr) >> 6] = 1; // k_nxt redoes only the macro steps that read a changed M
             Mout[xr] = res; RDout[xr] = (uint16_t)rd; state = LS_IDLE;
         }
@@ -827,7 +869,9 @@ __global__ void __launch_bounds__(ZB_MATCH_MAXT, ZB_MATCH_MINB) k_match(JobBufs 
     __shared__ uint32_t s_next;
     __shared__ __align__(8) unsigned long long s_mbar; // completion barrier of the window's bulk copy
     const uint32_t sub = jb.match_sub;
-    const uint32_t ts = (jb.match_list ? jb.match_list[blockIdx.x] : blockIdx.x) * sub;
+    // later iterations: the pieces of the dirty tiles (jb.skip_list, built by k_iter_lists)
+    const uint32_t per_tile = kMatchTile / sub;
+    const uint32_t ts = (jb.skip_list ? jb.skip_list[blockIdx.x / per_tile] * per_tile + blockIdx.x % per_tile : blockIdx.x) * sub;
     if (ts >= jb.N) return;
     {
         const uint32_t t0 = ts / kMatchTile, t1 = (min(ts + sub, jb.N) - 1) / kMatchTile;
@@ -1090,13 +1134,14 @@ __global__ void __launch_bounds__(1024) k_path_tiles(JobBufs jb)
     path_load(jb, tbeg, nx);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t nsub = kPathTile / kPathSub;
-    for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kPathSub, (s + 1) * kPathSub, lane);
+    // the exits are composed sub-tile by sub-tile with a barrier each: coarser sub-tiles than the marks use (kPathSub)
+    constexpr uint32_t kExitSub = 1024, nsub = kPathTile / kExitSub;
+    for (uint32_t s = warp; s < nsub; s += blockDim.x / 32) path_subtile(nx, ex, cn, s * kExitSub, (s + 1) * kExitSub, lane);
     __syncthreads();
     // compose sub-tiles from the back: afterwards ex[p] >= kPathTile or stuck
     for (int32_t j = (int32_t)nsub - 2; j >= 0; j--) {
-        for (uint32_t i = threadIdx.x; i < kPathSub; i += blockDim.x) {
-            const uint32_t p = (uint32_t)j * kPathSub + i;
+        for (uint32_t i = threadIdx.x; i < kExitSub; i += blockDim.x) {
+            const uint32_t p = (uint32_t)j * kExitSub + i;
             uint32_t t = ex[p];
             if (!(t & kStuck) && t < kPathTile) { cn[p] += cn[t]; ex[p] = ex[t]; }
         }
@@ -1445,6 +1490,51 @@ __global__ void __launch_bounds__(256) k_holes_cmp(JobBufs jb, uint32_t nwords, 
     __syncthreads();
     uint32_t *bm = jb.bucket_map + (size_t)((blockIdx.x * blockDim.x * 32) / kMatchTile) * 2048; // this CTA's positions lie in one tile
     for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) if (sb[i]) atomicOr(&bm[i], sb[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_iter_lists: the work lists of the next iteration, built where the flags are: the dirty match tiles (k_skip, k_match) and
+// the path tiles within reach of one (k_nxt, k_path_tiles), with their counts in the job info block the host reads anyway.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_iter_lists(JobBufs jb, uint32_t *skip_list, uint32_t *path_list, uint32_t npt)
+{
+    __shared__ uint32_t s_wsum[32], s_total, s_first;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_first = 0xffffffffu;
+    uint32_t base = 0;
+    for (int which = 0; which < 2; which++) {
+        const uint32_t n = which ? npt : jb.nmt;
+        uint32_t *out = which ? path_list : skip_list;
+        base = 0;
+        for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
+            const uint32_t i = c0 + tid;
+            const bool d = i < n && (which ? path_tile_dirty(jb, i) : jb.tile_dirty[i] != 0);
+            const uint32_t m = __ballot_sync(0xffffffffu, d);
+            __syncthreads(); // s_wsum / s_total of the previous chunk have been read
+            if (lane == 0) s_wsum[warp] = __popc(m);
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t v = s_wsum[lane];
+                uint32_t incl = v;
+#pragma unroll
+                for (int k = 1; k < 32; k <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= (uint32_t)k) incl += t; }
+                s_wsum[lane] = incl - v;
+                if (lane == 31) s_total = incl;
+            }
+            __syncthreads();
+            if (d) {
+                out[base + s_wsum[warp] + __popc(m & ((1u << lane) - 1u))] = i; // ascending: the first entry is the lowest tile
+                if (which) atomicMin(&s_first, i);
+            }
+            base += s_total;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (which) { jb.info->n_ptiles = base; jb.info->first_ptile = s_first == 0xffffffffu ? 0u : s_first; }
+            else jb.info->n_dirty = base;
+        }
+        if (tid == 0 && base == 0) out[0] = 0; // a launch over the list has at least one CTA
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

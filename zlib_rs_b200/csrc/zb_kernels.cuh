@@ -12,7 +12,10 @@ namespace zb {
 constexpr uint32_t kLinkTile = 32768;   // positions per k_links2 CTA (>= the largest link)
 constexpr uint32_t kMatchTile = 32768;  // dirty-tracking granularity of the match phase
 constexpr uint32_t kMatchSub = 8192;    // positions per k_match CTA (126 KiB of shared memory)
-constexpr uint32_t kPathTile = 16384;   // positions per path tile
+#ifndef ZB_PATH_TILE
+#define ZB_PATH_TILE 16384
+#endif
+constexpr uint32_t kPathTile = ZB_PATH_TILE; // positions per path tile
 constexpr uint32_t kPathSub = 256;      // positions per path sub-tile (exits: one warp; marks: one thread)
 constexpr uint32_t kLongPerSub = 4;     // long-match nodes are more than 16*max_lazy >= 96 positions apart: at most 3 per sub-tile
 #ifndef ZB_PATH_HEAD
@@ -40,13 +43,13 @@ struct JobInfo {              // device-resident result / control block of one d
     uint32_t n_syms;          // total symbols
     uint32_t final_base;      // window base when the last block is flushed
     uint32_t holes_changed;   // iteration control
+    uint32_t n_dirty, n_ptiles, first_ptile; // k_iter_lists: dirty match tiles, path tiles within their reach, the first of those
     uint32_t n_blocks;
     uint32_t data_type;
     uint32_t error;           // non-zero: internal invariant violated
     uint64_t total_bits;      // bits of header + all blocks (before final alignment)
     uint64_t out_bytes;       // final stream length
     uint32_t adler;
-    uint32_t pad;
     uint64_t marker_byte;     // not_last: byte offset of the empty stored block's LEN field
     unsigned long long dbg[8]; // ZB_DEBUG counters (k_match: CTAs, stage, skip, walk cycles, rounds, positions)
 };
@@ -97,8 +100,8 @@ struct JobBufs {
     uint32_t slow_mode;       // 1: deflate_slow path (levels 7..9); 2: Z_RLE (steps from k_rle, same path/emit kernels)
     uint16_t *link_last;      // per 32 KiB tile: last occurrence (1 + position in the tile) of every hash key (k_links2 -> k_links_fix)
     uint16_t *Lr;             // N + kPad: links with the holes bridged (k_skip); equals L while there are no holes
-    const uint32_t *skip_list;  // k_skip: match tile per CTA
-    const uint32_t *match_list; // k_match: sub-tile index per CTA (nullptr: all sub-tiles)
+    uint16_t *keys;           // N + kPad: hash key of every position (k_links2_std), for k_skip's bucket test
+    const uint32_t *skip_list;  // k_skip: match tile per CTA; k_match: match tile per group of CTAs (nullptr: all tiles)
     const uint32_t *nxt_list;   // k_nxt: path tile per 16 CTAs (nullptr: all tiles)
     uint4 *chain_state;       // k_path_chain: (entry, symbol base, done, tail entry) at every tile boundary
     uint32_t *bucket_map;     // per 32 KiB tile, 65536 bits: hash buckets in which a hole of that tile changed in the last iteration
