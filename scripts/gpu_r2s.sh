@@ -1,8 +1,9 @@
 #!/bin/bash
-# ncu --set full captures (first launch) of several kernels of one level-6 deflate
+# ncu --set full captures of single launches of one level-6 deflate: "kernel:skip" pairs
 mkdir -p gpurun_out
-TAG=${1:-r2s}
-for k in k_match k_nxt k_skip k_path_mark; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$k -s 0 -c 1 -f -o gpurun_out/prof_${k}_$TAG python scripts/one_deflate.py 1 6 > gpurun_out/ncu_full_${k}_$TAG.log 2>&1; echo "$k ncu rc=$?"
+TAG=${1:-r2s}; shift
+for spec in "$@"; do
+  k=${spec%%:*}; sk=${spec#*:}
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:^$k -s $sk -c 1 -f -o gpurun_out/prof_${k}_s${sk}_$TAG python scripts/one_deflate.py 1 6 > gpurun_out/ncu_full_${k}_$TAG.log 2>&1; echo "$k skip $sk ncu rc=$?"
 done
 ls -la gpurun_out/*_$TAG.ncu-rep

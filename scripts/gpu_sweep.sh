@@ -9,5 +9,5 @@ for so in zlib_rs_b200/variants/libz_b200_*.so; do
   if [ -n "$ms" ]; then export ZB_MSUB=$ms; else unset ZB_MSUB; fi
   fs=""; [[ $name =~ _fs([0-9]+) ]] && fs=${BASH_REMATCH[1]}   # *_fs16384: first pass with 16384 positions per CTA
   if [ -n "$fs" ]; then export ZB_MSUB1=$fs; else unset ZB_MSUB1; fi
-  echo "== $name $(ZB_LIB_PATH=$PWD/$so timeout 120 python scripts/variant_probe.py ${2:-6} 2>&1 | tail -1)"
+  echo "== $name $(ZB_LIB_PATH=$PWD/$so timeout 60 python scripts/variant_probe.py ${2:-6} 2>&1 | tail -1)"
 done 2>&1 | tee gpurun_out/sweep_${1:-s}.log

@@ -9,6 +9,12 @@
 #include "zb_kernels.cuh"
 #include "zb_engine_internal.h"
 
+#ifndef ZB_TAIL_TILES
+#define ZB_TAIL_TILES 2   // at most this many dirty tiles: the smallest pieces (a sparse pass is bounded by its slowest piece)
+#endif
+#ifndef ZB_TAIL_SUB
+#define ZB_TAIL_SUB 512
+#endif
 namespace zb {
 
 thread_local char g_err[256] = "";
@@ -465,7 +471,7 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     // bounded by its slowest piece, not by throughput.
                     uint32_t mthreads = 1024;
                     if (iters == 1) jb.match_sub = ZB_MATCH_CTX ? 8192 : 4096; // context schedule: one CTA of 1024 threads per SM
-                    else if (n_dirty <= 2) { jb.match_sub = 512; mthreads = 256; }
+                    else if (n_dirty <= ZB_TAIL_TILES) { jb.match_sub = ZB_TAIL_SUB; mthreads = 256; }
                     else {
                         const uint64_t per_cta = (uint64_t)n_dirty * kMatchTile / (4 * 148);
                         jb.match_sub = per_cta >= 8192 ? 8192 : per_cta >= 4096 ? 4096 : per_cta >= 2048 ? 2048 : 1024;

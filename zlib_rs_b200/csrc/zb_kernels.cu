@@ -250,23 +250,37 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
     // Chains are per hash bucket, and only buckets in which a hole changed (in this tile or the one before it: the staged span) can
     // have different bridged links than Lr already holds: everything below touches only positions of those buckets.  In the first
     // iterations that is nearly every position, in the last ones a few hundred.
-    for (uint32_t i = tid; i < ((span + 31) & ~31u); i += 1024) {
-        bool f = false;
-        if (i < span) { const uint32_t key = jb.keys[ws + i]; f = (sbm[key >> 5] >> (key & 31u)) & 1u; }
-        const uint32_t m = __ballot_sync(0xffffffffu, f);
-        if ((tid & 31u) == 0) sf[i >> 5] = m;
+    {   // eight keys per load (ws is a multiple of 32 KiB: aligned); four lanes make one bitmap word
+        const uint4 *kp = reinterpret_cast<const uint4 *>(jb.keys + ws);
+        const uint32_t ngrp = ((span + 31) & ~31u) / 8, ngrp_w = (ngrp + 31) & ~31u; // whole warps take part in the shuffles below
+#pragma unroll 4
+        for (uint32_t g = tid; g < ngrp_w; g += 1024) {
+            const bool valid = g < ngrp;
+            const uint4 kv = valid ? kp[g] : make_uint4(0, 0, 0, 0); // keys behind the input belong to positions whose links are 0
+            const uint32_t k[8] = {kv.x & 0xffffu, kv.x >> 16, kv.y & 0xffffu, kv.y >> 16, kv.z & 0xffffu, kv.z >> 16, kv.w & 0xffffu, kv.w >> 16};
+            uint32_t b = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) b |= ((sbm[k[j] >> 5] >> (k[j] & 31u)) & 1u) << j;
+            b <<= 8 * (tid & 3u);
+            b |= __shfl_xor_sync(0xffffffffu, b, 1);
+            b |= __shfl_xor_sync(0xffffffffu, b, 2);
+            if (valid && (tid & 3u) == 0) sf[g >> 2] = b;
+        }
     }
     __syncthreads();
     // Pointer jumping over the staged window.  Measured alternatives (r2e, r2h): visiting only the set bits of the hole bitmap
     // (0.13 instead of 0.07..0.11 ms per launch) and one serial walk per position through the holes (0.62 ms on the hole-dense
     // tiles of the first iterations) were both slower than this dense sweep.
-    // Thread tid owns the positions tid + 1024 k, i.e. lane `lane` of the bitmap words warp + 32 k: a warp first notes which of its
-    // 64 words hold a hole in play at all (two ballots), and the rounds visit only those -- in the last iterations a handful.
+    // Warp w owns the bitmap words [64 w, 64 w + 64), lane l the bit l of each; it first notes which of its words hold a hole in
+    // play at all (two ballots) and then visits only those, IN ASCENDING ORDER and each until it is stable: a jump is extended by the
+    // jump of its target, and targets lie below -- within the warp's range they are final by the time they are used, so a chain
+    // through a run of holes is bridged in one round instead of log2(run) rounds (hops inside one word: the repetition).  What
+    // remains for further rounds are chains that cross into another warp's range.
     const uint32_t lane = tid & 31, warp = tid >> 5, nwords = (span + 31) / 32;
     uint32_t nz[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const uint32_t w = warp + 32 * (lane + 32 * h);
+        const uint32_t w = warp * 64 + lane + 32 * h;
         nz[h] = __ballot_sync(0xffffffffu, w < nwords && (sh[w] & sf[w]) != 0);
     }
     for (uint32_t round = 0; round < 24; round++) {
@@ -275,18 +289,27 @@ __global__ void __launch_bounds__(1024) k_skip(JobBufs jb)
         for (int h = 0; h < 2; h++) {
             uint32_t m = nz[h];
             while (m) {
-                const uint32_t w = warp + 32 * ((__ffs(m) - 1) + 32 * h);
+                const uint32_t w = warp * 64 + (__ffs(m) - 1) + 32 * h;
                 m &= m - 1;
-                if (!(((sh[w] & sf[w]) >> lane) & 1u)) continue;
                 const uint32_t i = w * 32 + lane;
-                if (i >= span) continue;
-                const uint32_t d = sL[i];
-                if (d == 0 || d > i) continue;          // chain ends, or leaves the staged window
-                const uint32_t t = i - d;
-                if (!((sh[t >> 5] >> (t & 31)) & 1u)) continue; // already at an inserted position
-                const uint32_t d2 = sL[t];
-                sL[i] = (uint16_t)((d2 == 0 || d + d2 > md) ? 0u : d + d2);
-                ch = 1;
+                const bool on = (((sh[w] & sf[w]) >> lane) & 1u) && i < span;
+                for (int rep = 0; rep < 6; rep++) {
+                    bool c = false;
+                    if (on) {
+                        const uint32_t d = sL[i];
+                        if (d != 0 && d <= i) {             // else: the chain ends, or leaves the staged window
+                            const uint32_t t = i - d;
+                            if ((sh[t >> 5] >> (t & 31)) & 1u) { // not yet at an inserted position
+                                const uint32_t d2 = sL[t];
+                                sL[i] = (uint16_t)((d2 == 0 || d + d2 > md) ? 0u : d + d2);
+                                c = true;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (!__any_sync(0xffffffffu, c)) break;
+                    ch = 1;
+                }
             }
         }
         if (!__syncthreads_or(ch)) break;
@@ -336,6 +359,13 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 #ifndef ZB_SECOND_LOOK
 #define ZB_SECOND_LOOK 1
 #endif
+#ifndef ZB_CMP16
+#define ZB_CMP16 0 // 16 bytes per compare step instead of 8: measured equal (r3a: 9.01 vs 8.98 ms), the simpler one stays
+#endif
+#ifndef ZB_DRAIN
+#define ZB_DRAIN 0 // with the piece used up and at most this many lanes of a warp still walking, the warp shares their walks (0: off).
+                   // Measured (r2y): 8 changes nothing (9.26 vs 9.23 ms), 32 costs 4 ms -- off
+#endif
 #ifndef ZB_COOP_CMP
 #define ZB_COOP_CMP 4 // stragglers: with at most this many lanes still busy, the warp finishes a long compare together
                       // (256 bytes per step).  Offering it to every compare burst was measured slower (r2p: +0.26 ms at 12 lanes).
@@ -379,6 +409,67 @@ __device__ __forceinline__ void sld_u64u(uint32_t a, uint32_t &lo, uint32_t &hi)
     const uint32_t w0 = sld_u32(al), w1 = sld_u32(al + 4), w2 = sld_u32(al + 8);
     lo = __funnelshift_r(w0, w1, sh);
     hi = __funnelshift_r(w1, w2, sh);
+}
+
+// The drain of match_tile_fast (see there): the walks of the lanes in `todo`, one at a time, each shared by the warp.  Kept out of
+// line so that its registers do not weigh on the walk loop.
+__device__ __noinline__ void drain_walks(uint32_t todo, uint32_t dbase, uint32_t lbase, uint32_t nice, uint32_t xr, uint32_t lowr,
+                                         uint32_t cr, uint32_t best, uint32_t chain, uint32_t &res, uint32_t &rd)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    while (todo) {
+        const uint32_t src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t w_xr = __shfl_sync(0xffffffffu, xr, src), w_lowr = __shfl_sync(0xffffffffu, lowr, src);
+        uint32_t w_cr = __shfl_sync(0xffffffffu, cr, src), w_best = __shfl_sync(0xffffffffu, best, src);
+        uint32_t w_chain = __shfl_sync(0xffffffffu, chain, src), w_res = __shfl_sync(0xffffffffu, res, src), w_rd = 0;
+        for (;;) {
+            // list up to 32 candidates (lane k keeps the k-th)
+            const uint32_t lim = w_chain < 32u ? w_chain : 32u;
+            uint32_t n = 0, mycand = 0, c = w_cr;
+            bool ended = false;
+            for (uint32_t k = 0; k < lim; k++) {
+                if (lane == k) mycand = c;
+                n = k + 1;
+                const uint32_t d = sld_u16(lbase + 2 * c);
+                if (c < w_lowr + d) { ended = true; break; } // the chain ends or leaves the window behind this candidate
+                c -= d;
+            }
+            // common prefix of x and this lane's candidate (only if it can be longer than the best so far)
+            uint32_t len = 0;
+            if (lane < n && sld_u8(dbase + w_best + mycand) == sld_u8(dbase + w_best + w_xr)) {
+                uint32_t pa = dbase + w_xr, pb = dbase + mycand;
+                for (;;) {
+                    uint32_t a0, a1, b0, b1;
+                    sld_u64u(pa, a0, a1);
+                    sld_u64u(pb, b0, b1);
+                    const uint32_t d0 = a0 ^ b0, d1 = a1 ^ b1;
+                    if (d0 | d1) { len += d0 ? ((__ffs(d0) - 1) >> 3) : 4u + ((__ffs(d1) - 1) >> 3); break; }
+                    len += 8; pa += 8; pb += 8;
+                    if (len >= kMaxMatch) break;
+                }
+                if (len > kMaxMatch) len = kMaxMatch;
+            }
+            uint32_t pm = (lane < n && len > w_best) ? len : w_best; // inclusive prefix maximum in chain order
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pm, d); if (lane >= (uint32_t)d && t > pm) pm = t; }
+            const uint32_t stopm = __ballot_sync(0xffffffffu, lane < n && pm >= nice);
+            const uint32_t e = stopm ? __ffs(stopm) - 1 : n - 1; // the last candidate the serial walk would look at
+            const uint32_t nb = __shfl_sync(0xffffffffu, pm, e);
+            if (nb > w_best) {
+                const uint32_t k0 = __ffs(__ballot_sync(0xffffffffu, lane <= e && len == nb)) - 1; // the first one that long
+                w_res = (nb << 16) | (w_xr - __shfl_sync(0xffffffffu, mycand, k0));
+                w_best = nb;
+            }
+            const uint32_t cand_e = __shfl_sync(0xffffffffu, mycand, e);
+            if (stopm) { w_rd = w_xr - cand_e; break; }
+            w_chain -= n;
+            if (w_chain == 0) { w_rd = (w_xr - cand_e) | 0x8000u; break; } // budget
+            if (ended) { w_rd = 0xffffu; break; }
+            w_cr = c;
+        }
+        if (lane == src) { res = w_res; rd = w_rd; }
+    }
 }
 
 // Schedule: a lane is IDLE (needs a position), WALKing its chain, PENDing a compare with the candidate it stopped at, or FINished
@@ -501,6 +592,27 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             bool resolved = false;
             if (state == LS_PEND) {
                 uint32_t pa = dbase + xr + clen, pb = dbase + cr + clen;
+#if ZB_CMP16
+                // 16 bytes per step: five aligned words and four funnel shifts per side (a long compare is a chain of dependent
+                // steps: half as many of them)
+#pragma unroll 1
+                for (uint32_t k = 0; k < kCmpBurst / 2; k++) {
+                    const uint32_t ala = pa & ~3u, sha = (pa & 3u) * 8u, alb = pb & ~3u, shb = (pb & 3u) * 8u;
+                    const uint32_t x0 = sld_u32(ala), x1 = sld_u32(ala + 4), x2 = sld_u32(ala + 8), x3 = sld_u32(ala + 12), x4 = sld_u32(ala + 16);
+                    const uint32_t y0 = sld_u32(alb), y1 = sld_u32(alb + 4), y2 = sld_u32(alb + 8), y3 = sld_u32(alb + 12), y4 = sld_u32(alb + 16);
+                    const uint32_t d0 = __funnelshift_r(x0, x1, sha) ^ __funnelshift_r(y0, y1, shb);
+                    const uint32_t d1 = __funnelshift_r(x1, x2, sha) ^ __funnelshift_r(y1, y2, shb);
+                    const uint32_t d2 = __funnelshift_r(x2, x3, sha) ^ __funnelshift_r(y2, y3, shb);
+                    const uint32_t d3 = __funnelshift_r(x3, x4, sha) ^ __funnelshift_r(y3, y4, shb);
+                    if ((d0 | d1 | d2 | d3) != 0 || clen + 16 >= kMaxMatch) {
+                        len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3)
+                            : d2 ? clen + 8 + ((__ffs(d2) - 1) >> 3) : d3 ? clen + 12 + ((__ffs(d3) - 1) >> 3) : clen + 16;
+                        resolved = true;
+                        break;
+                    }
+                    clen += 16; pa += 16; pb += 16;
+                }
+#else
 #pragma unroll 1
                 for (uint32_t k = 0; k < kCmpBurst; k++) {
                     uint32_t a0, a1, b0, b1;
@@ -514,6 +626,7 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
                     }
                     clen += 8; pa += 8; pb += 8;
                 }
+#endif
             }
 #if ZB_COOP_CMP
             {
@@ -573,6 +686,13 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
         const uint32_t m_idle = __ballot_sync(0xffffffffu, state == LS_IDLE);
         const uint32_t m_busy = __ballot_sync(0xffffffffu, state == LS_WALK || state == LS_PEND);
         if ((m_idle | m_busy) == 0) break; // every lane is done
+#if ZB_DRAIN
+        // ---- the piece has no more positions to hand out and only a few lanes of this warp still walk: leave the loop, the warp
+        // shares those walks (below)
+        if (m_busy && __popc(m_busy) <= ZB_DRAIN && *reinterpret_cast<volatile uint32_t *>(s_next) >= te &&
+            __ballot_sync(0xffffffffu, state == LS_PEND) == 0)
+            break;
+#endif
         if (m_idle == 0) continue;
         if (__popc(m_idle) < (int)kBatch && m_busy != 0) continue;
         {
@@ -644,6 +764,25 @@ __device__ __forceinline__ void match_tile_fast(const JobBufs &jb, const uint8_t
             }
         }
     }
+#if ZB_DRAIN
+    // ---- drain.  A long walk of one lane (a hundred candidates with compares of a hundred bytes each: tens of thousands of cycles)
+    // would keep the warp -- in the sparse pieces of the later iterations the whole launch -- waiting, so the warp takes the
+    // remaining walks one at a time and works on each TOGETHER: 32 chain candidates are listed by a uniform walk over the links,
+    // every lane compares one of them completely, and the sequential rule (a candidate counts iff it is strictly longer than
+    // everything before it; the first one reaching nice_match ends the walk; the budget counts candidates) is a prefix maximum
+    // over the lanes (drain_walks).
+    {
+        const uint32_t m_left = __ballot_sync(0xffffffffu, state == LS_WALK);
+        if (m_left) {
+            uint32_t o_res = res, o_rd = 0;
+            drain_walks(m_left, dbase, lbase, nice, xr, lowr, cr, best, chain, o_res, o_rd);
+            if (state == LS_WALK) {
+                if (filt && Mout[xr] != o_res) jb.mchg[(ws + xr) >> 6] = 1;
+                Mout[xr] = o_res; RDout[xr] = (uint16_t)o_rd;
+            }
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1116,9 +1255,22 @@ constexpr uint32_t kPathSmem = kPathTile * 4 * 3;
 // Stage nxt of the tile; positions at or beyond tail_start behave as tail entries.
 __device__ __forceinline__ void path_load(const JobBufs &jb, uint32_t tbeg, uint32_t *nx)
 {
-    for (uint32_t i = threadIdx.x; i < kPathTile; i += blockDim.x) {
-        const uint32_t p = tbeg + i;
-        nx[i] = p < jb.tail_start ? jb.nxt[p] : (kNxtTail | 1u);
+    // four entries per load, the loads of a thread in flight together (one element at a time a thread waits for every single one)
+    const uint4 *src = reinterpret_cast<const uint4 *>(jb.nxt + tbeg);
+    uint4 *dst = reinterpret_cast<uint4 *>(nx);
+#pragma unroll 4
+    for (uint32_t g = threadIdx.x; g < kPathTile / 4; g += blockDim.x) {
+        const uint32_t p = tbeg + 4 * g;
+        uint4 v;
+        if (p + 3 < jb.tail_start) v = src[g];
+        else {
+            const uint32_t t = kNxtTail | 1u;
+            v.x = p < jb.tail_start ? jb.nxt[p] : t;
+            v.y = p + 1 < jb.tail_start ? jb.nxt[p + 1] : t;
+            v.z = p + 2 < jb.tail_start ? jb.nxt[p + 2] : t;
+            v.w = t;
+        }
+        dst[g] = v;
     }
 }
 
