@@ -51,8 +51,8 @@ __global__ void k_encode(JobBufs);
 __global__ void k_finish(JobBufs, const uint32_t *);
 __global__ void k_literal_syms(JobBufs);
 __global__ void k_stored(JobBufs);
-__global__ void k_links2_std(JobBufs);
-__global__ void k_links2_roll(JobBufs);
+__global__ void k_links2_std(JobBufs, uint32_t);
+__global__ void k_links2_roll(JobBufs, uint32_t);
 __global__ void k_links_fix_std(JobBufs);
 __global__ void k_links_fix_roll(JobBufs);
 __global__ void k_slow(JobBufs);
@@ -88,6 +88,8 @@ int Engine::init(int dev)
     CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&evf, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
+    for (int i = 0; i < kUpChunks; i++) CK(cudaEventCreateWithFlags(&evc[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&evk, cudaEventDisableTiming));
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(upload_tables());
@@ -122,6 +124,8 @@ Engine::~Engine()
     if (ev1) cudaEventDestroy(ev1);
     if (evf) cudaEventDestroy(evf);
     if (evt) cudaEventDestroy(evt);
+    for (int i = 0; i < kUpChunks; i++) if (evc[i]) cudaEventDestroy(evc[i]);
+    if (evk) cudaEventDestroy(evk);
     if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
 }
@@ -370,6 +374,26 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
 
     CK(cudaEventRecord(ev0, st));
     if (profile) { for (int i = 0; i < kPhases; i++) { phase_ms[i] = 0; phase_launches[i] = 0; } }
+    // A host input of some size for the chain-based levels arrives in chunks on the second stream; the link pass of a tile starts
+    // as soon as its bytes are there (the upload of 15.7 MB takes 0.6 ms, the link pass 0.4: they overlap instead of adding up).
+    uint32_t up_chunks = 0;
+    size_t up_len[kUpChunks] = {0};
+    static const bool up_off = getenv("ZB_UPLOAD_CHUNKED") && atoi(getenv("ZB_UPLOAD_CHUNKED")) == 0; // measurement switch
+    const bool chunked_upload = !up_off && !src_dev && !dstart && n_in >= ((size_t)4 << 20) && level != 0 && !jb.huffman_only &&
+                                !jb.serial_mode && jb.slow_mode != 2;
+    if (chunked_upload) {
+        // a chunk is at least one wave of the link kernel (one CTA per tile and SM): smaller launches only add CTA latencies
+        size_t chunk = (n_in / kUpChunks + kLinkTile - 1) / kLinkTile * kLinkTile;
+        if (chunk < (size_t)148 * kLinkTile) chunk = (size_t)148 * kLinkTile;
+        CK(cudaStreamWaitEvent(st2, ev0, 0));
+        for (size_t off = 0; off < n_in; off += chunk) {
+            const size_t len = n_in - off < chunk ? n_in - off : chunk;
+            CK(cudaMemcpyAsync(d_in + off, static_cast<const uint8_t *>(src) + off, len, cudaMemcpyHostToDevice, st2));
+            if (off + len == n_in) CK(cudaMemsetAsync(d_in + n, 0, kPad, st2));
+            CK(cudaEventRecord(evc[up_chunks], st2));
+            up_len[up_chunks++] = off + len;
+        }
+    } else
     if (!src_dev || dstart) {
         pbegin();
         if (dstart) CK(cudaMemcpyAsync(d_in, dict, dstart, src_dev ? cudaMemcpyDefault : cudaMemcpyHostToDevice, st));
@@ -384,12 +408,31 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
         CK(cudaMemcpyAsync(d_out, &h_prime, 1, cudaMemcpyHostToDevice, st));
     }
     // checksum of the input (deflate.rs:1705-1713 computes it while filling the window)
+    cudaStream_t st_ck = chunked_upload ? st2 : st; // chunked upload: behind the last chunk on st2, beside the link pass
     pbegin();
-    if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in + dstart, n_in, 1, d_ck, ck_bytes, d_check, st)); launches += 2; }
-    else if (wrap == 2 || (wrap == 0 && (flags & ZB_FLAG_CHECK_CRC))) { CK(launch_crc32(d_in + dstart, n_in, 0, d_ck, ck_bytes, d_check, st)); launches += 2; }
-    else CK(cudaMemsetAsync(d_check, 0, 4, st));
+    if (wrap == 1 || (wrap == 0 && (flags & ZB_FLAG_CHECK_ADLER))) { CK(launch_adler32(d_in + dstart, n_in, 1, d_ck, ck_bytes, d_check, st_ck)); launches += 2; }
+    else if (wrap == 2 || (wrap == 0 && (flags & ZB_FLAG_CHECK_CRC))) { CK(launch_crc32(d_in + dstart, n_in, 0, d_ck, ck_bytes, d_check, st_ck)); launches += 2; }
+    else CK(cudaMemsetAsync(d_check, 0, 4, st_ck));
+    if (chunked_upload) CK(cudaEventRecord(evk, st2));
     pend(8, 2);
 
+    // the link pass, tile by tile as the chunks of a host input arrive (or all tiles at once)
+    auto links_tiles = [&](bool roll) {
+        uint32_t t_done = 0;
+        for (uint32_t k = 0; k < (chunked_upload ? up_chunks : 1u); k++) {
+            uint32_t t_hi = nmt;
+            if (chunked_upload) {
+                cudaStreamWaitEvent(st, evc[k], 0);
+                if (k + 1 < up_chunks) t_hi = up_len[k] >= 64 ? (uint32_t)((up_len[k] - 64) / kLinkTile) : 0; // a tile reads 16 bytes past its end
+            }
+            if (t_hi <= t_done) continue;
+            if (roll) k_links2_roll<<<t_hi - t_done, 1024, kLinks2SmemBytes, st>>>(jb, t_done);
+            else k_links2_std<<<t_hi - t_done, 1024, kLinks2SmemBytes, st>>>(jb, t_done);
+            if (k) launches++;
+            t_done = t_hi;
+        }
+        if (chunked_upload) cudaStreamWaitEvent(st, evk, 0); // the checksum
+    };
     uint32_t iters = 0;
     if (level == 0) {
         const uint32_t nb = n_in == 0 ? 1 : (uint32_t)((n_in + 65534) / 65535);
@@ -418,11 +461,11 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
             if (jb.slow_mode == 2) {
                 // no hash chains
             } else if (jb.slow_mode && jb.sp.slow) {
-                k_links2_roll<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
+                links_tiles(true);
                 k_links_fix_roll<<<N / 256 + 1, 256, 0, st>>>(jb);
                 launches += 2;
             } else {
-                k_links2_std<<<nmt, 1024, kLinks2SmemBytes, st>>>(jb);
+                links_tiles(false);
                 k_links_fix_std<<<N / 256 + 1, 256, 0, st>>>(jb);
                 launches += 2;
                 if (dstart >= 3 && n_in) {

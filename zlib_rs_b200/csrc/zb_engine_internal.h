@@ -18,6 +18,9 @@ struct Engine {
     cudaStream_t st = nullptr, st2 = nullptr; // st2: the serial tail runs beside k_emit
     cudaEvent_t evf = nullptr, evt = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    static constexpr int kUpChunks = 8;
+    cudaEvent_t evk = nullptr;              // ... and the checksum behind the last chunk, also on st2
+    cudaEvent_t evc[kUpChunks] = {nullptr}; // chunks of a host input arriving on st2 while the link pass already runs on st
     Buf bufs[kSlots];
     void *h_stage = nullptr;
     size_t h_stage_cap = 0;

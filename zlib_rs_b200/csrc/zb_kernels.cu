@@ -98,8 +98,9 @@ __device__ __forceinline__ uint32_t lds_u32(const uint32_t *words, uint32_t byte
 constexpr uint32_t kFirstFlag = 0xffffu; // L value of a first occurrence until k_links_fix has seen it
 
 template <bool kRoll>
-__device__ __forceinline__ void links2_body(const JobBufs &jb)
+__device__ __forceinline__ void links2_body(const JobBufs &jb, uint32_t tile0)
 {
+    const uint32_t tile = tile0 + blockIdx.x; // a host input is linked chunk by chunk as it arrives
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
     uint16_t *head = reinterpret_cast<uint16_t *>(smem);                 // kKeys entries: 1 + position in the tile
@@ -110,7 +111,7 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
-    const uint32_t ts = blockIdx.x * kLinkTile;
+    const uint32_t ts = tile * kLinkTile;
     const uint32_t te = min(ts + kLinkTile, N);
     const uint32_t tv = N >= need ? min(te, N - need + 1) : ts; // positions with enough bytes to hash
     for (uint32_t i = tid; i < kKeys / 2; i += 1024) reinterpret_cast<uint32_t *>(head)[i] = 0;
@@ -185,7 +186,7 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb)
     }
     for (uint32_t x = tv + tid; x < te; x += 1024) jb.L[x] = 0; // positions without enough input are never hashed
     __syncthreads();
-    uint4 *out = reinterpret_cast<uint4 *>(jb.link_last + (size_t)blockIdx.x * kKeys);
+    uint4 *out = reinterpret_cast<uint4 *>(jb.link_last + (size_t)tile * kKeys);
     const uint4 *hv = reinterpret_cast<const uint4 *>(head);
     for (uint32_t i = tid; i < kKeys * 2 / 16; i += 1024) out[i] = hv[i];
 }
@@ -211,8 +212,8 @@ __device__ __forceinline__ void links_fix_body(const JobBufs &jb)
     jb.L[x] = (uint16_t)d;
 }
 
-__global__ void __launch_bounds__(1024) k_links2_std(JobBufs jb) { links2_body<false>(jb); }
-__global__ void __launch_bounds__(1024) k_links2_roll(JobBufs jb) { links2_body<true>(jb); }
+__global__ void __launch_bounds__(1024) k_links2_std(JobBufs jb, uint32_t tile0) { links2_body<false>(jb, tile0); }
+__global__ void __launch_bounds__(1024) k_links2_roll(JobBufs jb, uint32_t tile0) { links2_body<true>(jb, tile0); }
 __global__ void __launch_bounds__(256) k_links_fix_std(JobBufs jb) { links_fix_body<false>(jb); }
 __global__ void __launch_bounds__(256) k_links_fix_roll(JobBufs jb) { links_fix_body<true>(jb); }
 
