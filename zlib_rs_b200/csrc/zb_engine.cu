@@ -9,6 +9,9 @@
 #include "zb_kernels.cuh"
 #include "zb_engine_internal.h"
 
+#ifndef ZB_SLOW_SUB9
+#define ZB_SLOW_SUB9 24576u
+#endif
 #ifndef ZB_TAIL_TILES
 #define ZB_TAIL_TILES 2   // at most this many dirty tiles: the smallest pieces (a sparse pass is bounded by its slowest piece)
 #endif
@@ -67,7 +70,8 @@ constexpr uint32_t kMatchSmemBytes = (kWSize + kMatchSub + 512) + (kWSize + kMat
 constexpr uint32_t kPathSmemBytes = kPathTile * 4 * 3;
 constexpr uint32_t kLinks2SmemBytes = 65536 * 2 + kLinkTile * 2 + kLinkTile + 64 + 2048;
 constexpr uint32_t kSkipSmemBytes = 2 * kWSize * 2 + 2 * (2 * kWSize / 32) * 4 + 8192 + 64; // links, hole + bucket-flag bitmaps, bucket map
-constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSub + kSlowAhead) * 3;
+constexpr uint32_t kSlowSubMax = 24576;
+constexpr uint32_t kSlowSmemBytes = (kWSize + kSlowSubMax + kSlowAhead) * 3;
 constexpr uint32_t kChainSmemBytes = kChainChunkTiles * kPathHead * 8;
 constexpr uint32_t kChain2MaxSmem = 200 * 1024; // two-level chain: group heads + transfer functions of the groups
 constexpr uint32_t kSerialSmemBytes = (65536 + kWSize) * 2 + 35824 + 16; // head + prev tables of one stream + the input ring (level 2)
@@ -483,7 +487,13 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                     iters = 1;
                     pbegin();
                     if (jb.slow_mode == 2) k_rle<<<(N + 255) / 256, 256, 0, st>>>(jb);
-                    else k_slow<<<(N + kSlowSub - 1) / kSlowSub, 1024, kSlowSmemBytes, st>>>(jb);
+                    else {
+                        // positions per CTA.  A CTA lasts about as long as its most expensive node (at level 9 single lazy chains
+                        // cost milliseconds), so the level with the longest searches takes the largest pieces (measured, r3g/r3h)
+                        static const char *e_ss = getenv("ZB_SLOW_SUB");
+                        jb.match_sub = e_ss ? (uint32_t)atoi(e_ss) : level >= 9 ? ZB_SLOW_SUB9 : level == 8 ? 4096u : 8192u;
+                        k_slow<<<(N + jb.match_sub - 1) / jb.match_sub, 1024, (kWSize + jb.match_sub + kSlowAhead) * 3, st>>>(jb);
+                    }
                     pend(1, 1);
                     if (profile) phase_ms[11] = phase_ms[1];
                     pbegin();

@@ -349,7 +349,7 @@ constexpr uint32_t kMatchSmem = kMatchData + (kWSize + kMatchSub) * 2 + ((kWSize
 #define ZB_T_IDLE 8
 #endif
 #ifndef ZB_T_CMP
-#define ZB_T_CMP 4
+#define ZB_T_CMP 2
 #endif
 #ifndef ZB_WALK_BURST
 #define ZB_WALK_BURST 8

@@ -34,7 +34,10 @@ constexpr uint32_t kNxtTail = 0x80000000u; // nxt flag: the macro step reaches t
 constexpr uint32_t kNxtLong = 0x40000000u; // nxt flag: the macro step emits a match longer than 16*max_lazy (leaves holes)
 constexpr uint32_t kNxtLong258 = 0x20000000u; // ... and that match is 258 bytes long (levels 5/6: 257 otherwise)
 constexpr uint32_t kSymsPerThread = 16;
-constexpr uint32_t kSlowSub = 8192;     // positions per k_slow CTA
+#ifndef ZB_SLOW_SUB
+#define ZB_SLOW_SUB 8192
+#endif
+constexpr uint32_t kSlowSub = ZB_SLOW_SUB; // positions per k_slow CTA
 constexpr uint32_t kSlowAhead = 1024;   // bytes/links staged behind the last position of a k_slow CTA (<= kPad)
 
 struct JobInfo {              // device-resident result / control block of one deflate job

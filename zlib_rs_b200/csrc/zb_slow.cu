@@ -45,6 +45,10 @@ __device__ __forceinline__ uint32_t qld_u32u(uint32_t a) // unaligned
 
 constexpr uint32_t kSlowSafe = 1024; // nodes this close to the end of the input take the generic slow_step()
 constexpr uint32_t kSlowBatch = 8;
+#ifndef ZB_COOP_START
+#define ZB_COOP_START 16
+#endif
+constexpr uint32_t kCoopStart = ZB_COOP_START; // prev_length from which the warp shares a lane's re-rooting scan (level 9)
 #ifndef ZB_SLOW_BURST
 #define ZB_SLOW_BURST 8
 #endif
@@ -61,7 +65,8 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_next;
-    const uint32_t sub = kSlowSub;
+    __shared__ uint32_t s_tab[32][256]; // level 9: one re-rooting table per warp (the shared START scan)
+    const uint32_t sub = jb.match_sub; // positions per CTA: chosen by level (zb_engine.cu)
     const uint32_t ts = blockIdx.x * sub;
     const uint32_t N = jb.N;
     if (ts >= N) return;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
     const uint32_t ws = ts >= kWSize ? ts - kWSize : 0;
     const uint32_t span = te + kSlowAhead - ws; // <= kWSize + sub + kSlowAhead
     uint8_t *sdata = smem;
-    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kWSize + kSlowSub + kSlowAhead);
+    uint16_t *sL = reinterpret_cast<uint16_t *>(smem + kWSize + sub + kSlowAhead);
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_next = ts;
     {
@@ -175,9 +180,10 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
         // START/PEND lanes do not wait for the walkers when few lanes are busy at all
         const uint32_t thr = min(kSlowBatch, max(1u, (uint32_t)__popc(m_start | m_walk | m_pend) / 4u));
         if (m_start && (__popc(m_start) >= (int)thr || m_walk == 0)) {
+            // slow.rs:56-82 preconditions (lookahead >= 262 here)
+            bool search = false, big = false;
             if (state == SS_START) {
-                // slow.rs:56-82 preconditions (lookahead >= 262 here)
-                bool search = l < sp.lazy;
+                search = l < sp.lazy;
                 uint32_t hh = 0;
                 if (search) {
                     const uint32_t d = qld_u16(ladj + 2 * q);
@@ -193,21 +199,69 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                     limit = limit_base;
                     mo = 0;
                     cur = hh;
-                    bool ended = false;
-                    if (sp.slow && best >= 3) {
+                    big = best >= kCoopStart;
+                }
+            }
+            // The re-rooting scan of longest_match.rs:87-124 asks, for every 3-byte window of the string, where its hash chain enters
+            // the part of the input the parser has seen (head_at).  Done one window after the other that is up to 256 walks of up to
+            // 256 hops each on repetitive data (a third of all instructions of the level-9 kernel, and the reason a few CTAs ran
+            // five times longer than the average).  For a long string the warp does the scan of one lane together: the first hops of
+            // all windows go into a table, hops that land on a later window are resolved through the table (pointer jumping, in
+            // ascending chunks of 32), the minimum with its first index is a warp reduction.
+            {
+                uint32_t mb = __ballot_sync(0xffffffffu, big);
+                uint32_t *tab = s_tab[tid >> 5];
+                while (mb) {
+                    const uint32_t src = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const uint32_t w_q = __shfl_sync(0xffffffffu, q, src), w_B = __shfl_sync(0xffffffffu, B, src);
+                    const uint32_t n = __shfl_sync(0xffffffffu, best, src) - 2; // windows q+1 .. q+n
+                    uint32_t run_min = __shfl_sync(0xffffffffu, cur, src), run_mo = 0;
+                    for (uint32_t j = lane; j < n; j += 32) {
+                        const uint32_t x = w_q + 1 + j, d = qld_u16(ladj + 2 * x);
+                        tab[j] = d ? x - d : 0u; // 0: no link (reads as the window base)
+                    }
+                    __syncwarp();
+                    for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+                        const uint32_t j = c0 + lane;
+                        const bool valid = j < n;
+                        uint32_t v = valid ? tab[j] : 0u;
+                        for (int rep = 0; rep < 7; rep++) { // entries below this chunk are final; inside it a hop may need five more
+                            const bool hop = v > w_q;
+                            if (hop) v = tab[v - w_q - 1];
+                            __syncwarp();
+                            if (valid) tab[j] = v;
+                            __syncwarp();
+                            if (!__any_sync(0xffffffffu, hop)) break;
+                        }
+                        if (__any_sync(0xffffffffu, valid && v > w_q)) atomicOr(&jb.info->error, 64u); // cannot happen: 32 entries, 7 doublings
+                        const uint32_t pos = valid ? (v > w_B ? v : w_B) : 0xffffffffu;
+                        uint32_t m = pos;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+                        if (m < run_min) { run_min = m; run_mo = c0 + (__ffs(__ballot_sync(0xffffffffu, pos == m)) - 1) + 1; }
+                    }
+                    if (lane == src) { cur = run_min; mo = run_mo; }
+                    __syncwarp();
+                }
+            }
+            if (state == SS_START && search) {
+                bool ended = false;
+                if (sp.slow && best >= 3) {
+                    if (!big) {
                         for (uint32_t i = 0; i + 3 <= best; i++) {
                             const uint32_t pos = head_at(q + i + 1);
                             if (pos < cur) { mo = i + 1; cur = pos; }
                         }
-                        limit = limit_base + mo;
-                        ended = cur <= limit;
                     }
-                    if (ended) finish_search(best, mstart, true);
-                    else {
-                        xb = qld_u8(dadj + q + best);
-                        xw0 = qld_u32u(dadj + q);
-                        state = SS_WALK;
-                    }
+                    limit = limit_base + mo;
+                    ended = cur <= limit;
+                }
+                if (ended) finish_search(best, mstart, true);
+                else {
+                    xb = qld_u8(dadj + q + best);
+                    xw0 = qld_u32u(dadj + q);
+                    state = SS_WALK;
                 }
             }
             continue;
