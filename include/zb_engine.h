@@ -48,7 +48,8 @@ typedef struct zb_deflate_result {
     uint32_t carry;        /* END_PARTIAL / END_BLOCK: value of the partial last byte (its low bits_used bits), not part of the output */
 } zb_deflate_result;
 
-/* One engine = one CUDA device + stream + grow-only device buffers.  Not thread safe; create one per thread. */
+/* One engine = one CUDA device + stream + grow-only device buffers.  Not thread safe; create one per thread.
+ * Device sources (src_on_device = 1) need no padding and no alignment: the engine copies them into its own padded buffer. */
 ZB_API zb_engine *zb_engine_create(int device, int *err);
 ZB_API void zb_engine_destroy(zb_engine *e);
 ZB_API const char *zb_last_error(void);

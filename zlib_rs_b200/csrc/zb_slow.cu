@@ -48,6 +48,10 @@ constexpr uint32_t kSlowBatch = 8;
 #ifndef ZB_COOP_START
 #define ZB_COOP_START 16
 #endif
+#ifndef ZB_MONSTER
+#define ZB_MONSTER 0x7fffffff // off: measured (r3k, r3l) 64 -> 135 ms, 256..2048 -> 120..133 ms against 116..123 ms without, run-to-run spread 5 %
+#endif
+constexpr uint32_t kMonster = ZB_MONSTER; // candidates after which the warp takes over a lane's search (level 9; 0x7fffffff: never)
 constexpr uint32_t kCoopStart = ZB_COOP_START; // prev_length from which the warp shares a lane's re-rooting scan (level 9)
 #ifndef ZB_SLOW_BURST
 #define ZB_SLOW_BURST 8
@@ -267,8 +271,11 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
             continue;
         }
         if (m_pend && (__popc(m_pend) >= (int)thr || m_walk == 0)) {
+            // 1. every waiting lane: the full compare, and what it means for the search
+            uint32_t len = 0;
+            bool reroot = false; // a longer match whose chain is re-rooted (longest_match.rs:281-333)
             if (state == SS_PEND) {
-                uint32_t clen = 0, len;
+                uint32_t clen = 0;
                 const uint32_t pa = dadj + q, pb = dadj + cand;
                 for (;;) {
                     const uint32_t d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
@@ -285,38 +292,274 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                     if (best >= sp.nice) finish_search(best, mstart, true);
                     else {
                         xb = qld_u8(dadj + q + best);
-                        if (sp.slow && len > 3 && mstart + len < q) {
-                            // longest_match.rs:281-333
-                            cur = cand;
-                            mo = 0;
-                            uint32_t next_pos = cur;
-                            bool ended = false;
-                            for (uint32_t i = 0; i + 3 <= len; i++) {
-                                const uint32_t y = cur + i;
-                                const uint32_t d = qld_u16(ladj + 2 * y);
-                                const uint32_t pos = (d && y - d > B) ? y - d : B;
-                                if (pos < next_pos) {
-                                    if (pos <= limit_base + i) { ended = true; break; }
-                                    next_pos = pos;
-                                    mo = i;
-                                }
-                            }
-                            if (!ended) {
-                                cur = next_pos;
-                                const uint32_t pos = head_at(q + len - 4);
-                                if (pos < cur) {
-                                    mo = len - 4;
-                                    if (pos <= limit_base + mo) ended = true;
-                                    else cur = pos;
-                                }
-                            }
-                            if (ended) finish_search(best, mstart, true);
-                            else limit = limit_base + mo;
-                        } else next_in_chain();
+                        if (sp.slow && len > 3 && mstart + len < q) reroot = true;
+                        else next_in_chain();
                     }
                 } else next_in_chain();
             }
+            // 2. the re-rooting of a long match, shared by the warp, one lane's at a time.  Serially it is a scan over the len - 2
+            // windows of the match (one link each, a running minimum with an exit test at every new minimum) and one head_at() walk
+            // of up to len hops -- per ACCEPTED candidate, and on record-like data a search accepts hundreds: single lanes spent
+            // 10^8 cycles here and one SM stayed busy eight times as long as the average (profiles/r3_tail_iteration_digests.txt).
+            {
+                uint32_t mb = __ballot_sync(0xffffffffu, reroot && len >= kCoopStart);
+                uint32_t *tab = s_tab[tid >> 5];
+                while (mb) {
+                    const uint32_t src = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const uint32_t w_q = __shfl_sync(0xffffffffu, q, src), w_B = __shfl_sync(0xffffffffu, B, src);
+                    const uint32_t w_len = __shfl_sync(0xffffffffu, len, src), w_c = __shfl_sync(0xffffffffu, cand, src);
+                    const uint32_t w_lb = __shfl_sync(0xffffffffu, limit_base, src);
+                    // a. windows of the match: pos_i = prev[cand + i]; the first new minimum with pos_i <= limit_base + i ends the search
+                    uint32_t run_min = w_c, run_mo = 0;
+                    bool w_ended = false;
+                    const uint32_t n = w_len - 2;
+                    for (uint32_t c0 = 0; c0 < n && !w_ended; c0 += 32) {
+                        const uint32_t i = c0 + lane;
+                        uint32_t pos = 0xffffffffu;
+                        if (i < n) {
+                            const uint32_t y = w_c + i, d = qld_u16(ladj + 2 * y);
+                            pos = (d && y - d > w_B) ? y - d : w_B;
+                        }
+                        uint32_t ex = pos; // exclusive prefix minimum (with the running minimum): what next_pos is when i is looked at
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, ex, d); if (lane >= (uint32_t)d && t < ex) ex = t; }
+                        ex = __shfl_up_sync(0xffffffffu, ex, 1);
+                        if (lane == 0) ex = 0xffffffffu;
+                        if (run_min < ex) ex = run_min;
+                        const bool setter = i < n && pos < ex;
+                        const uint32_t m_end = __ballot_sync(0xffffffffu, setter && pos <= w_lb + i);
+                        const uint32_t m_set = __ballot_sync(0xffffffffu, setter);
+                        if (m_end) {
+                            w_ended = true;
+                        } else if (m_set) {
+                            const uint32_t last = 31 - __clz(m_set); // the last new minimum of the chunk = first index of its overall minimum
+                            run_min = __shfl_sync(0xffffffffu, pos, last);
+                            run_mo = c0 + last;
+                        }
+                    }
+                    uint32_t w_cur = run_min, w_mo = run_mo;
+                    if (!w_ended) {
+                        // b. head_at(q + len - 4): table of the first hops of the windows q+1 .. q+len-4, hops that land on a later
+                        // window resolved through the table (see START)
+                        const uint32_t nt = w_len - 4;
+                        for (uint32_t j = lane; j < nt; j += 32) {
+                            const uint32_t x = w_q + 1 + j, d = qld_u16(ladj + 2 * x);
+                            tab[j] = d ? x - d : 0u;
+                        }
+                        __syncwarp();
+                        uint32_t hv = 0;
+                        for (uint32_t c0 = 0; c0 < nt; c0 += 32) {
+                            const uint32_t j = c0 + lane;
+                            const bool valid = j < nt;
+                            uint32_t v = valid ? tab[j] : 0u;
+                            for (int rep = 0; rep < 7; rep++) {
+                                const bool hop = v > w_q;
+                                if (hop) v = tab[v - w_q - 1];
+                                __syncwarp();
+                                if (valid) tab[j] = v;
+                                __syncwarp();
+                                if (!__any_sync(0xffffffffu, hop)) break;
+                            }
+                            if (__any_sync(0xffffffffu, valid && v > w_q)) atomicOr(&jb.info->error, 64u);
+                            if (c0 + 32 >= nt) hv = __shfl_sync(0xffffffffu, v, (nt - 1) & 31u);
+                        }
+                        const uint32_t pos = hv > w_B ? hv : w_B;
+                        if (pos < w_cur) {
+                            w_mo = w_len - 4;
+                            if (pos <= w_lb + w_mo) w_ended = true;
+                            else w_cur = pos;
+                        }
+                    }
+                    if (lane == src) {
+                        if (w_ended) finish_search(best, mstart, true);
+                        else { cur = w_cur; mo = w_mo; limit = limit_base + w_mo; }
+                        reroot = false;
+                    }
+                    __syncwarp();
+                }
+            }
+            // 3. short matches: the same, serially
+            if (reroot) {
+                cur = cand;
+                mo = 0;
+                uint32_t next_pos = cur;
+                bool ended = false;
+                for (uint32_t i = 0; i + 3 <= len; i++) {
+                    const uint32_t y = cur + i;
+                    const uint32_t d = qld_u16(ladj + 2 * y);
+                    const uint32_t pos = (d && y - d > B) ? y - d : B;
+                    if (pos < next_pos) {
+                        if (pos <= limit_base + i) { ended = true; break; }
+                        next_pos = pos;
+                        mo = i;
+                    }
+                }
+                if (!ended) {
+                    cur = next_pos;
+                    const uint32_t pos = head_at(q + len - 4);
+                    if (pos < cur) {
+                        mo = len - 4;
+                        if (pos <= limit_base + mo) ended = true;
+                        else cur = pos;
+                    }
+                }
+                if (ended) finish_search(best, mstart, true);
+                else limit = limit_base + mo;
+            }
             continue;
+        }
+        // ---- a search that has already looked at kMonster candidates is finished by the whole warp.  On record-like data single
+        // searches run through their whole budget (1024 or 4096 candidates), most candidates pass the filters and every compare is a
+        // hundred bytes long: one lane then needs millions of cycles while the rest of the CTA -- at the end of the launch the rest
+        // of the GPU -- waits for it (ncu: the busiest SM was active eight times as long as the average).  Together: 32 chain
+        // candidates are listed by a uniform walk over the links, every lane filters and compares one of them, the first one that
+        // is longer than the best is accepted exactly as the serial walk would (the candidates before it cost one unit of budget
+        // each; an accepted match is re-rooted, which changes the chain, so the rest of the round is dropped).
+        {
+            const uint32_t chain0 = ((l ? l : 2u) >= sp.good) ? sp.chain >> 2 : sp.chain;
+            uint32_t mm = __ballot_sync(0xffffffffu, state == SS_WALK && chain0 - chain >= kMonster);
+            if (mm) {
+                uint32_t *tab = s_tab[tid >> 5];
+                while (mm) {
+                    const uint32_t src = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t w_q = __shfl_sync(0xffffffffu, q, src), w_B = __shfl_sync(0xffffffffu, B, src);
+                    const uint32_t w_lb = __shfl_sync(0xffffffffu, limit_base, src), w_xw0 = __shfl_sync(0xffffffffu, xw0, src);
+                    uint32_t w_cur = __shfl_sync(0xffffffffu, cur, src), w_mo = __shfl_sync(0xffffffffu, mo, src);
+                    uint32_t w_best = __shfl_sync(0xffffffffu, best, src), w_chain = __shfl_sync(0xffffffffu, chain, src);
+                    uint32_t w_limit = __shfl_sync(0xffffffffu, limit, src), w_ms = __shfl_sync(0xffffffffu, mstart, src);
+                    for (;;) {
+                        if (w_cur >= w_q) break; // the walk's own end test
+                        // list up to 32 candidates of the chain (lane k keeps the k-th); `after`: what next_in_chain() does behind the last
+                        const uint32_t lim = w_chain < 32u ? w_chain : 32u;
+                        uint32_t n = 0, mychain = 0, c = w_cur;
+                        bool stop_after = false;
+                        for (uint32_t k = 0; k < lim; k++) {
+                            if (lane == k) mychain = c;
+                            n = k + 1;
+                            if (w_chain - n == 0) { stop_after = true; break; }            // budget
+                            const uint32_t d = qld_u16(ladj + 2 * c);
+                            if (d == 0 || d >= c - w_limit) { stop_after = true; break; } // the chain ends or leaves the window
+                            c -= d;
+                        }
+                        // filter and compare
+                        const uint32_t xbw = qld_u8(dadj + w_q + w_best);
+                        uint32_t len = 0;
+                        const uint32_t cs = mychain - w_mo;
+                        if (lane < n) {
+                            bool pass = qld_u8(dadj + cs + w_best) == xbw;
+                            if (pass) {
+                                const uint32_t dw = qld_u32u(dadj + cs) ^ w_xw0;
+                                pass = (w_best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+                            }
+                            if (pass) {
+                                uint32_t clen = 0;
+                                const uint32_t pa = dadj + w_q, pb = dadj + cs;
+                                for (;;) {
+                                    const uint32_t d0 = qld_u32u(pa + clen) ^ qld_u32u(pb + clen);
+                                    const uint32_t d1 = qld_u32u(pa + clen + 4) ^ qld_u32u(pb + clen + 4);
+                                    if ((d0 | d1) == 0 && clen + 8 < kMaxMatch) { clen += 8; continue; }
+                                    len = d0 ? clen + ((__ffs(d0) - 1) >> 3) : d1 ? clen + 4 + ((__ffs(d1) - 1) >> 3) : clen + 8;
+                                    break;
+                                }
+                                if (len > kMaxMatch) len = kMaxMatch;
+                            }
+                        }
+                        const uint32_t m_acc = __ballot_sync(0xffffffffu, lane < n && len > w_best);
+                        if (m_acc == 0) { // all of them rejected: each cost one unit; the last one may have ended the walk
+                            w_chain -= n;
+                            if (stop_after) break;
+                            w_cur = c;
+                            continue;
+                        }
+                        const uint32_t ka = __ffs(m_acc) - 1;
+                        w_chain -= ka; // the candidates before the accepted one
+                        const uint32_t a_len = __shfl_sync(0xffffffffu, len, ka), a_cs = __shfl_sync(0xffffffffu, cs, ka);
+                        const uint32_t a_chain = __shfl_sync(0xffffffffu, mychain, ka);
+                        w_ms = a_cs;
+                        w_best = a_len;
+                        if (w_best >= sp.nice) break;
+                        if (a_len > 3 && a_cs + a_len < w_q) {
+                            // longest_match.rs:281-333 (as in the PEND phase)
+                            uint32_t run_min = a_cs, run_mo = 0;
+                            bool w_ended = false;
+                            const uint32_t nn = a_len - 2;
+                            for (uint32_t c0 = 0; c0 < nn && !w_ended; c0 += 32) {
+                                const uint32_t i = c0 + lane;
+                                uint32_t pos = 0xffffffffu;
+                                if (i < nn) {
+                                    const uint32_t y = a_cs + i, d = qld_u16(ladj + 2 * y);
+                                    pos = (d && y - d > w_B) ? y - d : w_B;
+                                }
+                                uint32_t ex = pos;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, ex, d); if (lane >= (uint32_t)d && t < ex) ex = t; }
+                                ex = __shfl_up_sync(0xffffffffu, ex, 1);
+                                if (lane == 0) ex = 0xffffffffu;
+                                if (run_min < ex) ex = run_min;
+                                const bool setter = i < nn && pos < ex;
+                                const uint32_t m_end = __ballot_sync(0xffffffffu, setter && pos <= w_lb + i);
+                                const uint32_t m_set = __ballot_sync(0xffffffffu, setter);
+                                if (m_end) w_ended = true;
+                                else if (m_set) {
+                                    const uint32_t last = 31 - __clz(m_set);
+                                    run_min = __shfl_sync(0xffffffffu, pos, last);
+                                    run_mo = c0 + last;
+                                }
+                            }
+                            if (w_ended) break;
+                            uint32_t n_cur = run_min, n_mo = run_mo;
+                            uint32_t hpos = w_q; // head_at(q + len - 4); len == 4: the window at q itself
+                            const uint32_t nt = a_len - 4;
+                            if (nt) {
+                                for (uint32_t j = lane; j < nt; j += 32) {
+                                    const uint32_t x = w_q + 1 + j, d = qld_u16(ladj + 2 * x);
+                                    tab[j] = d ? x - d : 0u;
+                                }
+                                __syncwarp();
+                                uint32_t hv = 0;
+                                for (uint32_t c0 = 0; c0 < nt; c0 += 32) {
+                                    const uint32_t j = c0 + lane;
+                                    const bool valid = j < nt;
+                                    uint32_t v = valid ? tab[j] : 0u;
+                                    for (int rep = 0; rep < 7; rep++) {
+                                        const bool hop = v > w_q;
+                                        if (hop) v = tab[v - w_q - 1];
+                                        __syncwarp();
+                                        if (valid) tab[j] = v;
+                                        __syncwarp();
+                                        if (!__any_sync(0xffffffffu, hop)) break;
+                                    }
+                                    if (__any_sync(0xffffffffu, valid && v > w_q)) atomicOr(&jb.info->error, 64u);
+                                    if (c0 + 32 >= nt) hv = __shfl_sync(0xffffffffu, v, (nt - 1) & 31u);
+                                }
+                                hpos = hv > w_B ? hv : w_B;
+                            }
+                            if (hpos < n_cur) {
+                                n_mo = a_len - 4;
+                                if (hpos <= w_lb + n_mo) break; // ended
+                                n_cur = hpos;
+                            }
+                            w_cur = n_cur; w_mo = n_mo; w_limit = w_lb + n_mo;
+                            continue;
+                        }
+                        // accepted without re-rooting: on to the next candidate of the same chain
+                        if (--w_chain == 0) break;
+                        {
+                            const uint32_t d = qld_u16(ladj + 2 * a_chain);
+                            if (d == 0 || d >= a_chain - w_limit) break;
+                            w_cur = a_chain - d;
+                        }
+                    }
+                    if (lane == src) {
+                        best = w_best; mstart = w_ms; chain = w_chain; cur = w_cur; mo = w_mo; limit = w_limit;
+                        finish_search(best, mstart, true);
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
         }
 #pragma unroll
         for (uint32_t burst = 0; burst < kBurst9; burst++) {

@@ -17,6 +17,9 @@
 
 namespace {
 
+// One engine per calling thread, created on first use and kept until the process ends (it is deliberately not destroyed from a
+// thread_local destructor: at process exit that would run after the CUDA runtime has started to unload).  A thread pool therefore
+// keeps one stream + buffer set per worker; short-lived threads should use the zb_* API with their own engine and destroy it.
 thread_local zb_engine *t_engine = nullptr;
 thread_local int t_engine_err = 0;
 
