@@ -353,6 +353,15 @@ def test_config4_calgary_mix_level9_whole_and_chunk_sharded(eng):
     assert rc == 0 and got == d
 
 
+def test_calgary_mix_64MiB_level6_bit_exact(eng):
+    """A 64 MiB input at level 6: 2049 match tiles and 4097 path tiles -- the work lists of the later iterations are built in more
+    than one 1024-thread chunk, the two-level path chain runs with 64 groups, the host input arrives in eight chunks."""
+    d = calgary_mix()
+    out, res = eng.deflate(d, level=6)
+    assert res.exact_parity == 1 and res.iterations >= 2
+    assert out == O.compress(d, 6)[1]
+
+
 FLUSH_KATS = [v for v in KAT["vectors"] if v["kind"] == "deflate" and v["flush"] != 4]
 
 
