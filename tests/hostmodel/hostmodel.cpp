@@ -81,9 +81,14 @@ extern "C" int hm_parse_parallel(const uint8_t *data, uint32_t N, int level, Sym
         first = false;
         // P1: nxt for every canonical position below the tail
         for (uint32_t p = 0; p < tail_start; p++) {
-            uint32_t ns;
-            uint32_t np = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns);
+            uint32_t ns, nlong = 0, lpos = 0, llen = 0;
+            uint32_t np = macro_step(a, p, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy) { nlong++; lpos = s.pos; llen = s.lc + 3u; }
+            }, &ns);
             nxt[p] = np;
+            // what k_nxt / k_holes rely on (zb_kernels.cu): a long match is the last symbol of its macro step, alone, and 257 or 258
+            // bytes long at levels 5/6 (the step is the match at levels 3/4)
+            if (nlong && (nlong != 1 || lpos + llen != np || (lp.early_exit ? lpos != p : (llen != 257u && llen != 258u)))) return -2;
         }
         // P2: path from 0
         path.clear();
