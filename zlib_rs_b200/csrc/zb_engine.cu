@@ -518,10 +518,6 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
                 uint32_t n_dirty = nmt;
                 for (;;) {
                     iters++;
-                    // first pass: 8 KiB of positions per CTA; later passes touch few tiles, so smaller pieces spread
-                    // them over more SMs
-                    // few dirty tiles: small pieces on many SMs, few warps each (the walk of a sparse piece is issue-bound per warp)
-                    // one wave of CTAs if possible: the per-piece latency, not the throughput, bounds a sparse pass
                     // Pieces: the full first pass runs two CTAs per SM (4 KiB of positions each: the window copy of a CTA is 111 KiB);
                     // later passes cut the dirty tiles into enough pieces for about four CTAs per SM, because a sparse pass is
                     // bounded by its slowest piece, not by throughput.
