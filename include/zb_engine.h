@@ -55,10 +55,9 @@ ZB_API void zb_engine_destroy(zb_engine *e);
 ZB_API const char *zb_last_error(void);
 ZB_API int zb_device_count(void);
 
-/* window_bits follows deflateInit2: 9..15 zlib, -9..-15 raw, 25..31 gzip.  The parallel kernels implement the 32 KiB window.
- * Smaller windows give the reference's bytes at level 0, with Z_HUFFMAN_ONLY and at levels 1/2 (any input size), at levels 3..6
- * for inputs up to 32000 bytes, and at every level when the input never leaves the window's match range
- * (src_len <= 2^bits - 262); otherwise the 32 KiB engine is used (valid stream, CINFO=7, exact_parity = 0). */
+/* window_bits follows deflateInit2: 9..15 zlib, -9..-15 raw, 25..31 gzip.  Every window size gives the reference's bytes at every
+ * level and strategy (the parallel kernels take the window size as a parameter); only a preset dictionary together with a window
+ * smaller than 32 KiB uses the 32 KiB engine (valid stream, CINFO = 7, exact_parity = 0). */
 ZB_API int zb_deflate(zb_engine *e, const void *src, size_t src_len, int src_on_device, void *dst, size_t dst_cap, int dst_on_device,
                int level, int strategy, int window_bits, zb_deflate_result *res);
 /* flags for zb_deflate_ex */

@@ -509,6 +509,51 @@ extern "C" int hm_parse_slow(const uint8_t *data, uint32_t N, int level, SymOut 
     return 0;
 }
 
+// The lazy levels with a window smaller than 32 KiB (windowBits 9..14): the same steps with the window size in SlowParams
+// (window schedule, match range, reach of the level-9 tables), links capped accordingly.
+struct SlowAccW {
+    const uint8_t *data; uint32_t N; const uint16_t *L; uint32_t need; uint32_t w;
+    uint32_t byte(uint32_t y) const {
+        while (y >= N) { if (y < 2 * w) return 0; y -= w; }
+        return data[y];
+    }
+    uint32_t link(uint32_t y) const { return y + need <= N ? L[y] : 0; }
+};
+
+extern "C" int hm_parse_slow_w(const uint8_t *data, uint32_t N, int level, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    SlowParams sp = slow_params(level);
+    sp.wsize = 1u << wbits;
+    std::vector<uint16_t> L(N + 8, 0);
+    if (sp.slow) {
+        std::vector<int64_t> head(32768, -1);
+        for (uint32_t x = 0; x + 3 <= N; x++) {
+            uint32_t h = hash_roll3(data[x], data[x + 1], data[x + 2]);
+            if (head[h] >= 0 && x - head[h] <= sp.wsize - 1) L[x] = (uint16_t)(x - head[h]);
+            head[h] = x;
+        }
+    } else {
+        std::vector<int64_t> head(65536, -1);
+        for (uint32_t x = 0; x + 4 <= N; x++) {
+            uint32_t v = data[x] | (data[x + 1] << 8) | (data[x + 2] << 16) | ((uint32_t)data[x + 3] << 24);
+            uint32_t h = hash_u32(v);
+            if (head[h] >= 0 && x - head[h] <= sp.maxdist()) L[x] = (uint16_t)(x - head[h]);
+            head[h] = x;
+        }
+    }
+    SlowAccW a{data, N, L.data(), sp.slow ? 3u : 4u, sp.wsize};
+    uint32_t n = 0, p = 0;
+    while (p < N) {
+        SlowStep s = slow_step(a, p, N, sp);
+        for (uint32_t i = 0; i < s.nlit; i++) { if (n < cap) out[n] = SymOut{p + i, 0, data[p + i]}; n++; }
+        if (s.len) { if (n < cap) out[n] = SymOut{p + s.nlit, (uint16_t)s.dist, (uint16_t)(s.len - 3)}; n++; }
+        if (s.next <= p) return -3;
+        p = s.next;
+    }
+    *nsyms = n;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Levels 1 and 2 (zb_serial.h): the warp-serial restatement of deflate_quick / deflate_fast with scalar Ops.
 // ------------------------------------------------------------------------------------------
@@ -605,6 +650,47 @@ extern "C" int hm_oracle_trace_w(const uint8_t *data, uint32_t N, int level, int
     zo_deflate_end(&s);
     *nsyms = t.n;
     return rc == ZO_STREAM_END ? 0 : -2;
+}
+
+// the oracle's symbol trace with a strategy (Z_RLE = 3, Z_FILTERED = 1)
+extern "C" int hm_oracle_trace_ws(const uint8_t *data, uint32_t N, int level, int wbits, int mem_level, int strategy, SymOut *out, uint32_t cap,
+                                  uint32_t *nsyms)
+{
+    zo_stream s;
+    memset(&s, 0, sizeof s);
+    if (zo_deflate_init(&s, level, wbits, mem_level, strategy) != 0) return -1;
+    TraceCtx t{out, cap, 0};
+    zo_deflate_set_trace(&s, trace_cb, &t);
+    std::vector<uint8_t> dst(zo_compress_bound(N) + N / 4 + 1024);
+    s.next_in = data; s.avail_in = N; s.next_out = dst.data(); s.avail_out = (uint32_t)dst.size();
+    int rc = zo_deflate(&s, ZO_FINISH);
+    zo_deflate_end(&s);
+    *nsyms = t.n;
+    return rc == ZO_STREAM_END ? 0 : -2;
+}
+
+// Z_RLE with any window: the step of k_rle (zb_slow.cu) -- the window only enters through the look-ahead at a loop-top
+extern "C" int hm_parse_rle_w(const uint8_t *d, uint32_t N, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms)
+{
+    const uint32_t w = 1u << wbits;
+    uint32_t n = 0, p = 0;
+    while (p < N) {
+        const uint32_t B = base_at(p, N, w), la = lookahead_at(p, B, N, w);
+        uint32_t len = 0;
+        if (la >= 3 && p > 0 && p + 1 < N && d[p - 1] == d[p] && d[p] == d[p + 1]) {
+            const uint32_t c = d[p - 1];
+            uint32_t k = 0;
+            while (k < 256 && p + 2 + k < N && d[p + 2 + k] == c) k++;
+            len = k + 2;
+            if (len > la) len = la;
+            if (len > kMaxMatch) len = kMaxMatch;
+            if (len < 3) len = 0;
+        }
+        if (len) { if (n < cap) out[n] = SymOut{p, 1, (uint16_t)(len - 3)}; n++; p += len; }
+        else { if (n < cap) out[n] = SymOut{p, 0, d[p]}; n++; p++; }
+    }
+    *nsyms = n;
+    return 0;
 }
 
 extern "C" int hm_parse_small_window(const uint8_t *data, uint32_t N, int level, int wbits, SymOut *out, uint32_t cap, uint32_t *nsyms)

@@ -268,8 +268,8 @@ def test_small_windows_that_fit_are_exact(eng):
         for level in (0, 1, 2, 6, 9):
             out, res = eng.deflate(d, level=level, window_bits=wb)
             assert res.exact_parity == 1 and out == O.compress(d, level, wb)[1], (wb, level)
-        out, res = eng.deflate(d + b"x", level=9, window_bits=wb)  # one byte more: 32 KiB engine, CINFO 7, still a valid stream
-        assert res.exact_parity == 0 and zlib.decompress(out) == d + b"x"
+        out, res = eng.deflate(d + b"x", level=9, window_bits=wb)  # one byte more: the window slides (round 2b: exact at the lazy levels too)
+        assert res.exact_parity == 1 and out == O.compress(d + b"x", 9, wb)[1]
 
 
 def test_small_windows_serial_path_levels_3_to_6(eng):
@@ -531,6 +531,26 @@ def test_small_windows_parallel_path_levels_3_to_6(eng):
     d = srcs[1][:100000]
     assert eng.deflate(d, level=6, window_bits=-12)[0] == O.compress(d, 6, -12)[1]
     assert eng.deflate(d, level=6, window_bits=28, mem_level=4)[0] == O.compress(d, 6, 28, 4)[1]
-    for level in (7, 9):  # not built: the lazy levels keep the 32 KiB engine for sliding small windows (valid stream, CINFO 7)
-        out, res = eng.deflate(d, level=level, window_bits=12)
-        assert res.exact_parity == 0 and zlib.decompress(out) == d
+
+
+def test_small_windows_lazy_levels_and_rle(eng):
+    """windowBits 9..14 at levels 7..9 and with Z_RLE, inputs that slide the window hundreds of times (round 2b): the lazy steps take
+    the window size from SlowParams (window schedule, match range, the reach of the level-9 tables), Z_RLE from the look-ahead."""
+    rng = np.random.default_rng(3)
+    runs = bytearray()
+    while len(runs) < 200000:
+        runs += bytes([int(rng.integers(0, 4))]) * int(rng.integers(1, 700))
+    srcs = [synthetic_mix(200000, 9), silesia_member(9)[:200000], silesia_member(1)[:150000], silesia_member(3)[:120000], bytes(runs),
+            rng.integers(0, 256, 150000, dtype=np.uint8).tobytes()]
+    for wb in (9, 10, 11, 12, 13, 14):
+        for i, src in enumerate(srcs):
+            for level in ((7, 9) if (wb + i) % 2 else (8,)):
+                out, res = eng.deflate(src, level=level, window_bits=wb)
+                assert res.exact_parity == 1 and out == O.compress(src, level, wb)[1], (wb, i, level)
+            out, res = eng.deflate(src, level=6, strategy=3, window_bits=wb)
+            assert res.exact_parity == 1 and out == O.compress(src, 6, wb, 8, 3)[1], (wb, i, "rle")
+    d = srcs[1][:100000]
+    assert eng.deflate(d, level=9, window_bits=-12)[0] == O.compress(d, 9, -12)[1]
+    assert eng.deflate(d, level=8, window_bits=28, mem_level=4)[0] == O.compress(d, 8, 28, 4)[1]
+    assert eng.deflate(d, level=7, strategy=1, window_bits=11)[0] == O.compress(d, 7, 11, 8, 1)[1]  # Z_FILTERED
+    assert eng.deflate(d, level=1, strategy=3, window_bits=10)[0] == O.compress(d, 1, 10, 8, 3)[1]  # Z_RLE at a low level

@@ -189,6 +189,28 @@ def test_fuzz_smoke():
     assert cases == 150 and bad == 0
 
 
+def test_lazy_levels_and_rle_with_small_windows():
+    """Levels 7..9 (slow_step with the window size in SlowParams) and Z_RLE (the step of k_rle) against the oracle's symbol trace for
+    windowBits 9..14: window schedule, match range, the reach of the level-9 tables, the look-ahead at the fill boundaries."""
+    rng = np.random.default_rng(5)
+    runs = bytearray()
+    while len(runs) < 90000:
+        runs += bytes([int(rng.integers(0, 4))]) * int(rng.integers(1, 700))
+    srcs = {"mix": synthetic_mix(70000, 9), "m9": silesia_member(9)[:70000], "m1": silesia_member(1)[:60000], "runs": bytes(runs)}
+    for name, data in srcs.items():
+        n = len(data)
+        a = np.zeros((n + 16) * 2, dtype=np.uint32); b = np.zeros((n + 16) * 2, dtype=np.uint32)
+        na = ctypes.c_uint32(); nb = ctypes.c_uint32()
+        for wbits in (9, 10, 12, 14):
+            for level in (7, 8, 9):
+                assert H().hm_parse_slow_w(data, n, level, wbits, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na)) == 0
+                assert H().hm_oracle_trace_w(data, n, level, wbits, 8, b.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(nb)) == 0
+                assert na.value == nb.value and (a[: na.value * 2] == b[: nb.value * 2]).all(), (name, wbits, level)
+            assert H().hm_parse_rle_w(data, n, wbits, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na)) == 0
+            assert H().hm_oracle_trace_ws(data, n, 6, wbits, 8, 3, b.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(nb)) == 0
+            assert na.value == nb.value and (a[: na.value * 2] == b[: nb.value * 2]).all(), (name, wbits, "rle")
+
+
 def test_parallel_formulation_with_small_windows():
     """windowBits 9..14 at levels 3..6 on inputs that slide the window many times: the phases of the GPU pipeline (links capped at
     the window's match range, M for every position, macro steps with the DynWin window schedule, path, hole fixed point, serial

@@ -362,6 +362,15 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
         jb.cinfo = (uint32_t)(wb_eff - 8);
         exact = true;
     }
+    // ... and so do the lazy levels 7..9 and Z_RLE (round 2b): the window size rides in SlowParams / jb.wsize (window schedule, match
+    // range, the reach of the level-9 tables, the look-ahead at a loop-top); host model vs the oracle's trace for windowBits 9..14.
+    static const bool slow_win_off = getenv("ZB_SLOW_WIN") && atoi(getenv("ZB_SLOW_WIN")) == 0;
+    const bool slow_win = !slow_win_off && wb_eff < 15 && !small_ok && dstart == 0 && level != 0 && ((level >= 7 && strategy != 2) || strategy == 3);
+    if (slow_win) {
+        jb.wsize = 1u << wb_eff;
+        jb.cinfo = (uint32_t)(wb_eff - 8);
+        exact = true;
+    }
     // level 0 does not depend on the window at all (stored.rs copies straight from the input); Z_HUFFMAN_ONLY only through the
     // stored-block rule (window base at flush time, k_block_hist); levels 1 and 2 emulate the window literally (zb_serial.h)
     if (wb_eff < 15 && (level == 0 || (strategy == 2 && level != 0) || serial_low)) {
@@ -372,7 +381,7 @@ int Engine::deflate(const void *src, size_t n_in, bool src_dev, void *dst, size_
     if (level != 0 && !jb.huffman_only) {
         if (level < 3 && !serial_low) { eng_level = 3; exact = exact && strategy == 3; } // ZB_FLAG_LOW_PARALLEL: level-3 kernel set instead
         if (strategy == 3) jb.slow_mode = 2; // Z_RLE (algorithm/rle.rs) at every level
-        else if (level > 6) { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; }
+        else if (level > 6) { jb.slow_mode = 1; jb.sp = slow_params(level); jb.sp.filtered = strategy == 1; jb.sp.wsize = jb.wsize; }
     }
     if (jb.slow_mode) jb.tail_start = N; // the lazy path needs no serial tail: every step knows the end of the input
     jb.lp = level_params(eng_level);

@@ -110,7 +110,7 @@ __device__ __forceinline__ void links2_body(const JobBufs &jb, uint32_t tile0)
     __shared__ uint16_t c_base[32], c_total[32];
     const uint32_t *words = reinterpret_cast<const uint32_t *>(sd);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
+    const uint32_t N = jb.N, need = kRoll ? 3u : 4u, cap = kRoll ? jb.wsize - 1u : jb.wsize - kMinLookahead; // kLinkCapSlow for 32 KiB
     const uint32_t ts = tile * kLinkTile;
     const uint32_t te = min(ts + kLinkTile, N);
     const uint32_t tv = N >= need ? min(te, N - need + 1) : ts; // positions with enough bytes to hash
@@ -197,7 +197,7 @@ __device__ __forceinline__ void links_fix_body(const JobBufs &jb)
     constexpr uint32_t kKeys = kRoll ? 32768u : 65536u;
     const uint32_t x = blockIdx.x * 256 + threadIdx.x;
     if (x >= jb.N || jb.L[x] != kFirstFlag) return;
-    const uint32_t tile = x / kLinkTile, cap = kRoll ? kLinkCapSlow : jb.wsize - kMinLookahead;
+    const uint32_t tile = x / kLinkTile, cap = kRoll ? jb.wsize - 1u : jb.wsize - kMinLookahead;
     uint32_t d = 0;
     if (tile > 0) {
         const uint8_t *q = jb.in + x;
@@ -1781,9 +1781,9 @@ __global__ void __launch_bounds__(256) k_block_hist(JobBufs jb, uint32_t *freq /
                 const uint32_t q = jb.syms[li].pos, w = jb.wsize;
                 Bf = q < 2 * w ? 0 : w * (1 + (q - 2 * w) / w);
             } else if (jb.slow_mode == 2) {
-                Bf = base_at(jb.syms[li].pos, jb.N);     // Z_RLE tallies a symbol at its own loop-top
+                Bf = base_at(jb.syms[li].pos, jb.N, jb.wsize);     // Z_RLE tallies a symbol at its own loop-top
             } else if (jb.slow_mode) {
-                Bf = base_at(jb.syms[li].pos + 1, jb.N); // the symbol is tallied at the loop-top behind its first byte (slow.rs:84-136)
+                Bf = base_at(jb.syms[li].pos + 1, jb.N, jb.wsize); // the symbol is tallied at the loop-top behind its first byte (slow.rs:84-136)
             } else Bf = li < n_mid ? wbase_w(DynWin{jb.wsize}, jb.syms[li].pos) : jb.sym_base[li - n_mid];
         }
         bd.have_window = start >= Bf;

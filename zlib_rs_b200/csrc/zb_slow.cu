@@ -15,13 +15,13 @@ namespace zb {
 struct SlowSAcc {
     const uint8_t *sdata;
     const uint16_t *sL;
-    uint32_t ws, N, need;
+    uint32_t ws, N, need, w; // w: window size (1 << windowBits)
     __device__ __forceinline__ uint32_t byte(uint32_t y) const
     {
         // bytes beyond the input are what the reference's window buffer still holds there
         while (y >= N) {
-            if (y < 2 * kWSize) return 0;
-            y -= kWSize;
+            if (y < 2 * w) return 0;
+            y -= w;
         }
         return sdata[y - ws];
     }
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
         for (uint32_t i = tid; i < nl; i += 1024) ld[i] = ls[i];
     }
     __syncthreads();
-    const SlowSAcc acc{sdata, sL, ws, N, jb.sp.slow ? 3u : 4u};
+    const SlowSAcc acc{sdata, sL, ws, N, jb.sp.slow ? 3u : 4u, jb.sp.wsize};
     const SlowParams sp = jb.sp;
     // shared addresses of absolute position 0 (only positions >= ws are ever dereferenced)
     const uint32_t dadj = (uint32_t)__cvta_generic_to_shared(sdata) - ws;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
             if (rlen <= l) { write_node(q - 1 + l, q - 1 - p, l, q - 1 - ms); return; }
             l = rlen; ms = rstart; q++;
         }
-        const uint32_t Bq = base_at(q, N);
+        const uint32_t Bq = base_at(q, N, sp.wsize);
         if (Bq != B) {
             B = Bq;
             if (ms < Bq) { write_node(q, q - p, 0, 0); return; } // pending match dropped by the slide (deflate.rs:1792-1797)
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                     write_node(s.next, s.nlit, s.len, s.dist);
                 } else {
                     p = q = x; l = 0; ms = 0;
-                    B = base_at(x, N);
+                    B = base_at(x, N, sp.wsize);
                     state = SS_START;
                 }
             }
@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                 if (search) {
                     const uint32_t d = qld_u16(ladj + 2 * q);
                     hh = q - d;
-                    search = d != 0 && d <= kMaxDist && hh > B;
+                    search = d != 0 && d <= sp.maxdist() && hh > B;
                 }
                 if (!search) finish_search(2, ms, false);
                 else {
                     best = l ? l : 2;
                     mstart = ms;
                     chain = best >= sp.good ? sp.chain >> 2 : sp.chain;
-                    limit_base = (q - B > kMaxDist) ? q - kMaxDist : B;
+                    limit_base = (q - B > sp.maxdist()) ? q - sp.maxdist() : B;
                     limit = limit_base;
                     mo = 0;
                     cur = hh;
@@ -625,14 +625,14 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                 if (search) {
                     const uint32_t d = qld_u16(ladj + 2 * q);
                     hh = q - d;
-                    search = d != 0 && d <= kMaxDist && hh > B;
+                    search = d != 0 && d <= sp.maxdist() && hh > B;
                 }
                 if (!search) finish_search(2, ms, false);
                 else {
                     best = l ? l : 2;
                     mstart = ms;
                     chain = best >= sp.good ? sp.chain >> 2 : sp.chain;
-                    limit_base = (q - B > kMaxDist) ? q - kMaxDist : B;
+                    limit_base = (q - B > sp.maxdist()) ? q - sp.maxdist() : B;
                     limit = limit_base;
                     mo = 0;
                     cur = hh;
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
                     write_node(s.next, s.nlit, s.len, s.dist);
                 } else {
                     p = q = x; l = 0; ms = 0;
-                    B = base_at(x, N);
+                    B = base_at(x, N, sp.wsize);
                     state = SS_START;
                 }
             }
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(256) k_rle(JobBufs jb)
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, N = jb.N;
     if (p >= N) return;
     const uint8_t *d = jb.in;
-    const uint32_t B = base_at(p, N), la = lookahead_at(p, B, N);
+    const uint32_t B = base_at(p, N, jb.wsize), la = lookahead_at(p, B, N, jb.wsize);
     uint32_t len = 0;
     if (la >= 3 && p > 0 && d[p - 1] == d[p] && d[p] == d[p + 1]) {
         const uint32_t c = d[p - 1];
@@ -777,7 +777,7 @@ __global__ void k_tail_slow(JobBufs jb)
     uint32_t n = jb.info->n_mid_syms;
     if (jb.N > jb.start) n += emit_step(jb, jb.info->tail_entry, jb.syms + n);
     jb.info->n_syms = n;
-    jb.info->final_base = base_at(jb.N, jb.N);
+    jb.info->final_base = base_at(jb.N, jb.N, jb.wsize);
     uint32_t nb = n / jb.block_syms + 1;
     // deflate_slow tallies a pending last literal after its loop and ignores that the symbol buffer may just have filled up
     // (slow.rs:150-153): the full block then IS the last block instead of being followed by an empty one

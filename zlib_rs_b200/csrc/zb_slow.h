@@ -29,14 +29,16 @@ struct SlowParams {
     uint32_t good, lazy, nice, chain;
     uint32_t slow; // max_chain > 1024: SLOW matcher + rolling hash (hash_calc.rs:14-20, slow.rs:18)
     uint32_t filtered; // Z_FILTERED: matches of length <= 5 are dropped (slow.rs:76-80)
+    uint32_t wsize = kWSize; // window size, 1 << windowBits (512 .. 32768): the window schedule, the match range, the reach of the tables
+    ZB_HD uint32_t maxdist() const { return wsize - kMinLookahead; }
 };
 ZB_HD SlowParams slow_params(int level)
 {
     // deflate/algorithm/mod.rs:69-82 rows 7..9
     switch (level) {
-    case 7: return {8, 32, 128, 256, 0, 0};
-    case 8: return {32, 128, 258, 1024, 0, 0};
-    default: return {32, 258, 258, 4096, 1, 0};
+    case 7: return {8, 32, 128, 256, 0, 0, kWSize};
+    case 8: return {32, 128, 258, 1024, 0, 0, kWSize};
+    default: return {32, 258, 258, 4096, 1, 0, kWSize};
     }
 }
 
@@ -47,16 +49,16 @@ ZB_HD uint32_t hash_roll3(uint32_t b0, uint32_t b1, uint32_t b2) { return ((b0 <
 // Window base in force at a loop-top at p, after its own fill_window check (deflate.rs:1776-1806).  Mid-stream
 // this is wbase(p); once the input is exhausted fill_window runs at every loop-top and slides as soon as
 // strstart >= w_size + max_dist, i.e. one position earlier.
-ZB_HD uint32_t base_at(uint32_t p, uint32_t N)
+ZB_HD uint32_t base_at(uint32_t p, uint32_t N, uint32_t w = kWSize)
 {
-    uint32_t B = p ? wbase(p - 1) : 0;
-    const uint32_t F = (uint64_t)B + 2 * kWSize < N ? B + 2 * kWSize : N;
-    if (F - p < kMinLookahead && p - B >= kWSize + kMaxDist) B += kWSize;
+    uint32_t B = p ? wbase_w(DynWin{w}, p - 1) : 0;
+    const uint32_t F = (uint64_t)B + 2 * w < N ? B + 2 * w : N;
+    if (F - p < kMinLookahead && p - B >= w + (w - kMinLookahead)) B += w;
     return B;
 }
-ZB_HD uint32_t lookahead_at(uint32_t p, uint32_t B, uint32_t N)
+ZB_HD uint32_t lookahead_at(uint32_t p, uint32_t B, uint32_t N, uint32_t w = kWSize)
 {
-    const uint32_t F = (uint64_t)B + 2 * kWSize < N ? B + 2 * kWSize : N;
+    const uint32_t F = (uint64_t)B + 2 * w < N ? B + 2 * w : N;
     return F - p;
 }
 
@@ -72,13 +74,13 @@ ZB_HD uint32_t prevpos(const A &a, uint32_t y, uint32_t B)
 
 // head[hash of the 3 bytes at x] while the parser stands at p: the latest inserted position (<= p) of that bucket.
 template <class A>
-ZB_HDN uint32_t headpos(const A &a, uint32_t x, uint32_t p, uint32_t B, uint32_t N)
+ZB_HDN uint32_t headpos(const A &a, uint32_t x, uint32_t p, uint32_t B, uint32_t N, uint32_t w = kWSize)
 {
     if (x + 3 > N) {
         // the string reaches into the stale bytes behind the input: no link was ever built for it
         const uint32_t h = hash_roll3(a.byte(x), a.byte(x + 1), a.byte(x + 2));
         uint32_t q = p + 3 <= N ? p : (N >= 3 ? N - 3 : 0);
-        const uint32_t lo = p > kLinkCapSlow ? p - kLinkCapSlow : 0;
+        const uint32_t lo = p > w - 1 ? p - (w - 1) : 0; // the tables reach w - 1 back (kLinkCapSlow for 32 KiB)
         for (;; q--) {
             if (q + 3 <= N && hash_roll3(a.byte(q), a.byte(q + 1), a.byte(q + 2)) == h) return q > B ? q : B;
             if (q <= lo || q <= B) return B;
@@ -104,12 +106,12 @@ ZB_HDN Match lm_slow(const A &a, uint32_t p, uint32_t pl, uint32_t ms_in, uint32
     uint32_t match_start = ms_in;
     uint32_t chain = sp.chain;
     if (best >= sp.good) chain >>= 2;
-    const uint32_t limit_base = (p - B > kMaxDist) ? p - kMaxDist : B;
+    const uint32_t limit_base = (p - B > sp.maxdist()) ? p - sp.maxdist() : B;
     uint32_t limit = limit_base, mo = 0, cur = hh;
     if (sp.slow && best >= 3) {
         // longest_match.rs:87-124: most distant chain among the hashes of scan[1..], scan[2..], ...
         for (uint32_t i = 0; i + 3 <= best; i++) {
-            const uint32_t pos = headpos(a, p + i + 1, p, B, N);
+            const uint32_t pos = headpos(a, p + i + 1, p, B, N, sp.wsize);
             if (pos < cur) { mo = i + 1; cur = pos; }
         }
         limit = limit_base + mo;
@@ -150,7 +152,7 @@ ZB_HDN Match lm_slow(const A &a, uint32_t p, uint32_t pl, uint32_t ms_in, uint32
                         }
                     }
                     cur = next_pos;
-                    const uint32_t pos = headpos(a, p + len - 4, p, B, N);
+                    const uint32_t pos = headpos(a, p + len - 4, p, B, N, sp.wsize);
                     if (pos < cur) {
                         mo = len - 4;
                         if (pos <= limit_base + mo) return Match{min_u32(best, lookahead), match_start};
@@ -179,11 +181,11 @@ struct SlowStep {
 template <class A>
 ZB_HD Match slow_search(const A &a, uint32_t q, uint32_t pl, uint32_t ms, uint32_t B, uint32_t N, const SlowParams &sp)
 {
-    const uint32_t la = lookahead_at(q, B, N);
+    const uint32_t la = lookahead_at(q, B, N, sp.wsize);
     Match r{2, ms};
     if (la < 4 || pl >= sp.lazy) return r;
     const uint32_t d = a.link(q);
-    if (!d || d > kMaxDist) return r;
+    if (!d || d > sp.maxdist()) return r;
     const uint32_t hh = q - d;
     if (hh <= B) return r; // hash_head == 0 (NIL or slid out)
     r = lm_slow(a, q, pl, ms, hh, la, B, N, sp);
@@ -195,14 +197,14 @@ ZB_HD Match slow_search(const A &a, uint32_t q, uint32_t pl, uint32_t ms, uint32
 template <class A>
 ZB_HDN SlowStep slow_step(const A &a, uint32_t p, uint32_t N, const SlowParams &sp)
 {
-    uint32_t B = base_at(p, N);
+    uint32_t B = base_at(p, N, sp.wsize);
     Match m = slow_search(a, p, 0, 0, B, N, sp);
     if (m.len < 3) return SlowStep{p + 1, 1, 0, 0};
     uint32_t l = m.len, ms = m.start, q = p + 1;
     for (;;) {
         // loop-top q with a pending match (q-1, l, ms)
         if (q >= N) return SlowStep{q, q - p, 0, 0}; // cannot happen for l >= 3; kept as a guard
-        const uint32_t Bq = base_at(q, N);
+        const uint32_t Bq = base_at(q, N, sp.wsize);
         if (Bq != B) {
             B = Bq;
             // fill_window slid: a pending match whose source is left of the new window is dropped (deflate.rs:1792-1797)
