@@ -78,12 +78,20 @@ def deflate_huff(d, wb, mem):
     return buf.raw[: n.value]
 
 
+def syms_w(fn, d, *args):
+    n = len(d)
+    a = np.zeros((n + 16) * 2, dtype=np.uint32)
+    k = ctypes.c_uint32()
+    assert getattr(H, fn)(d, n, *args, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(k)) == 0
+    return a[: k.value * 2]
+
+
 def run(secs, seed, max_cases=1 << 60):
     rng = np.random.default_rng(seed)
     t0, cases, bad = time.time(), 0, 0
     while time.time() - t0 < secs and cases < max_cases:
         d = gen(rng)
-        which = int(rng.integers(0, 6))
+        which = int(rng.integers(0, 9))
         try:
             if which == 0:
                 lv = int(rng.integers(3, 7))
@@ -108,12 +116,33 @@ def run(secs, seed, max_cases=1 << 60):
                 wb, mem = int(rng.integers(9, 16)), int(rng.integers(1, 10))
                 ok = deflate_huff(d, wb, mem) == O.compress(d, 6, wb, mem, 2)[1]
                 tag = ("huff", wb, mem)
-            else:
+            elif which == 5:
                 lv = int(rng.integers(3, 7))
                 o = T._syms("hm_oracle_trace", d, lv)
                 s = T._syms("hm_parse_parallel", d, lv, True)
                 ok = len(o) == len(s) and (o == s).all()
                 tag = ("parallel-parse", lv)
+            elif which == 6:  # the lazy levels with a sliding small window (SlowParams.wsize)
+                lv, wb = int(rng.integers(7, 10)), int(rng.integers(9, 15))
+                o, s = syms_w("hm_oracle_trace_w", d, lv, wb, 8), syms_w("hm_parse_slow_w", d, lv, wb)
+                ok = len(o) == len(s) and (o == s).all()
+                tag = ("slow-window", lv, wb)
+            elif which == 7:  # Z_RLE with any window
+                wb = int(rng.integers(9, 16))
+                o, s = syms_w("hm_oracle_trace_ws", d, 6, wb, 8, 3), syms_w("hm_parse_rle_w", d, wb)
+                ok = len(o) == len(s) and (o == s).all()
+                tag = ("rle-window", wb)
+            else:  # levels 3..6 with a sliding small window, parallel formulation
+                d = d[:120000]
+                lv, wb = int(rng.integers(3, 7)), int(rng.integers(9, 15))
+                n = len(d)
+                a = np.zeros((n + 16) * 2, dtype=np.uint32)
+                na, it = ctypes.c_uint32(), ctypes.c_uint32()
+                assert H.hm_parse_parallel_w(d, n, lv, wb, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na), ctypes.byref(it)) == 0
+                o = syms_w("hm_oracle_trace_w", d, lv, wb, 8)
+                s = a[: na.value * 2]
+                ok = len(o) == len(s) and (o == s).all()
+                tag = ("parallel-window", lv, wb)
         except AssertionError as e:
             ok, tag = False, ("assert", which, str(e)[:80])
         cases += 1
