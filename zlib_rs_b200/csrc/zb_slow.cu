@@ -581,6 +581,10 @@ __global__ void __launch_bounds__(1024) k_slow(JobBufs jb)
         return;
     }
     uint32_t fadj = 0; // dadj + best - mo: the filter byte of candidate chain position `cur` sits at fadj + cur
+    auto first_ok = [&](uint32_t c) -> bool {
+        const uint32_t dw = qld_u32u(dadj + c) ^ xw0;
+        return (best == 2 ? (dw & 0x00ffffffu) : dw) == 0;
+    };
     for (;;) {
         if (state == SS_WALK) {
             if (chain > kSlowBurst) {
