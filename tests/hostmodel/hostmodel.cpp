@@ -814,3 +814,38 @@ extern "C" int hm_iter_experiment(const uint8_t *data, uint32_t N, int level, in
     *iters_out = iters;
     return 0;
 }
+
+// Experiment ("what the next factor needs"): how much of M would a LAZY evaluation need?  One walker per chunk of C
+// positions follows nxt[] from the chunk's first position to its end; the true path enters a chunk somewhere else and is followed
+// until it meets the chunk walker's trail.  stats: [0] positions on the true path, [1] positions visited by the chunk walkers,
+// [2] true-path nodes not on a walker's trail (the second round's work), [3] the longest such run, [4] chunks whose entry needed > 32 steps.
+extern "C" int hm_lazy_experiment(const uint8_t *data, uint32_t N, int level, uint32_t C, uint64_t *stats)
+{
+    LevelParams lp = level_params(level);
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), M(N + 1024, 0), nxt(N + 1, 0);
+    HostAcc a{data, N, L.data(), holes.data(), M.data()};
+    const uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    for (uint32_t x = 0; x < N; x++) {
+        Match m = (x + kMSafe <= N) ? lm_walk(a, x, 0xffffffffu, lp) : Match{0, 0};
+        M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+    }
+    for (uint32_t p = 0; p < tail_start; p++) { uint32_t ns; nxt[p] = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns); }
+    std::vector<uint8_t> trail(N + 1, 0);
+    uint64_t visited = 0;
+    for (uint32_t c0 = 0; c0 < tail_start; c0 += C) {
+        uint32_t p = c0;
+        while (p < tail_start && p < c0 + C) { if (!trail[p]) { trail[p] = 1; visited++; } p = nxt[p]; }
+    }
+    uint64_t on_path = 0, off = 0, longest = 0, run = 0, slow_chunks = 0;
+    uint32_t p = 0, cur_chunk = 0xffffffffu;
+    while (p < tail_start) {
+        on_path++;
+        if (p / C != cur_chunk) { cur_chunk = p / C; if (run > 32) slow_chunks++; run = 0; }
+        if (!trail[p]) { off++; run++; if (run > longest) longest = run; } else run = 0;
+        p = nxt[p];
+    }
+    stats[0] = on_path; stats[1] = visited; stats[2] = off; stats[3] = longest; stats[4] = slow_chunks;
+    return 0;
+}
