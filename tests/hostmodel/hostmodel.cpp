@@ -849,3 +849,90 @@ extern "C" int hm_lazy_experiment(const uint8_t *data, uint32_t N, int level, ui
     stats[0] = on_path; stats[1] = visited; stats[2] = off; stats[3] = longest; stats[4] = slow_chunks;
     return 0;
 }
+
+// The lazy formulation as a whole: M and the macro steps are evaluated on demand along chunk walkers and along the
+// true path; the hole fixed point runs on top of it exactly as in hm_parse_parallel.  Output: the symbols (to be compared with the
+// oracle's trace) and, per iteration, how many positions had their M evaluated.  evals[i] = M evaluations of iteration i.
+struct LazyAcc {
+    const uint8_t *data; uint32_t N; const uint16_t *L; const uint32_t *holes; uint32_t *M; uint8_t *have; const LevelParams *lp; uint64_t *count;
+    uint32_t byte(uint32_t y) const { while (y >= N) { if (y < 65536) return 0; y -= 32768; } return data[y]; }
+    uint32_t link(uint32_t y) const { return y + 4 <= N ? L[y] : 0; }
+    bool inserted(uint32_t y) const { return !((holes[y >> 5] >> (y & 31)) & 1u); }
+    Match mlook(uint32_t x) const
+    {
+        if (!have[x]) {
+            Match m = (x + kMSafe <= N) ? lm_walk(*this, x, 0xffffffffu, *lp) : Match{0, 0};
+            M[x] = m.len ? ((m.len << 16) | (x - m.start)) : 0;
+            have[x] = 1;
+            (*count)++;
+        }
+        const uint32_t v = M[x];
+        return Match{v >> 16, x - (v & 0xffff)};
+    }
+};
+
+extern "C" int hm_parse_lazy(const uint8_t *data, uint32_t N, int level, uint32_t C, SymOut *out, uint32_t cap, uint32_t *nsyms, uint64_t *evals,
+                             uint32_t evals_cap, uint32_t *iters_out)
+{
+    LevelParams lp = level_params(level);
+    std::vector<uint16_t> L;
+    build_links(data, N, L);
+    std::vector<uint32_t> holes((N >> 5) + 2, 0), newholes((N >> 5) + 2, 0), M(N + 1024, 0), nxt(N + 1, 0);
+    std::vector<uint8_t> have(N + 1024, 0), hnxt(N + 1, 0);
+    uint64_t count = 0;
+    LazyAcc a{data, N, L.data(), holes.data(), M.data(), have.data(), &lp, &count};
+    const uint32_t tail_start = N > 2 * kTailZone ? N - kTailZone : 0;
+    auto step = [&](uint32_t p) -> uint32_t {
+        if (!hnxt[p]) { uint32_t ns; nxt[p] = macro_step(a, p, lp, tail_start, [](Sym) {}, &ns); hnxt[p] = 1; }
+        return nxt[p];
+    };
+    std::vector<uint32_t> path;
+    uint32_t iters = 0, tail_entry = 0;
+    for (;;) {
+        std::fill(have.begin(), have.end(), 0);
+        std::fill(hnxt.begin(), hnxt.end(), 0);
+        count = 0;
+        // round 1: one walker per chunk (on the GPU: one lane each, all chunks at once)
+        for (uint32_t c0 = 0; c0 < tail_start; c0 += C) {
+            uint32_t p = c0;
+            while (p < tail_start && p < c0 + C) p = step(p);
+        }
+        // round 2: the true path; where it is off the trails it is evaluated on demand (<= 20 steps per chunk boundary on the corpus)
+        path.clear();
+        uint32_t p = 0;
+        while (p < tail_start) {
+            const uint32_t np = step(p);
+            if (np >= tail_start) break;
+            path.push_back(p);
+            p = np;
+        }
+        tail_entry = p;
+        if (iters < evals_cap) evals[iters] = count;
+        iters++;
+        std::fill(newholes.begin(), newholes.end(), 0);
+        for (uint32_t q : path) {
+            uint32_t ns;
+            macro_step(a, q, lp, tail_start, [&](Sym s) {
+                if (s.dist && (uint32_t)s.lc + 3 > 16 * lp.lazy)
+                    for (uint32_t y = s.pos + 1; y + 1 < s.pos + s.lc + 3; y++) newholes[y >> 5] |= 1u << (y & 31);
+            }, &ns);
+        }
+        if (newholes == holes) break;
+        holes = newholes;
+        a.holes = holes.data();
+        if (iters > N / 257u + 64u) return -1;
+    }
+    uint32_t n = 0;
+    for (uint32_t q : path) {
+        uint32_t ns;
+        macro_step(a, q, lp, tail_start, [&](Sym s) { if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc}; n++; }, &ns);
+    }
+    std::vector<uint32_t> ins(64 + (N - tail_entry) / 32 + 2, 0);
+    serial_medium(a, N, tail_entry, ins.data(), (uint32_t)ins.size(), lp, [&](Sym s, uint32_t) {
+        if (n < cap) out[n] = SymOut{s.pos, s.dist, s.lc};
+        n++;
+    });
+    *nsyms = n;
+    *iters_out = iters;
+    return 0;
+}

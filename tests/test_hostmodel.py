@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from corpus import silesia_member, synthetic_mix
+from corpus import periodic_mutated, silesia_member, synthetic_mix
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _H = None
@@ -209,6 +209,22 @@ def test_lazy_levels_and_rle_with_small_windows():
             assert H().hm_parse_rle_w(data, n, wbits, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na)) == 0
             assert H().hm_oracle_trace_ws(data, n, 6, wbits, 8, 3, b.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(nb)) == 0
             assert na.value == nb.value and (a[: na.value * 2] == b[: nb.value * 2]).all(), (name, wbits, "rle")
+
+
+def test_lazy_formulation_is_exact():
+    """The next design: M and the macro steps evaluated on demand along one walker per 256-position chunk and along
+    the true path, the hole fixed point on top -- the same symbols as the oracle, with M evaluated at a fraction of the positions."""
+    cases = [(silesia_member(1)[:300000], 6), (silesia_member(9)[:250000], 6), (silesia_member(10)[:300000], 5), (silesia_member(0)[:200000], 3),
+             (periodic_mutated(150000, 37, 40, 4), 6)]
+    for data, level in cases:
+        n = len(data)
+        a = np.zeros((n + 16) * 2, dtype=np.uint32); b = np.zeros((n + 16) * 2, dtype=np.uint32)
+        na, nb, it = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        ev = (ctypes.c_uint64 * 64)()
+        assert H().hm_parse_lazy(data, n, level, 256, a.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(na), ev, 64, ctypes.byref(it)) == 0
+        assert H().hm_oracle_trace(data, n, level, b.ctypes.data_as(ctypes.c_void_p), n + 16, ctypes.byref(nb)) == 0
+        assert na.value == nb.value and (a[: na.value * 2] == b[: nb.value * 2]).all(), level
+        assert ev[0] < 0.8 * n  # and far fewer than one evaluation per position
 
 
 def test_parallel_formulation_with_small_windows():
